@@ -1,0 +1,123 @@
+"""ctypes binding of libaerial_gym_b200.so (the C ABI in include/aerial_gym_b200.h).
+
+Fails loudly: no library -> ImportError-like RuntimeError naming the build command;
+nothing here falls back to torch or CPU code."""
+import ctypes as C
+import os
+
+from . import _build
+
+AGX_MAX_MOTORS = 8
+
+# controller ids (AGX_CTRL_*)
+CTRL_NONE, CTRL_ATTITUDE, CTRL_POSITION, CTRL_VELOCITY = 0, 1, 2, 3
+CTRL_ACCELERATION, CTRL_RATES, CTRL_FULLY_ACTUATED, CTRL_VELOCITY_STEERING = 4, 5, 6, 7
+# flags (AGX_F_*)
+F_USE_RPS, F_MOTOR_RK4, F_DISCRETE_MIX, F_GYROSCOPIC = 0x1, 0x2, 0x4, 0x8
+F_RANDOMIZE_GAINS, F_DEVICE_RNG_RESET, F_STRICT_STALE_OBS = 0x10, 0x20, 0x40
+
+f32 = C.c_float
+fp = C.c_void_p  # device pointers travel as integers
+
+
+class AgxHp1Config(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_motors", C.c_int32), ("controller", C.c_int32),
+        ("num_actions", C.c_int32), ("physics_steps", C.c_int32), ("flags", C.c_int32),
+        ("episode_len_steps", C.c_int32), ("env_id_offset", C.c_int32),
+        ("seed", C.c_uint64),
+        ("dt", f32), ("gravity", f32 * 3), ("mass", f32),
+        ("inertia", f32 * 9), ("inertia_inv", f32 * 9),
+        ("alloc_pinv", f32 * (AGX_MAX_MOTORS * 6)), ("wrench_map", f32 * (6 * AGX_MAX_MOTORS)),
+        ("com", f32 * 3),
+        ("min_thrust", f32), ("max_thrust", f32), ("max_thrust_rate", f32), ("max_yaw_rate", f32),
+        ("drag_lin1", f32 * 3), ("drag_lin2", f32 * 3), ("drag_ang1", f32 * 3), ("drag_ang2", f32 * 3),
+        ("linear_damping", f32), ("angular_damping", f32),
+        ("max_linear_velocity", f32), ("max_angular_velocity", f32),
+        ("K_pos", f32 * 3), ("K_vel", f32 * 3), ("K_rot", f32 * 3), ("K_angvel", f32 * 3),
+        ("tau_inc", f32), ("tau_dec", f32), ("k_thrust", f32), ("crash_distance", f32),
+        ("min_init_state", f32 * 13), ("max_init_state", f32 * 13),
+        ("bounds_lo_min", f32 * 3), ("bounds_lo_max", f32 * 3),
+        ("bounds_hi_min", f32 * 3), ("bounds_hi_max", f32 * 3),
+        ("tau_inc_range", f32 * 2), ("tau_dec_range", f32 * 2), ("k_thrust_range", f32 * 2),
+        ("K_pos_min", f32 * 3), ("K_pos_max", f32 * 3), ("K_vel_min", f32 * 3), ("K_vel_max", f32 * 3),
+        ("K_rot_min", f32 * 3), ("K_rot_max", f32 * 3), ("K_angvel_min", f32 * 3), ("K_angvel_max", f32 * 3),
+    ]
+
+
+_HP1_BUF_FIELDS = [
+    "root_state", "motor_thrust", "sim_steps", "actions", "disturbance", "target_position",
+    "tau_inc", "tau_dec", "k_thrust", "K_pos", "K_vel", "K_rot", "K_angvel", "bounds_min", "bounds_max",
+    "euler", "vehicle_orientation", "vehicle_linvel", "body_linvel", "body_angvel", "body_wrench",
+    "obs", "reward", "terminations", "truncations", "reset_mask", "any_reset", "episode_count",
+]
+
+
+class AgxHp1Buffers(C.Structure):
+    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS]
+
+
+_HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",
+                    "tau_inc", "tau_dec", "thrust", "k_thrust"]
+
+
+class AgxHp1ResetDraws(C.Structure):
+    _fields_ = [(n, fp) for n in _HP1_DRAW_FIELDS]
+
+
+class AgxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (once) and type the library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise AgxError(
+            f"{path} not found: build it with `python -m aerial_gym_simulator_b200._build` "
+            "(nvcc, sm_100a).  There is no CPU / torch fallback."
+        )
+    lib = C.CDLL(path)
+    lib.agx_abi_version.restype = C.c_int
+    lib.agx_last_error.restype = C.c_char_p
+    lib.agx_sizeof.restype = C.c_uint64
+    lib.agx_sizeof.argtypes = [C.c_int]
+    for name, args in {
+        "agx_hp1_physics_step": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_hp1_position_task_step": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_hp1_reset": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p,
+                          C.POINTER(AgxHp1ResetDraws), C.c_void_p],
+        "agx_hp1_refresh": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_int, C.c_void_p],
+    }.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
+            or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):
+        raise AgxError("ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise AgxError(f"{what} failed ({rc}): {load().agx_last_error().decode()}")
+
+
+def declared_symbols():
+    """extern "C" function names declared in include/aerial_gym_b200.h (for the export test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_build.PKG), "include", "aerial_gym_b200.h")
+    txt = open(hdr).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(agx_[a-z0-9_]+)\s*\(", txt)))

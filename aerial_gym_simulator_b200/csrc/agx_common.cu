@@ -1,0 +1,39 @@
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/aerial_gym_b200.h"
+#include "agx_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int agx_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int agx_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return AGX_OK;
+    return agx_set_error(AGX_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int agx_check_launch(const char* what) { return agx_check_cuda(cudaPeekAtLastError(), what); }
+
+extern "C" {
+int agx_abi_version(void) { return AGX_ABI_VERSION; }
+const char* agx_last_error(void) { return g_err; }
+uint64_t agx_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(AgxHp1Config);
+        case 1: return sizeof(AgxHp1Buffers);
+        case 2: return sizeof(AgxHp1ResetDraws);
+#ifdef AGX_HAVE_HP2
+        case 3: return sizeof(AgxHp2Scene);
+        case 4: return sizeof(AgxHp2Sensor);
+#endif
+        default: return 0;
+    }
+}
+}

@@ -1,0 +1,786 @@
+// HP1: fused multirotor step for sm_100a.
+//
+//   update_states -> Lee controller -> allocation -> motor model -> drag/disturbance ->
+//   rigid-body integrate  (x physics_steps)  [-> position-task reward / flags / reset / obs]
+//
+// One thread per environment, one warp per 32-env tile.  The [N,13] AoS root-state rows the
+// reference API exposes (IGE_env_manager.py:301-311, views must stay views) are moved with
+// coalesced 16-byte loads of the contiguous 32x13 tile into shared memory and read back
+// conflict-free (row stride 13 is coprime with the 32 banks); [N,4]/[N,8] arrays are one or
+// two float4 per thread.  No tensor-core path: per-env work is <= 8x6 contractions.
+//
+// Reference functions restated here are cited inline (paths relative to aerial_gym/).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/aerial_gym_b200.h"
+#include "agx_common.cuh"
+#include "agx_math.cuh"
+
+using namespace agx;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 2;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kTileFloats = 32 * 13;
+
+struct EnvState {
+    V3 x;
+    Q4 q;
+    V3 v;
+    V3 w;
+};
+struct Derived {
+    V3 euler;
+    Q4 qveh;
+    V3 vveh;
+    V3 vb;
+    V3 wb;
+};
+struct Gains {
+    V3 kp, kv, kr, kw;
+};
+
+// ---- tile IO ---------------------------------------------------------------------------
+// rows [env0, env0+n_valid) of a dense [N,13] array -> this lane's row in r[13]
+__device__ __forceinline__ void load_rows13(const float* __restrict__ base, int env0, int n_valid,
+                                            float* tile, int lane, float r[13], bool vec_ok) {
+    const float* src = base + (size_t)env0 * 13;
+    if (n_valid == 32 && vec_ok) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* t4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = lane + 32 * i;
+            if (idx < kTileFloats / 4) t4[idx] = s4[idx];
+        }
+    } else {
+        int n = n_valid * 13;
+        for (int i = lane; i < n; i += 32) tile[i] = src[i];
+    }
+    __syncwarp();
+    if (lane < n_valid) {
+#pragma unroll
+        for (int j = 0; j < 13; ++j) r[j] = tile[lane * 13 + j];
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void store_rows13(float* __restrict__ base, int env0, int n_valid, float* tile,
+                                             int lane, const float r[13], bool vec_ok) {
+    if (lane < n_valid) {
+#pragma unroll
+        for (int j = 0; j < 13; ++j) tile[lane * 13 + j] = r[j];
+    }
+    __syncwarp();
+    float* dst = base + (size_t)env0 * 13;
+    if (n_valid == 32 && vec_ok) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        const float4* t4 = reinterpret_cast<const float4*>(tile);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = lane + 32 * i;
+            if (idx < kTileFloats / 4) d4[idx] = t4[idx];
+        }
+    } else {
+        int n = n_valid * 13;
+        for (int i = lane; i < n; i += 32) dst[i] = tile[i];
+    }
+    __syncwarp();
+}
+template <int M>
+__device__ __forceinline__ void load_m(const float* __restrict__ p, int env, float out[M]) {
+    if constexpr (M % 4 == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(p + (size_t)env * M);
+#pragma unroll
+        for (int i = 0; i < M / 4; ++i) {
+            float4 v = p4[i];
+            out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) out[i] = p[(size_t)env * M + i];
+    }
+}
+template <int M>
+__device__ __forceinline__ void store_m(float* __restrict__ p, int env, const float in[M]) {
+    if constexpr (M % 4 == 0) {
+        float4* p4 = reinterpret_cast<float4*>(p + (size_t)env * M);
+#pragma unroll
+        for (int i = 0; i < M / 4; ++i) p4[i] = make_float4(in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[(size_t)env * M + i] = in[i];
+    }
+}
+__device__ __forceinline__ void st3(float* p, int env, V3 v) {
+    p[(size_t)env * 3 + 0] = v.x; p[(size_t)env * 3 + 1] = v.y; p[(size_t)env * 3 + 2] = v.z;
+}
+__device__ __forceinline__ V3 ld3c(const float* c) { return V3{c[0], c[1], c[2]}; }
+
+__device__ __forceinline__ EnvState unpack(const float r[13]) {
+    EnvState s;
+    s.x = V3{r[0], r[1], r[2]};
+    s.q = Q4{r[3], r[4], r[5], r[6]};
+    s.v = V3{r[7], r[8], r[9]};
+    s.w = V3{r[10], r[11], r[12]};
+    return s;
+}
+__device__ __forceinline__ void pack(const EnvState& s, float r[13]) {
+    r[0] = s.x.x; r[1] = s.x.y; r[2] = s.x.z;
+    r[3] = s.q.x; r[4] = s.q.y; r[5] = s.q.z; r[6] = s.q.w;
+    r[7] = s.v.x; r[8] = s.v.y; r[9] = s.v.z;
+    r[10] = s.w.x; r[11] = s.w.y; r[12] = s.w.z;
+}
+
+// ---- a1: BaseMultirotor.update_states   robots/base_multirotor.py:287-294 ----------------
+__device__ __forceinline__ Derived update_states(const EnvState& s) {
+    Derived d;
+    V3 e = euler_xyz_0_2pi(s.q);
+    d.euler = V3{ssa_0_2pi(e.x), ssa_0_2pi(e.y), ssa_0_2pi(e.z)};
+    d.qveh = quat_from_yaw(e.z);  // vehicle_frame_quat_from_quat uses the [0,2pi) yaw
+    d.vveh = quat_rotate_inverse(d.qveh, s.v);
+    d.vb = quat_rotate_inverse(s.q, s.v);
+    d.wb = quat_rotate_inverse(s.q, s.w);
+    return d;
+}
+
+// ---- a2: compute_acceleration           control/controllers/base_lee_controller.py:120-134
+__device__ __forceinline__ V3 compute_acceleration(const EnvState& s, const Derived& d, const Gains& g, V3 sp_pos,
+                                                   V3 sp_vel) {
+    V3 pos_err = sp_pos - s.x;
+    V3 vel_err = quat_rotate(d.qveh, sp_vel) - s.v;
+    return g.kp * pos_err + g.kv * vel_err;
+}
+// ---- a5: euler_rates_to_body_rates      base_lee_controller.py:200-215 (yaw-rate only column
+// plus the generic roll/pitch entries the reference writes) --------------------------------
+__device__ __forceinline__ V3 euler_rates_to_body_rates(V3 euler, V3 rates) {
+    float sp, cp, sr, cr;
+    sincosf(euler.y, &sp, &cp);
+    sincosf(euler.x, &sr, &cr);
+    // T = [[1,0,-sp],[0,cr,sr*cp],[0,-sr,cr*cp]]
+    return V3{rates.x + (-sp) * rates.z, cr * rates.y + (sr * cp) * rates.z, (-sr) * rates.y + (cr * cp) * rates.z};
+}
+// ---- a6: compute_body_torque            base_lee_controller.py:136-154 -------------------
+__device__ __forceinline__ V3 compute_body_torque(const AgxHp1Config& cfg, const EnvState& s, const Derived& d,
+                                                  const Gains& g, Q4 q_des, V3 w_des) {
+    w_des.z = fminf(fmaxf(w_des.z, -cfg.max_yaw_rate), cfg.max_yaw_rate);
+    Q4 qe = quat_mul(quat_conj(s.q), q_des);
+    M33 R = quat_to_matrix(qe);
+    // 0.5 * vee(R^T - R): [-S12, S02, -S01], S = R^T - R
+    V3 rot_err{0.5f * -(R.m[7] - R.m[5]), 0.5f * (R.m[6] - R.m[2]), 0.5f * -(R.m[3] - R.m[1])};
+    V3 angvel_err = d.wb - quat_rotate(qe, w_des);
+    const float* J = cfg.inertia;
+    V3 W = d.wb;
+    V3 JW{J[0] * W.x + J[1] * W.y + J[2] * W.z, J[3] * W.x + J[4] * W.y + J[5] * W.z,
+          J[6] * W.x + J[7] * W.y + J[8] * W.z};
+    V3 ff = cross(W, JW);
+    return neg(g.kr * rot_err) - g.kw * angvel_err + ff;
+}
+// ---- a3: calculate_desired_orientation_for_position_velocity_control  :173-194 ----------
+__device__ __forceinline__ Q4 desired_orientation_pos_vel(V3 f, float yaw) {
+    float fn = norm3(f);
+    V3 b3{f.x / fn, f.y / fn, f.z / fn};
+    float sy, cy;
+    sincosf(yaw, &sy, &cy);
+    V3 b2 = cross(b3, V3{cy, sy, 0.0f});
+    float n2 = norm3(b2);
+    b2 = V3{b2.x / n2, b2.y / n2, b2.z / n2};
+    V3 b1 = cross(b2, b3);
+    return matrix_cols_to_quat(b1, b2, b3);
+}
+// ---- a4: calculate_desired_orientation_from_forces_and_yaw  :157-169 --------------------
+__device__ __forceinline__ Q4 desired_orientation_forces_yaw(V3 f, float yaw) {
+    float pitch = atan2f(f.x, f.z);
+    float roll = atan2f(-f.y, sqrtf(f.z * f.z + f.x * f.x));
+    return quat_from_euler(roll, pitch, yaw);
+}
+
+// ---- a7: controller dispatch -> wrench[6] (or motor refs for AGX_CTRL_NONE) --------------
+__device__ __forceinline__ void controller_wrench(const AgxHp1Config& cfg, const EnvState& s, const Derived& d,
+                                                  const Gains& g, const float* act, float wr[6]) {
+    const V3 grav = ld3c(cfg.gravity);
+    const float m = cfg.mass;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) wr[i] = 0.0f;
+    const int c = cfg.controller;
+    const V3 zero3{0.0f, 0.0f, 0.0f};
+    if (c == AGX_CTRL_ATTITUDE) {  // controllers/attitude_control.py:16-43
+        wr[2] = (act[0] + 1.0f) * m * norm3(grav);
+        V3 w_des = euler_rates_to_body_rates(d.euler, V3{0.0f, 0.0f, act[3]});
+        Q4 q_des = quat_from_euler(act[1], act[2], d.euler.z);
+        V3 t = compute_body_torque(cfg, s, d, g, q_des, w_des);
+        wr[3] = t.x; wr[4] = t.y; wr[5] = t.z;
+        return;
+    }
+    if (c == AGX_CTRL_RATES) {  // controllers/rates_control.py:23-26 (intent; reference line raises)
+        wr[2] = (act[0] - grav.z) * m;
+        V3 t = compute_body_torque(cfg, s, d, g, s.q, V3{act[1], act[2], act[3]});
+        wr[3] = t.x; wr[4] = t.y; wr[5] = t.z;
+        return;
+    }
+    if (c == AGX_CTRL_FULLY_ACTUATED) {  // controllers/fully_actuated_control.py:14-32
+        float qn = fmaxf(sqrtf(act[3] * act[3] + act[4] * act[4] + act[5] * act[5] + act[6] * act[6]), 1e-9f);
+        Q4 q_des{act[3] / qn, act[4] / qn, act[5] / qn, act[6] / qn};
+        V3 accel = compute_acceleration(s, d, g, V3{act[0], act[1], act[2]}, zero3);
+        V3 forces = (accel - grav) * m;
+        V3 fb = quat_rotate_inverse(s.q, forces);
+        wr[0] = fb.x; wr[1] = fb.y; wr[2] = fb.z;
+        V3 t = compute_body_torque(cfg, s, d, g, q_des, zero3);
+        wr[3] = t.x; wr[4] = t.y; wr[5] = t.z;
+        return;
+    }
+    // thrust-vectoring family: position / velocity / velocity-steering / acceleration
+    V3 accel;
+    if (c == AGX_CTRL_POSITION) accel = compute_acceleration(s, d, g, V3{act[0], act[1], act[2]}, zero3);
+    else if (c == AGX_CTRL_ACCELERATION) accel = V3{act[0], act[1], act[2]};
+    else accel = compute_acceleration(s, d, g, s.x, V3{act[0], act[1], act[2]});
+    V3 forces = (accel - grav) * m;
+    M33 R = quat_to_matrix(s.q);
+    wr[2] = forces.x * R.m[2] + forces.y * R.m[5] + forces.z * R.m[8];
+    Q4 q_des;
+    V3 w_des = zero3;
+    if (c == AGX_CTRL_POSITION || c == AGX_CTRL_VELOCITY_STEERING) {
+        q_des = desired_orientation_pos_vel(forces, act[3]);
+    } else if (c == AGX_CTRL_VELOCITY) {
+        q_des = desired_orientation_pos_vel(forces, d.euler.z);
+        w_des = euler_rates_to_body_rates(d.euler, V3{0.0f, 0.0f, act[3]});
+    } else {  // acceleration
+        q_des = desired_orientation_forces_yaw(forces, d.euler.z);
+        w_des = euler_rates_to_body_rates(d.euler, V3{0.0f, 0.0f, act[3]});
+    }
+    V3 t = compute_body_torque(cfg, s, d, g, q_des, w_des);
+    wr[3] = t.x; wr[4] = t.y; wr[5] = t.z;
+}
+
+// ---- a9: MotorModel.update_motor_thrusts   control/motor_model.py:88-251 -----------------
+__device__ __forceinline__ float motor_rate(float err, float mix, float max_rate) {
+    return fmaxf(fminf(mix * err, max_rate), -max_rate);  // tensor_clamp, motor_model.py:160-162
+}
+__device__ __forceinline__ float motor_rk4(float ref, float cur, float mix, float max_rate, float dt) {
+    float k1 = motor_rate(ref - cur, mix, max_rate);
+    float k2 = motor_rate(ref - (cur + 0.5f * dt * k1), mix, max_rate);
+    float k3 = motor_rate(ref - (cur + 0.5f * dt * k2), mix, max_rate);
+    float k4 = motor_rate(ref - (cur + dt * k3), mix, max_rate);
+    return (dt / 6.0f) * (k1 + 2.0f * k2 + 2.0f * k3 + k4);
+}
+__device__ __forceinline__ float motor_update(const AgxHp1Config& cfg, float cur, float ref_in, float tau_inc,
+                                              float tau_dec, float k) {
+    const float dt = cfg.dt;
+    float ref = fminf(fmaxf(ref_in, cfg.min_thrust), cfg.max_thrust);
+    float err = ref - cur;
+    bool decreasing = (cur > 0.0f && err < 0.0f) || (cur < 0.0f && err > 0.0f);  // sign(f)*sign(err) < 0
+    float tau = decreasing ? tau_dec : tau_inc;
+    float mix = (cfg.flags & AGX_F_DISCRETE_MIX) ? 1.0f / (dt + tau) : 1.0f / tau;
+    const bool rk4 = cfg.flags & AGX_F_MOTOR_RK4;
+    if (cfg.flags & AGX_F_USE_RPS) {
+        float rpm = sqrtf(cur / k);
+        float rpm_ref = sqrtf(ref / k);
+        if (rk4) rpm += motor_rk4(rpm_ref, rpm, mix, cfg.max_thrust_rate, dt);
+        else rpm += motor_rate(rpm_ref - rpm, mix, cfg.max_thrust_rate) * dt;
+        return k * (rpm * rpm);
+    }
+    if (rk4) return cur + motor_rk4(ref, cur, mix, cfg.max_thrust_rate, dt);
+    return cur + motor_rate(err, mix, cfg.max_thrust_rate) * dt;
+}
+
+// ---- a13: rigid-body integrator -- OUR SPEC (DESIGN.md "Integrator spec"; oracle
+// rigid_body_integrate).  Replaces gym.simulate (env_manager/IGE_env_manager.py:477). --------
+__device__ __forceinline__ void integrate(const AgxHp1Config& cfg, EnvState& s, V3 F, V3 T) {
+    const float dt = cfg.dt;
+    V3 a = quat_rotate(s.q, F) * (1.0f / cfg.mass) + ld3c(cfg.gravity);
+    V3 v = (s.v + a * dt) * fmaxf(0.0f, 1.0f - dt * cfg.linear_damping);
+    float vn = norm3(v);
+    if (vn > cfg.max_linear_velocity) v = v * (cfg.max_linear_velocity / vn);
+    V3 W = quat_rotate_inverse(s.q, s.w);
+    const float* J = cfg.inertia;
+    const float* Ji = cfg.inertia_inv;
+    V3 rhs = T;
+    if (cfg.flags & AGX_F_GYROSCOPIC) {
+        V3 JW{J[0] * W.x + J[1] * W.y + J[2] * W.z, J[3] * W.x + J[4] * W.y + J[5] * W.z,
+              J[6] * W.x + J[7] * W.y + J[8] * W.z};
+        rhs = T - cross(W, JW);
+    }
+    V3 al{Ji[0] * rhs.x + Ji[1] * rhs.y + Ji[2] * rhs.z, Ji[3] * rhs.x + Ji[4] * rhs.y + Ji[5] * rhs.z,
+          Ji[6] * rhs.x + Ji[7] * rhs.y + Ji[8] * rhs.z};
+    V3 Wn = W + al * dt;
+    V3 w = quat_rotate(s.q, Wn) * fmaxf(0.0f, 1.0f - dt * cfg.angular_damping);
+    float wn = norm3(w);
+    if (wn > cfg.max_angular_velocity) {
+        w = w * (cfg.max_angular_velocity / wn);
+        wn = norm3(w);
+    }
+    s.x = s.x + v * dt;
+    float sh, ch;
+    sincosf(0.5f * dt * wn, &sh, &ch);
+    float so = (wn > 0.0f) ? sh / wn : 0.0f;
+    Q4 dq{w.x * so, w.y * so, w.z * so, ch};
+    Q4 qn = quat_mul(dq, s.q);
+    float inv = 1.0f / sqrtf(qn.x * qn.x + qn.y * qn.y + qn.z * qn.z + qn.w * qn.w);
+    s.q = Q4{qn.x * inv, qn.y * inv, qn.z * inv, qn.w * inv};
+    s.v = v;
+    s.w = w;
+}
+
+// ---- a15: reset arithmetic (uniforms in registers) ----------------------------------------
+template <int M>
+struct EnvParams {
+    float thrust[M], tau_inc[M], tau_dec[M], k[M];
+    Gains g;
+    V3 bmin, bmax;
+};
+__device__ __forceinline__ float lerp_u(float lo, float hi, float u) { return (hi - lo) * u + lo; }  // math.py:51-54
+
+template <int M>
+__device__ __forceinline__ void apply_reset(const AgxHp1Config& cfg, const float us[13], const float ubl[3],
+                                            const float ubh[3], const float ug[12], const float um[4 * M],
+                                            EnvState& s, EnvParams<M>& p) {
+    // IGE_env_manager.py:513-519
+    p.bmin = V3{lerp_u(cfg.bounds_lo_min[0], cfg.bounds_lo_max[0], ubl[0]), lerp_u(cfg.bounds_lo_min[1], cfg.bounds_lo_max[1], ubl[1]),
+                lerp_u(cfg.bounds_lo_min[2], cfg.bounds_lo_max[2], ubl[2])};
+    p.bmax = V3{lerp_u(cfg.bounds_hi_min[0], cfg.bounds_hi_max[0], ubh[0]), lerp_u(cfg.bounds_hi_min[1], cfg.bounds_hi_max[1], ubh[1]),
+                lerp_u(cfg.bounds_hi_min[2], cfg.bounds_hi_max[2], ubh[2])};
+    // base_multirotor.py:177-199
+    float rs[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) rs[j] = lerp_u(cfg.min_init_state[j], cfg.max_init_state[j], us[j]);
+    s.x = V3{p.bmin.x + (p.bmax.x - p.bmin.x) * rs[0], p.bmin.y + (p.bmax.y - p.bmin.y) * rs[1],
+             p.bmin.z + (p.bmax.z - p.bmin.z) * rs[2]};
+    s.q = quat_from_euler(rs[3], rs[4], rs[5]);
+    s.v = V3{rs[7], rs[8], rs[9]};
+    s.w = V3{rs[10], rs[11], rs[12]};
+    if (cfg.flags & AGX_F_RANDOMIZE_GAINS) {  // base_lee_controller.py:101-118
+        p.g.kp = V3{lerp_u(cfg.K_pos_min[0], cfg.K_pos_max[0], ug[0]), lerp_u(cfg.K_pos_min[1], cfg.K_pos_max[1], ug[1]), lerp_u(cfg.K_pos_min[2], cfg.K_pos_max[2], ug[2])};
+        p.g.kv = V3{lerp_u(cfg.K_vel_min[0], cfg.K_vel_max[0], ug[3]), lerp_u(cfg.K_vel_min[1], cfg.K_vel_max[1], ug[4]), lerp_u(cfg.K_vel_min[2], cfg.K_vel_max[2], ug[5])};
+        p.g.kr = V3{lerp_u(cfg.K_rot_min[0], cfg.K_rot_max[0], ug[6]), lerp_u(cfg.K_rot_min[1], cfg.K_rot_max[1], ug[7]), lerp_u(cfg.K_rot_min[2], cfg.K_rot_max[2], ug[8])};
+        p.g.kw = V3{lerp_u(cfg.K_angvel_min[0], cfg.K_angvel_max[0], ug[9]), lerp_u(cfg.K_angvel_min[1], cfg.K_angvel_max[1], ug[10]), lerp_u(cfg.K_angvel_min[2], cfg.K_angvel_max[2], ug[11])};
+    }
+    // motor_model.py:140-154
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        p.tau_inc[i] = lerp_u(cfg.tau_inc_range[0], cfg.tau_inc_range[1], um[4 * i + 0]);
+        p.tau_dec[i] = lerp_u(cfg.tau_dec_range[0], cfg.tau_dec_range[1], um[4 * i + 1]);
+        p.thrust[i] = lerp_u(cfg.min_thrust, cfg.max_thrust, um[4 * i + 2]);
+        if (cfg.flags & AGX_F_USE_RPS) p.k[i] = lerp_u(cfg.k_thrust_range[0], cfg.k_thrust_range[1], um[4 * i + 3]);
+    }
+}
+
+// device-RNG draw layout (oracle/philox.py restates it):
+//   block 0..2 -> state[0..11]; block 3 -> state[12], bounds_lo[0..2]; block 4 -> bounds_hi[0..2], -
+//   block 5..8 -> K_pos, K_vel, K_rot, K_angvel (xyz, -); block 9+i -> motor i: tau_inc, tau_dec, thrust, k
+template <int M>
+__device__ __noinline__ void device_rng_reset(const AgxHp1Config& cfg, uint32_t env_gid, uint32_t episode, EnvState& s,
+                                              EnvParams<M>& p) {
+    const uint32_t k0 = (uint32_t)(cfg.seed & 0xffffffffu), k1 = (uint32_t)(cfg.seed >> 32);
+    float us[13], ubl[3], ubh[3], ug[12], um[4 * M];
+    U4 b;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b = philox4x32_10(U4{env_gid, episode, (uint32_t)i, 0u}, k0, k1);
+        us[4 * i] = u01(b.x); us[4 * i + 1] = u01(b.y); us[4 * i + 2] = u01(b.z); us[4 * i + 3] = u01(b.w);
+    }
+    b = philox4x32_10(U4{env_gid, episode, 3u, 0u}, k0, k1);
+    us[12] = u01(b.x); ubl[0] = u01(b.y); ubl[1] = u01(b.z); ubl[2] = u01(b.w);
+    b = philox4x32_10(U4{env_gid, episode, 4u, 0u}, k0, k1);
+    ubh[0] = u01(b.x); ubh[1] = u01(b.y); ubh[2] = u01(b.z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        b = philox4x32_10(U4{env_gid, episode, (uint32_t)(5 + i), 0u}, k0, k1);
+        ug[3 * i] = u01(b.x); ug[3 * i + 1] = u01(b.y); ug[3 * i + 2] = u01(b.z);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        b = philox4x32_10(U4{env_gid, episode, (uint32_t)(9 + i), 0u}, k0, k1);
+        um[4 * i] = u01(b.x); um[4 * i + 1] = u01(b.y); um[4 * i + 2] = u01(b.z); um[4 * i + 3] = u01(b.w);
+    }
+    apply_reset<M>(cfg, us, ubl, ubh, ug, um, s, p);
+}
+
+template <int M>
+__device__ __forceinline__ void load_params(const AgxHp1Config& cfg, const AgxHp1Buffers& buf, int env, EnvParams<M>& p) {
+    load_m<M>(buf.motor_thrust, env, p.thrust);
+    if (buf.tau_inc) load_m<M>(buf.tau_inc, env, p.tau_inc);
+    else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p.tau_inc[i] = cfg.tau_inc;
+    }
+    if (buf.tau_dec) load_m<M>(buf.tau_dec, env, p.tau_dec);
+    else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p.tau_dec[i] = cfg.tau_dec;
+    }
+    if (buf.k_thrust) load_m<M>(buf.k_thrust, env, p.k);
+    else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p.k[i] = cfg.k_thrust;
+    }
+    p.g.kp = buf.K_pos ? ld3(buf.K_pos + (size_t)env * 3) : ld3c(cfg.K_pos);
+    p.g.kv = buf.K_vel ? ld3(buf.K_vel + (size_t)env * 3) : ld3c(cfg.K_vel);
+    p.g.kr = buf.K_rot ? ld3(buf.K_rot + (size_t)env * 3) : ld3c(cfg.K_rot);
+    p.g.kw = buf.K_angvel ? ld3(buf.K_angvel + (size_t)env * 3) : ld3c(cfg.K_angvel);
+}
+template <int M>
+__device__ __forceinline__ void store_reset_params(const AgxHp1Buffers& buf, int env, const EnvParams<M>& p) {
+    if (buf.tau_inc) store_m<M>(buf.tau_inc, env, p.tau_inc);
+    if (buf.tau_dec) store_m<M>(buf.tau_dec, env, p.tau_dec);
+    if (buf.k_thrust) store_m<M>(buf.k_thrust, env, p.k);
+    if (buf.K_pos) st3(buf.K_pos, env, p.g.kp);
+    if (buf.K_vel) st3(buf.K_vel, env, p.g.kv);
+    if (buf.K_rot) st3(buf.K_rot, env, p.g.kr);
+    if (buf.K_angvel) st3(buf.K_angvel, env, p.g.kw);
+    if (buf.bounds_min) st3(buf.bounds_min, env, p.bmin);
+    if (buf.bounds_max) st3(buf.bounds_max, env, p.bmax);
+}
+__device__ __forceinline__ void store_derived(const AgxHp1Buffers& buf, int env, const Derived& d) {
+    if (buf.euler) st3(buf.euler, env, d.euler);
+    if (buf.vehicle_orientation)
+        reinterpret_cast<float4*>(buf.vehicle_orientation)[env] = make_float4(d.qveh.x, d.qveh.y, d.qveh.z, d.qveh.w);
+    if (buf.vehicle_linvel) st3(buf.vehicle_linvel, env, d.vveh);
+    if (buf.body_linvel) st3(buf.body_linvel, env, d.vb);
+    if (buf.body_angvel) st3(buf.body_angvel, env, d.wb);
+}
+__device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3 tgt, float o[13]) {
+    // process_obs_for_task, task/position_setpoint_task/position_setpoint_task.py:194-203
+    o[0] = tgt.x - s.x.x; o[1] = tgt.y - s.x.y; o[2] = tgt.z - s.x.z;
+    o[3] = s.q.x; o[4] = s.q.y; o[5] = s.q.z; o[6] = s.q.w;
+    o[7] = d.vb.x; o[8] = d.vb.y; o[9] = d.vb.z;
+    o[10] = d.wb.x; o[11] = d.wb.y; o[12] = d.wb.z;
+}
+
+// =========================================================================================
+// main kernel
+// =========================================================================================
+template <int M, bool TASK>
+__global__ void __launch_bounds__(kThreads)
+hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tiles[warp];
+    const int N = cfg.num_envs;
+    const int n_tiles = (N + 31) >> 5;
+    const int A = cfg.num_actions;
+
+    for (int t = blockIdx.x * kWarpsPerBlock + warp; t < n_tiles; t += gridDim.x * kWarpsPerBlock) {
+        const int env0 = t << 5;
+        const int n_valid = min(32, N - env0);
+        const int env = env0 + lane;
+        const bool valid = lane < n_valid;
+
+        float r[13];
+        load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        EnvState s;
+        EnvParams<M> p;
+        Derived d;
+        float act[AGX_MAX_MOTORS];
+        float Fx = 0, Fy = 0, Fz = 0, Tx = 0, Ty = 0, Tz = 0;
+        if (valid) {
+            s = unpack(r);
+            load_params<M>(cfg, buf, env, p);
+            if (A == 4) {
+                float4 a4 = reinterpret_cast<const float4*>(buf.actions)[env];
+                act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+#pragma unroll
+                for (int i = 4; i < AGX_MAX_MOTORS; ++i) act[i] = 0.0f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = (i < A) ? buf.actions[(size_t)env * A + i] : 0.0f;
+            }
+            // clip_actions, robots/base_multirotor.py:207-211
+#pragma unroll
+            for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = fminf(fmaxf(act[i], -10.0f), 10.0f);
+
+            d = update_states(s);  // also covers physics_steps == 0
+            for (int step = 0; step < cfg.physics_steps; ++step) {
+                if (step > 0) d = update_states(s);
+                float ref[M];
+                if (cfg.controller == AGX_CTRL_NONE) {  // update_motor_thrusts_with_forces
+#pragma unroll
+                    for (int i = 0; i < M; ++i) ref[i] = act[i];
+                } else {
+                    float wr[6];
+                    controller_wrench(cfg, s, d, p.g, act, wr);
+                    // f_ref = pinv(A) w   control/control_allocation.py:87-89
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc += cfg.alloc_pinv[i * 6 + j] * wr[j];
+                        ref[i] = acc;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) p.thrust[i] = motor_update(cfg, p.thrust[i], ref[i], p.tau_inc[i], p.tau_dec[i], p.k[i]);
+                // thrust -> base-frame wrench about the COM (control_allocation.py:103-114 applied
+                // link-local, IGE_env_manager.py:444-449)
+                float w6[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) acc += cfg.wrench_map[j * AGX_MAX_MOTORS + i] * p.thrust[i];
+                    w6[j] = acc;
+                }
+                // simulate_drag, robots/base_multirotor.py:260-285 (body 0)
+                float vbn = norm3(d.vb);
+                V3 df = neg(ld3c(cfg.drag_lin1) * d.vb) + neg(ld3c(cfg.drag_lin2) * vbn * d.vb);
+                V3 wabs{fabsf(d.wb.x), fabsf(d.wb.y), fabsf(d.wb.z)};
+                V3 dtq = neg(ld3c(cfg.drag_ang1) * d.wb) + neg(ld3c(cfg.drag_ang2) * wabs * d.wb);
+                if (buf.disturbance) {  // apply_disturbance :213-234 (draws stay in torch)
+                    const float* dp = buf.disturbance + (size_t)env * 6;
+                    df = df + V3{dp[0], dp[1], dp[2]};
+                    dtq = dtq + V3{dp[3], dp[4], dp[5]};
+                }
+                V3 com = ld3c(cfg.com);
+                V3 F{w6[0] + df.x, w6[1] + df.y, w6[2] + df.z};
+                V3 T = V3{w6[3], w6[4], w6[5]} + dtq + cross(neg(com), df);
+                Fx = F.x; Fy = F.y; Fz = F.z; Tx = T.x; Ty = T.y; Tz = T.z;
+                integrate(cfg, s, F, T);
+            }
+        }
+
+        float o[13];
+        bool do_reset = false;
+        if constexpr (TASK) {
+            if (valid) {
+                // ---- a16 reward + flags: position_setpoint_task.py:205-282 (stale derived) -----
+                int steps = buf.sim_steps[env] + 1;  // env_manager.py:429
+                V3 tgt = buf.target_position ? ld3(buf.target_position + (size_t)env * 3) : V3{0, 0, 0};
+                V3 e = quat_apply(quat_conj(d.qveh), tgt - s.x);
+                float dist = norm3(e);
+                float pos_reward = 3.0f * expf(-8.0f * dist * dist) + 2.0f * expf(-4.0f * dist * dist);
+                float dist_reward = (20.0f - dist) / 40.0f;
+                V3 ups = quat_rotate(s.q, V3{0.0f, 0.0f, 1.0f});
+                float tilt = fabsf(1.0f - ups.z);
+                float up_reward = 0.2f / (0.1f + tilt * tilt);
+                float spin = norm3(d.wb);
+                float ang_reward = (1.0f / (1.0f + spin * spin)) * 3.0f;
+                float total = pos_reward + dist_reward + pos_reward * (up_reward + ang_reward);
+                bool crash = dist > cfg.crash_distance;
+                if (crash) total = -20.0f;
+                bool trunc = steps > cfg.episode_len_steps;  // :172-174
+                do_reset = crash || trunc;
+                buf.reward[env] = total;
+                buf.terminations[env] = crash ? 1 : 0;
+                buf.truncations[env] = trunc ? 1 : 0;
+                if (buf.reset_mask) buf.reset_mask[env] = do_reset ? 1 : 0;
+                bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
+                if (do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET)) {
+                    uint32_t ep = buf.episode_count[env];
+                    device_rng_reset<M>(cfg, (uint32_t)(cfg.env_id_offset + env), ep, s, p);
+                    buf.episode_count[env] = ep + 1u;
+                    store_reset_params<M>(buf, env, p);
+                    steps = 0;  // env_manager.py:301
+                    fresh = true;
+                }
+                buf.sim_steps[env] = steps;
+                if (fresh) d = update_states(s);
+                make_obs(s, d, tgt, o);
+            }
+            unsigned any = __ballot_sync(0xffffffffu, do_reset);
+            if (any && lane == 0) atomicOr(buf.any_reset, 1);
+        }
+        if (valid) {
+            store_m<M>(buf.motor_thrust, env, p.thrust);
+            store_derived(buf, env, d);
+            if (buf.body_wrench) {
+                float* bw = buf.body_wrench + (size_t)env * 6;
+                bw[0] = Fx; bw[1] = Fy; bw[2] = Fz; bw[3] = Tx; bw[4] = Ty; bw[5] = Tz;
+            }
+            pack(s, r);
+        }
+        store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        if constexpr (TASK) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+    }
+}
+
+// refresh pass: update_states for all envs (+ obs).  only_if_flag: gated on any_reset[0] and the
+// last-arriving block clears flag + arrival counter (so no memset node is needed per step).
+__global__ void __launch_bounds__(kThreads)
+hp1_refresh_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int only_if_flag,
+                   int vec_ok) {
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
+    __shared__ int s_flag;
+    if (only_if_flag) {
+        if (threadIdx.x == 0) {
+            int f = *reinterpret_cast<volatile int*>(buf.any_reset);
+            s_flag = f;
+            __threadfence();
+            int arrived = atomicAdd(buf.any_reset + 1, 1);
+            if (arrived == (int)gridDim.x - 1) {  // every block has read the flag
+                buf.any_reset[0] = 0;
+                buf.any_reset[1] = 0;
+            }
+        }
+        __syncthreads();
+        if (s_flag == 0) return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tiles[warp];
+    const int N = cfg.num_envs;
+    const int n_tiles = (N + 31) >> 5;
+    for (int t = blockIdx.x * kWarpsPerBlock + warp; t < n_tiles; t += gridDim.x * kWarpsPerBlock) {
+        const int env0 = t << 5;
+        const int n_valid = min(32, N - env0);
+        const int env = env0 + lane;
+        float r[13], o[13];
+        load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        if (lane < n_valid) {
+            EnvState s = unpack(r);
+            Derived d = update_states(s);
+            store_derived(buf, env, d);
+            if (buf.obs) {
+                V3 tgt = buf.target_position ? ld3(buf.target_position + (size_t)env * 3) : V3{0, 0, 0};
+                make_obs(s, d, tgt, o);
+            }
+        }
+        if (buf.obs) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+    }
+}
+
+// masked reset with caller-supplied uniforms (torch RNG, reference call order) or device RNG
+template <int M>
+__global__ void __launch_bounds__(kThreads)
+hp1_reset_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf,
+                 const uint8_t* __restrict__ mask, const __grid_constant__ AgxHp1ResetDraws dr, int have_draws) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= cfg.num_envs || !mask[env]) return;
+    EnvState s;
+    EnvParams<M> p;
+    load_params<M>(cfg, buf, env, p);
+    if (have_draws) {
+        float us[13], ubl[3], ubh[3], ug[12], um[4 * M];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) us[j] = dr.state[(size_t)env * 13 + j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            ubl[j] = dr.bounds_lo ? dr.bounds_lo[(size_t)env * 3 + j] : 0.0f;
+            ubh[j] = dr.bounds_hi ? dr.bounds_hi[(size_t)env * 3 + j] : 0.0f;
+            ug[j] = dr.K_pos ? dr.K_pos[(size_t)env * 3 + j] : 0.0f;
+            ug[3 + j] = dr.K_vel ? dr.K_vel[(size_t)env * 3 + j] : 0.0f;
+            ug[6 + j] = dr.K_rot ? dr.K_rot[(size_t)env * 3 + j] : 0.0f;
+            ug[9 + j] = dr.K_angvel ? dr.K_angvel[(size_t)env * 3 + j] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            um[4 * i + 0] = dr.tau_inc[(size_t)env * M + i];
+            um[4 * i + 1] = dr.tau_dec[(size_t)env * M + i];
+            um[4 * i + 2] = dr.thrust[(size_t)env * M + i];
+            um[4 * i + 3] = dr.k_thrust ? dr.k_thrust[(size_t)env * M + i] : 0.0f;
+        }
+        apply_reset<M>(cfg, us, ubl, ubh, ug, um, s, p);
+    } else {
+        uint32_t ep = buf.episode_count[env];
+        device_rng_reset<M>(cfg, (uint32_t)(cfg.env_id_offset + env), ep, s, p);
+        buf.episode_count[env] = ep + 1u;
+    }
+    float r[13];
+    pack(s, r);
+#pragma unroll
+    for (int j = 0; j < 13; ++j) buf.root_state[(size_t)env * 13 + j] = r[j];
+    store_m<M>(buf.motor_thrust, env, p.thrust);
+    store_reset_params<M>(buf, env, p);
+    if (buf.sim_steps) buf.sim_steps[env] = 0;  // env_manager.py:301
+}
+
+int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
+    if (!cfg || !buf) return agx_set_error(AGX_E_NULL, "cfg/buf is NULL");
+    if (cfg->num_envs < 0) return agx_set_error(AGX_E_INVALID, "num_envs < 0");
+    if (cfg->num_motors != 4 && cfg->num_motors != 8)
+        return agx_set_error(AGX_E_INVALID, "num_motors must be 4 or 8 (got %d)", cfg->num_motors);
+    if (cfg->controller < AGX_CTRL_NONE || cfg->controller > AGX_CTRL_VELOCITY_STEERING)
+        return agx_set_error(AGX_E_INVALID, "unknown controller id %d", cfg->controller);
+    int need = (cfg->controller == AGX_CTRL_NONE) ? cfg->num_motors : (cfg->controller == AGX_CTRL_FULLY_ACTUATED ? 7 : 4);
+    if (cfg->num_actions != need)
+        return agx_set_error(AGX_E_INVALID, "controller %d needs %d action columns (got %d)", cfg->controller, need, cfg->num_actions);
+    if (cfg->physics_steps < 0) return agx_set_error(AGX_E_INVALID, "physics_steps < 0");
+    if (!buf->root_state || !buf->motor_thrust || !buf->actions) return agx_set_error(AGX_E_NULL, "root_state/motor_thrust/actions is NULL");
+    if (((uintptr_t)buf->motor_thrust | (uintptr_t)buf->actions | (uintptr_t)buf->tau_inc | (uintptr_t)buf->tau_dec |
+         (uintptr_t)buf->k_thrust | (uintptr_t)buf->vehicle_orientation) & 15)
+        return agx_set_error(AGX_E_INVALID, "[N,M]/[N,4] arrays must be 16-byte aligned");
+    if (task) {
+        if (!buf->sim_steps || !buf->obs || !buf->reward || !buf->terminations || !buf->truncations || !buf->any_reset)
+            return agx_set_error(AGX_E_NULL, "task step needs sim_steps/obs/reward/terminations/truncations/any_reset");
+        if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && !buf->episode_count)
+            return agx_set_error(AGX_E_NULL, "device-RNG reset needs episode_count");
+    }
+    return AGX_OK;
+}
+
+inline int vec_ok_of(const AgxHp1Buffers* buf) {
+    return (((uintptr_t)buf->root_state | (uintptr_t)buf->obs) & 15) == 0;
+}
+inline int grid_for(int n_envs) {
+    int tiles = (n_envs + 31) / 32;
+    int blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return blocks < 1 ? 1 : blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream) {
+    int rc = validate(cfg, buf, false);
+    if (rc) return rc;
+    if (cfg->num_envs == 0) return AGX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
+    if (cfg->num_motors == 4) hp1_step_kernel<4, false><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    else hp1_step_kernel<8, false><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    return agx_check_launch("hp1_step_kernel");
+}
+
+int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream) {
+    int rc = validate(cfg, buf, true);
+    if (rc) return rc;
+    if (cfg->num_envs == 0) return AGX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
+    if (cfg->num_motors == 4) hp1_step_kernel<4, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    rc = agx_check_launch("hp1_step_kernel<task>");
+    if (rc) return rc;
+    // stale-derived-state quirk: if ANY env reset this step the reference refreshes
+    // the derived states of ALL envs before the observation is read (base_multirotor.py:204-205).
+    if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS)) {
+        hp1_refresh_kernel<<<g, kThreads, 0, st>>>(*cfg, *buf, 1, v);
+        rc = agx_check_launch("hp1_refresh_kernel");
+    }
+    return rc;
+}
+
+int agx_hp1_reset(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, const uint8_t* mask, const AgxHp1ResetDraws* draws,
+                  void* stream) {
+    if (!cfg || !buf || !mask) return agx_set_error(AGX_E_NULL, "cfg/buf/mask is NULL");
+    if (cfg->num_motors != 4 && cfg->num_motors != 8) return agx_set_error(AGX_E_INVALID, "num_motors must be 4 or 8");
+    if (!buf->root_state || !buf->motor_thrust) return agx_set_error(AGX_E_NULL, "root_state/motor_thrust is NULL");
+    if (draws) {
+        if (!draws->state || !draws->tau_inc || !draws->tau_dec || !draws->thrust)
+            return agx_set_error(AGX_E_NULL, "reset draws need state/tau_inc/tau_dec/thrust");
+        if ((cfg->flags & AGX_F_USE_RPS) && !draws->k_thrust) return agx_set_error(AGX_E_NULL, "use_rps reset needs k_thrust draws");
+        if ((cfg->flags & AGX_F_RANDOMIZE_GAINS) && !(draws->K_pos && draws->K_vel && draws->K_rot && draws->K_angvel))
+            return agx_set_error(AGX_E_NULL, "randomised gains need K_* draws");
+    } else if (!buf->episode_count) {
+        return agx_set_error(AGX_E_NULL, "device-RNG reset needs episode_count");
+    }
+    if (cfg->num_envs == 0) return AGX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    AgxHp1ResetDraws d0 = {};
+    const AgxHp1ResetDraws& d = draws ? *draws : d0;
+    int threads = 128, g = (cfg->num_envs + threads - 1) / threads;
+    if (cfg->num_motors == 4) hp1_reset_kernel<4><<<g, threads, 0, st>>>(*cfg, *buf, mask, d, draws != nullptr);
+    else hp1_reset_kernel<8><<<g, threads, 0, st>>>(*cfg, *buf, mask, d, draws != nullptr);
+    return agx_check_launch("hp1_reset_kernel");
+}
+
+int agx_hp1_refresh(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, int only_if_flag, void* stream) {
+    if (!cfg || !buf) return agx_set_error(AGX_E_NULL, "cfg/buf is NULL");
+    if (!buf->root_state) return agx_set_error(AGX_E_NULL, "root_state is NULL");
+    if (only_if_flag && !buf->any_reset) return agx_set_error(AGX_E_NULL, "only_if_flag needs any_reset");
+    if (cfg->num_envs == 0) return AGX_OK;
+    hp1_refresh_kernel<<<grid_for(cfg->num_envs), kThreads, 0, (cudaStream_t)stream>>>(*cfg, *buf, only_if_flag, vec_ok_of(buf));
+    return agx_check_launch("hp1_refresh_kernel");
+}
+
+}  // extern "C"

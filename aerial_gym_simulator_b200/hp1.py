@@ -1,0 +1,297 @@
+"""Host side of HP1: owns the device tensors (PyTorch = allocator + streams only) and calls the
+C ABI (include/aerial_gym_b200.h) through ctypes.  No arithmetic of the hot path happens here.
+
+``MultirotorSpec`` is the flat, already-resolved description of one robot x controller x sim
+configuration (what the reference spreads over robot_config / controller_config / sim_config /
+Isaac Gym asset properties).  ``Hp1Engine`` binds a spec to N environments on one GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AgxHp1Buffers, AgxHp1Config, AgxHp1ResetDraws
+
+PI = math.pi
+
+
+@dataclass
+class MultirotorSpec:
+    """Field names deliberately match ``oracle.hp1_oracle.Hp1Model`` so tests can build the
+    checker from the same numbers (``dataclasses.asdict``)."""
+
+    num_motors: int = 4
+    controller: int = _lib.CTRL_ATTITUDE
+    dt: float = 0.01
+    gravity: tuple = (0.0, 0.0, -9.81)
+    mass: float = 0.25
+    inertia: np.ndarray = field(default_factory=lambda: np.diag([8.45e-4, 8.45e-4, 1.69e-3]))
+    com: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    allocation_matrix: np.ndarray = None
+    motor_directions: np.ndarray = None
+    thrust_to_torque_ratio: float = 0.01
+    force_application_level: str = "motor_link"
+    link_r: np.ndarray = None
+    link_R: np.ndarray = None
+    use_rps: bool = True
+    integration_scheme: str = "rk4"
+    use_discrete_approximation: bool = True
+    min_thrust: float = 0.0
+    max_thrust: float = 2.0
+    max_thrust_rate: float = 100000.0
+    tau_inc_range: tuple = (0.04, 0.04)
+    tau_dec_range: tuple = (0.04, 0.04)
+    k_thrust_range: tuple = (0.00000926312, 0.00001826312)
+    max_yaw_rate: float = PI / 3.0
+    K_pos_range: tuple = ((2.0, 2.0, 1.0), (3.0, 3.0, 2.0))
+    K_vel_range: tuple = ((2.0, 2.0, 2.0), (3.0, 3.0, 3.0))
+    K_rot_range: tuple = ((0.8, 0.8, 0.4), (1.2, 1.2, 0.6))
+    K_angvel_range: tuple = ((0.1, 0.1, 0.1), (0.2, 0.2, 0.2))
+    randomize_params: bool = False
+    drag_lin1: tuple = (0.0, 0.0, 0.0)
+    drag_lin2: tuple = (0.0, 0.0, 0.0)
+    drag_ang1: tuple = (0.0, 0.0, 0.0)
+    drag_ang2: tuple = (0.0, 0.0, 0.0)
+    enable_disturbance: bool = False
+    prob_apply_disturbance: float = 0.02
+    max_disturbance: tuple = (0.75, 0.75, 0.75, 0.004, 0.004, 0.004)
+    linear_damping: float = 0.01
+    angular_damping: float = 0.01
+    max_linear_velocity: float = 100.0
+    max_angular_velocity: float = 100.0
+    gyroscopic: bool = True
+    min_init_state: tuple = (0.1, 0.15, 0.15, 0, 0, -PI / 6, 1.0, -0.2, -0.2, -0.2, -0.2, -0.2, -0.2)
+    max_init_state: tuple = (0.2, 0.85, 0.85, 0, 0, PI / 6, 1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2)
+    bounds_lower_range: tuple = ((-1.0, -1.0, -1.0), (-1.0, -1.0, -1.0))
+    bounds_upper_range: tuple = ((1.0, 1.0, 1.0), (1.0, 1.0, 1.0))
+
+    def __post_init__(self):
+        M = self.num_motors
+        if self.allocation_matrix is None:  # base_quad_config.py:166-173
+            self.allocation_matrix = [
+                [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0],
+                [-0.13, -0.13, 0.13, 0.13], [-0.13, 0.13, 0.13, -0.13], [-0.01, 0.01, -0.01, 0.01],
+            ]
+        if self.motor_directions is None:
+            self.motor_directions = [1, -1, 1, -1]
+        if self.link_r is None:  # resources/robots/quad/quad.urdf joints base_link_to_motor_{0..3}
+            self.link_r = [[0.13, -0.13, 0.0], [-0.13, -0.13, 0.0], [-0.13, 0.13, 0.0], [0.13, 0.13, 0.0]]
+        if self.link_R is None:
+            self.link_R = np.tile(np.eye(3), (M, 1, 1))
+        self.allocation_matrix = np.asarray(self.allocation_matrix, dtype=np.float64)
+        self.motor_directions = np.asarray(self.motor_directions, dtype=np.float64)
+        self.link_r = np.asarray(self.link_r, dtype=np.float64)
+        self.link_R = np.asarray(self.link_R, dtype=np.float64)
+        self.inertia = np.asarray(self.inertia, dtype=np.float64)
+        self.com = np.asarray(self.com, dtype=np.float64)
+        if self.allocation_matrix.shape != (6, M):
+            raise ValueError("Allocation matrix must have 6 rows and num_motors columns.")
+
+    @property
+    def num_actions(self) -> int:
+        if self.controller == _lib.CTRL_NONE:
+            return self.num_motors
+        return 7 if self.controller == _lib.CTRL_FULLY_ACTUATED else 4
+
+    def wrench_map(self) -> np.ndarray:
+        """[6,M] motor thrust -> base-frame wrench about the COM:
+        motor_link: per-link local force [0,0,f], torque -cq*dir*[0,0,f] (control_allocation.py:103-114)
+        carried through the fixed URDF transform of link i; otherwise the allocation matrix at body 0."""
+        M = self.num_motors
+        if self.force_application_level == "motor_link":
+            W = np.zeros((6, M))
+            for i in range(M):
+                ez = self.link_R[i] @ np.array([0.0, 0.0, 1.0])
+                W[0:3, i] = ez
+                W[3:6, i] = np.cross(self.link_r[i] - self.com, ez) - self.thrust_to_torque_ratio * self.motor_directions[i] * ez
+            return W
+        W = self.allocation_matrix.copy()
+        for i in range(M):
+            W[3:6, i] += np.cross(-self.com, W[0:3, i])
+        return W
+
+    def alloc_pinv(self) -> np.ndarray:
+        # torch.linalg.pinv of the fp32 matrix, as control_allocation.py:46-48 does
+        A = torch.tensor(self.allocation_matrix, dtype=torch.float32)
+        return torch.linalg.pinv(A).double().numpy()
+
+
+def _set(arr, vals):
+    vals = np.asarray(vals, dtype=np.float64).reshape(-1)
+    for i, v in enumerate(vals):
+        arr[i] = float(v)
+
+
+def build_config(spec: MultirotorSpec, num_envs: int, *, physics_steps=1, episode_len_steps=500, seed=0,
+                 env_id_offset=0, device_rng_reset=True, strict_stale_obs=True, crash_distance=8.0) -> AgxHp1Config:
+    c = AgxHp1Config()
+    M = spec.num_motors
+    c.num_envs, c.num_motors, c.controller, c.num_actions = num_envs, M, spec.controller, spec.num_actions
+    c.physics_steps, c.episode_len_steps, c.env_id_offset = physics_steps, episode_len_steps, env_id_offset
+    c.seed = seed & 0xFFFFFFFFFFFFFFFF
+    flags = 0
+    flags |= _lib.F_USE_RPS if spec.use_rps else 0
+    flags |= _lib.F_MOTOR_RK4 if spec.integration_scheme != "euler" else 0
+    flags |= _lib.F_DISCRETE_MIX if spec.use_discrete_approximation else 0
+    flags |= _lib.F_GYROSCOPIC if spec.gyroscopic else 0
+    flags |= _lib.F_RANDOMIZE_GAINS if spec.randomize_params else 0
+    flags |= _lib.F_DEVICE_RNG_RESET if device_rng_reset else 0
+    flags |= _lib.F_STRICT_STALE_OBS if strict_stale_obs else 0
+    c.flags = flags
+    c.dt, c.mass = spec.dt, spec.mass
+    _set(c.gravity, spec.gravity)
+    _set(c.inertia, spec.inertia)
+    _set(c.inertia_inv, np.linalg.inv(spec.inertia))
+    _set(c.alloc_pinv, spec.alloc_pinv())  # [M,6] row-major
+    W = np.zeros((6, _lib.AGX_MAX_MOTORS))
+    W[:, :M] = spec.wrench_map()
+    _set(c.wrench_map, W)
+    _set(c.com, spec.com)
+    c.min_thrust, c.max_thrust, c.max_thrust_rate = spec.min_thrust, spec.max_thrust, spec.max_thrust_rate
+    c.max_yaw_rate = spec.max_yaw_rate
+    _set(c.drag_lin1, spec.drag_lin1); _set(c.drag_lin2, spec.drag_lin2)
+    _set(c.drag_ang1, spec.drag_ang1); _set(c.drag_ang2, spec.drag_ang2)
+    c.linear_damping, c.angular_damping = spec.linear_damping, spec.angular_damping
+    c.max_linear_velocity, c.max_angular_velocity = spec.max_linear_velocity, spec.max_angular_velocity
+    # construction-time gains: mid-point of min/max in fp32 (base_lee_controller.py:59-62)
+    mid = lambda r: ((np.float32(r[1]) + np.float32(r[0])) / np.float32(2.0)).astype(np.float64)
+    f32a = lambda x: np.asarray(x, dtype=np.float32)
+    _set(c.K_pos, mid((f32a(spec.K_pos_range[0]), f32a(spec.K_pos_range[1]))))
+    _set(c.K_vel, mid((f32a(spec.K_vel_range[0]), f32a(spec.K_vel_range[1]))))
+    _set(c.K_rot, mid((f32a(spec.K_rot_range[0]), f32a(spec.K_rot_range[1]))))
+    _set(c.K_angvel, mid((f32a(spec.K_angvel_range[0]), f32a(spec.K_angvel_range[1]))))
+    c.tau_inc, c.tau_dec, c.k_thrust = spec.tau_inc_range[0], spec.tau_dec_range[0], spec.k_thrust_range[0]
+    c.crash_distance = crash_distance
+    _set(c.min_init_state, spec.min_init_state); _set(c.max_init_state, spec.max_init_state)
+    _set(c.bounds_lo_min, spec.bounds_lower_range[0]); _set(c.bounds_lo_max, spec.bounds_lower_range[1])
+    _set(c.bounds_hi_min, spec.bounds_upper_range[0]); _set(c.bounds_hi_max, spec.bounds_upper_range[1])
+    _set(c.tau_inc_range, spec.tau_inc_range); _set(c.tau_dec_range, spec.tau_dec_range)
+    _set(c.k_thrust_range, spec.k_thrust_range)
+    _set(c.K_pos_min, spec.K_pos_range[0]); _set(c.K_pos_max, spec.K_pos_range[1])
+    _set(c.K_vel_min, spec.K_vel_range[0]); _set(c.K_vel_max, spec.K_vel_range[1])
+    _set(c.K_rot_min, spec.K_rot_range[0]); _set(c.K_rot_max, spec.K_rot_range[1])
+    _set(c.K_angvel_min, spec.K_angvel_range[0]); _set(c.K_angvel_max, spec.K_angvel_range[1])
+    return c
+
+
+class Hp1Engine:
+    """N environments of one MultirotorSpec on one CUDA device.
+
+    per_env_params: "auto" allocates a per-env array only for parameters whose reset range is
+    non-degenerate (they must be streamed); "all" allocates every array (needed to inject
+    arbitrary values, e.g. in parity tests)."""
+
+    DERIVED = ("euler", "vehicle_orientation", "vehicle_linvel", "body_linvel", "body_angvel")
+
+    def __init__(self, spec: MultirotorSpec, num_envs: int, device="cuda:0", *, physics_steps=1,
+                 episode_len_steps=500, seed=0, env_id_offset=0, device_rng_reset=True, strict_stale_obs=True,
+                 materialize_derived=True, per_env_params="auto", debug_wrench=False):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.AgxError("Hp1Engine needs a CUDA device: there is no CPU path")
+        self.spec, self.N, self.M = spec, int(num_envs), spec.num_motors
+        self.cfg = build_config(spec, self.N, physics_steps=physics_steps, episode_len_steps=episode_len_steps,
+                                seed=seed, env_id_offset=env_id_offset, device_rng_reset=device_rng_reset,
+                                strict_stale_obs=strict_stale_obs)
+        N, M, dev = self.N, self.M, self.device
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.root_state = z(N, 13)
+        self.root_state[:, 6] = 1.0
+        self.motor_thrust = z(N, M)
+        self.sim_steps = z(N, dt=torch.int32)
+        self.target_position = z(N, 3)
+        self.obs = z(N, 13)
+        self.reward = z(N)
+        self.terminations = z(N, dt=torch.bool)
+        self.truncations = z(N, dt=torch.bool)
+        self.reset_mask = z(N, dt=torch.bool)
+        self.any_reset = z(2, dt=torch.int32)
+        self.episode_count = z(N, dt=torch.int32)
+        self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
+        self.bounds_max = torch.tensor(spec.bounds_upper_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
+        allp = per_env_params == "all"
+        nd = lambda r: allp or (np.asarray(r[0]) != np.asarray(r[1])).any()
+        full = lambda v, *s: torch.full(s, float(v), dtype=torch.float32, device=dev)
+        self.tau_inc = full(spec.tau_inc_range[0], N, M) if nd(spec.tau_inc_range) else None
+        self.tau_dec = full(spec.tau_dec_range[0], N, M) if nd(spec.tau_dec_range) else None
+        self.k_thrust = full(spec.k_thrust_range[0], N, M) if (spec.use_rps and nd(spec.k_thrust_range)) else None
+        gains = allp or spec.randomize_params
+        gk = lambda a: torch.tensor([a[i] for i in range(3)], dtype=torch.float32, device=dev).expand(N, -1).clone()
+        self.K_pos = gk(self.cfg.K_pos) if gains else None
+        self.K_vel = gk(self.cfg.K_vel) if gains else None
+        self.K_rot = gk(self.cfg.K_rot) if gains else None
+        self.K_angvel = gk(self.cfg.K_angvel) if gains else None
+        self.euler = z(N, 3) if materialize_derived else None
+        self.vehicle_orientation = z(N, 4) if materialize_derived else None
+        self.vehicle_linvel = z(N, 3) if materialize_derived else None
+        self.body_linvel = z(N, 3) if materialize_derived else None
+        self.body_angvel = z(N, 3) if materialize_derived else None
+        self.body_wrench = z(N, 6) if debug_wrench else None
+        self._actions = None
+        self._buf = AgxHp1Buffers()
+        self._sync_buffers()
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _ptr(self, t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    def _sync_buffers(self):
+        b = self._buf
+        for name in _lib._HP1_BUF_FIELDS:
+            if name in ("actions", "disturbance"):
+                continue
+            setattr(b, name, self._ptr(getattr(self, name, None)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_actions(self, actions):
+        if actions.shape != (self.N, self.cfg.num_actions):
+            raise ValueError("Action tensor does not have the correct number of environments")
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
+            raise ValueError("actions must be a contiguous float32 tensor on the engine's device")
+        self._buf.actions = actions.data_ptr()
+
+    # ---- C ABI calls ------------------------------------------------------------------------
+    def physics_step(self, actions, disturbance=None, physics_steps=None):
+        self._check_actions(actions)
+        self._buf.disturbance = self._ptr(disturbance)
+        if physics_steps is not None:
+            self.cfg.physics_steps = int(physics_steps)
+        _lib.check(self.lib.agx_hp1_physics_step(C.byref(self.cfg), C.byref(self._buf), self._stream()),
+                   "agx_hp1_physics_step")
+
+    def position_task_step(self, actions, disturbance=None, physics_steps=None):
+        self._check_actions(actions)
+        self._buf.disturbance = self._ptr(disturbance)
+        if physics_steps is not None:
+            self.cfg.physics_steps = int(physics_steps)
+        _lib.check(self.lib.agx_hp1_position_task_step(C.byref(self.cfg), C.byref(self._buf), self._stream()),
+                   "agx_hp1_position_task_step")
+
+    def reset(self, mask: torch.Tensor, draws: Optional[dict] = None):
+        """mask: bool [N].  draws: dict of uniform [0,1) tensors keyed like AgxHp1ResetDraws, or None
+        for the device RNG."""
+        if mask.dtype != torch.bool or mask.shape != (self.N,):
+            raise ValueError("mask must be bool [N]")
+        d = None
+        if draws is not None:
+            d = AgxHp1ResetDraws()
+            for k in _lib._HP1_DRAW_FIELDS:
+                t = draws.get(k)
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                    raise ValueError(f"draw {k} must be contiguous float32")
+                setattr(d, k, self._ptr(t))
+        _lib.check(self.lib.agx_hp1_reset(C.byref(self.cfg), C.byref(self._buf), C.c_void_p(mask.data_ptr()),
+                                          C.byref(d) if d is not None else None, self._stream()), "agx_hp1_reset")
+
+    def refresh(self, only_if_flag=False):
+        _lib.check(self.lib.agx_hp1_refresh(C.byref(self.cfg), C.byref(self._buf), int(only_if_flag), self._stream()),
+                   "agx_hp1_refresh")
