@@ -65,6 +65,31 @@ class AgxHp1ResetDraws(C.Structure):
     _fields_ = [(n, fp) for n in _HP1_DRAW_FIELDS]
 
 
+class AgxHp2Scene(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_objects", C.c_int32), ("leaves_pow2", C.c_int32),
+        ("tris_per_object", C.c_int32), ("num_templates", C.c_int32), ("obj_pose_stride", C.c_int32),
+        ("tmpl_tri_offset", fp), ("tmpl_tris", fp), ("tmpl_seg_base", fp), ("tmpl_seg_mask", fp),
+        ("obj_pose", fp), ("obj_template", fp), ("obj_seg_counter", fp), ("bounds_min", fp), ("bounds_max", fp),
+        ("tris", fp), ("nodes", fp), ("leaf_object", fp),
+    ]
+
+
+class AgxHp2Sensor(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("num_sensors", C.c_int32),
+        ("calculate_depth", C.c_int32), ("return_pointcloud", C.c_int32), ("pointcloud_in_world_frame", C.c_int32),
+        ("segmentation", C.c_int32), ("fuse_epilogue", C.c_int32), ("normalize_range", C.c_int32),
+        ("c_x", C.c_int32), ("c_y", C.c_int32), ("kinv", f32 * 9), ("far_plane", f32),
+        ("max_range", f32), ("min_range", f32), ("far_out_of_range_value", f32), ("near_out_of_range_value", f32),
+        ("frame_quat", f32 * 4), ("robot_pose_stride", C.c_int32), ("pad_", C.c_int32),
+        ("robot_pose", fp), ("mount", fp), ("ray_table", fp), ("pixels", fp), ("seg_pixels", fp),
+    ]
+
+
+SENSOR_CAMERA, SENSOR_LIDAR = 0, 1
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -95,13 +120,21 @@ def load():
     for name, args in {
         "agx_hp1_physics_step": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p],
         "agx_hp1_position_task_step": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_hp1_position_task_step_profiled": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p,
+                                                C.c_void_p],
         "agx_hp1_reset": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p,
                           C.POINTER(AgxHp1ResetDraws), C.c_void_p],
         "agx_hp1_refresh": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_int, C.c_void_p],
+        "agx_hp2_update_scene": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_void_p],
+        "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
     }.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = args
+    lib.agx_hp2_scene_bytes.restype = C.c_uint64
+    lib.agx_hp2_scene_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    if lib.agx_sizeof(3) != C.sizeof(AgxHp2Scene) or lib.agx_sizeof(4) != C.sizeof(AgxHp2Sensor):
+        raise AgxError("HP2 ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
             or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):
         raise AgxError("ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")

@@ -694,6 +694,7 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
     if (cfg->num_actions != need)
         return agx_set_error(AGX_E_INVALID, "controller %d needs %d action columns (got %d)", cfg->controller, need, cfg->num_actions);
     if (cfg->physics_steps < 0) return agx_set_error(AGX_E_INVALID, "physics_steps < 0");
+    if (cfg->num_envs == 0) return AGX_OK;  /* empty batch: nothing to check or launch */
     if (!buf->root_state || !buf->motor_thrust || !buf->actions) return agx_set_error(AGX_E_NULL, "root_state/motor_thrust/actions is NULL");
     if (((uintptr_t)buf->motor_thrust | (uintptr_t)buf->actions | (uintptr_t)buf->tau_inc | (uintptr_t)buf->tau_dec |
          (uintptr_t)buf->k_thrust | (uintptr_t)buf->vehicle_orientation) & 15)
@@ -732,6 +733,11 @@ int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void
 }
 
 int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream) {
+    return agx_hp1_position_task_step_profiled(cfg, buf, stream, nullptr);
+}
+
+int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream,
+                                        void* ev_after_main) {
     int rc = validate(cfg, buf, true);
     if (rc) return rc;
     if (cfg->num_envs == 0) return AGX_OK;
@@ -741,6 +747,10 @@ int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf
     else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     rc = agx_check_launch("hp1_step_kernel<task>");
     if (rc) return rc;
+    if (ev_after_main) {
+        rc = agx_check_cuda(cudaEventRecord((cudaEvent_t)ev_after_main, st), "cudaEventRecord");
+        if (rc) return rc;
+    }
     // stale-derived-state quirk: if ANY env reset this step the reference refreshes
     // the derived states of ALL envs before the observation is read (base_multirotor.py:204-205).
     if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS)) {
@@ -752,6 +762,7 @@ int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf
 
 int agx_hp1_reset(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, const uint8_t* mask, const AgxHp1ResetDraws* draws,
                   void* stream) {
+    if (cfg && cfg->num_envs == 0) return AGX_OK;
     if (!cfg || !buf || !mask) return agx_set_error(AGX_E_NULL, "cfg/buf/mask is NULL");
     if (cfg->num_motors != 4 && cfg->num_motors != 8) return agx_set_error(AGX_E_INVALID, "num_motors must be 4 or 8");
     if (!buf->root_state || !buf->motor_thrust) return agx_set_error(AGX_E_NULL, "root_state/motor_thrust is NULL");
@@ -768,13 +779,14 @@ int agx_hp1_reset(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, const uint8
     cudaStream_t st = (cudaStream_t)stream;
     AgxHp1ResetDraws d0 = {};
     const AgxHp1ResetDraws& d = draws ? *draws : d0;
-    int threads = 128, g = (cfg->num_envs + threads - 1) / threads;
+    int threads = kThreads, g = (cfg->num_envs + threads - 1) / threads;
     if (cfg->num_motors == 4) hp1_reset_kernel<4><<<g, threads, 0, st>>>(*cfg, *buf, mask, d, draws != nullptr);
     else hp1_reset_kernel<8><<<g, threads, 0, st>>>(*cfg, *buf, mask, d, draws != nullptr);
     return agx_check_launch("hp1_reset_kernel");
 }
 
 int agx_hp1_refresh(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, int only_if_flag, void* stream) {
+    if (cfg && cfg->num_envs == 0) return AGX_OK;
     if (!cfg || !buf) return agx_set_error(AGX_E_NULL, "cfg/buf is NULL");
     if (!buf->root_state) return agx_set_error(AGX_E_NULL, "root_state is NULL");
     if (only_if_flag && !buf->any_reset) return agx_set_error(AGX_E_NULL, "only_if_flag needs any_reset");

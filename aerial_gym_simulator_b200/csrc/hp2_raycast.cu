@@ -1,0 +1,574 @@
+// HP2: depth / segmentation / LiDAR ray-caster for sm_100a.
+//
+//   agx_hp2_update_scene : per env (one CTA): instance transform of template triangles into
+//                          world space, object AABBs, 30-bit Morton codes, bitonic sort in shared
+//                          memory, implicit balanced binary BVH (heap order) bottom-up.
+//   agx_hp2_cast         : persistent CTAs; a work item is one (env, sensor, row block).  The
+//                          env's whole scene (BVH nodes + leaf map + triangle slabs) is staged
+//                          into shared memory with TMA bulk copies (cp.async.bulk + mbarrier,
+//                          SASS UBLKCP) when it fits (<= ~200 KB), else traversed from L2.
+//                          Per ray: sensor pose compose, ray generation, stack traversal,
+//                          Moller-Trumbore on the leaf's triangle slab, fused range-limit /
+//                          normalise epilogue, coalesced row stores.
+//
+// This unit is compiled with -fmad=false and every fusable multiply-add on the RESULT path is an
+// explicit fmaf(): the arithmetic is then bit-reproducible by oracle/hp2_oracle.c
+// (-ffp-contract=off), so depth and segmentation are bit-identical to the brute-force oracle
+// regardless of traversal order (ties on t resolve to the lowest triangle index in both).
+// The AABB slab tests only cull, are padded, and need no bit contract.
+//
+// No tensor-core path: closest-hit traversal is divergent scalar FP32 work.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/aerial_gym_b200.h"
+#include "agx_common.cuh"
+
+namespace {
+
+struct v3 {
+    float x, y, z;
+};
+struct q4 {
+    float x, y, z, w;
+};
+
+// ---- result-path arithmetic (bit contract with oracle/hp2_oracle.c) ----------------------
+__device__ __forceinline__ float dot3(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ v3 cross3(v3 a, v3 b) {
+    return v3{fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))};
+}
+__device__ __forceinline__ v3 sub3(v3 a, v3 b) { return v3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ v3 normalize3(v3 a) {
+    float n = sqrtf(dot3(a, a));
+    return v3{a.x / n, a.y / n, a.z / n};
+}
+// warp quat_rotate == utils/math.py:58-65
+__device__ __forceinline__ v3 quat_rotate(q4 q, v3 v) {
+    v3 qv{q.x, q.y, q.z};
+    float s = fmaf(2.0f * q.w, q.w, -1.0f);
+    v3 c = cross3(qv, v);
+    float d2 = 2.0f * dot3(qv, v);
+    float w2 = 2.0f * q.w;
+    return v3{fmaf(qv.x, d2, fmaf(c.x, w2, v.x * s)), fmaf(qv.y, d2, fmaf(c.y, w2, v.y * s)),
+              fmaf(qv.z, d2, fmaf(c.z, w2, v.z * s))};
+}
+// utils/math.py:313-320 quat_apply
+__device__ __forceinline__ v3 quat_apply(q4 q, v3 v) {
+    v3 qv{q.x, q.y, q.z};
+    v3 c = cross3(qv, v);
+    v3 t{2.0f * c.x, 2.0f * c.y, 2.0f * c.z};
+    v3 c2 = cross3(qv, t);
+    return v3{fmaf(q.w, t.x, v.x) + c2.x, fmaf(q.w, t.y, v.y) + c2.y, fmaf(q.w, t.z, v.z) + c2.z};
+}
+// utils/math.py:242-263 quat_mul
+__device__ __forceinline__ q4 quat_mul(q4 a, q4 b) {
+    float ww = (a.z + a.x) * (b.x + b.y);
+    float yy = (a.w - a.y) * (b.w + b.z);
+    float zz = (a.w + a.y) * (b.w - b.z);
+    float xx = ww + yy + zz;
+    float qq = 0.5f * fmaf(a.z - a.x, b.x - b.y, xx);
+    q4 r;
+    r.w = fmaf(a.z - a.y, b.y - b.z, qq - ww);
+    r.x = fmaf(a.x + a.w, b.x + b.w, qq - xx);
+    r.y = fmaf(a.w - a.x, b.y + b.z, qq - yy);
+    r.z = fmaf(a.z + a.y, b.w - b.x, qq - zz);
+    return r;
+}
+__device__ __forceinline__ v3 kinv_mul(const float* k, v3 c) {
+    return v3{fmaf(k[2], c.z, fmaf(k[1], c.y, k[0] * c.x)), fmaf(k[5], c.z, fmaf(k[4], c.y, k[3] * c.x)),
+              fmaf(k[8], c.z, fmaf(k[7], c.y, k[6] * c.x))};
+}
+
+constexpr float kAabbPad = 1e-4f;  // metres; culling only
+constexpr int kNodeFloats = 8;     // lo.xyz,0 | hi.xyz,0
+constexpr int kTriFloats = 12;     // v0.xyz,seg | e1.xyz,0 | e2.xyz,0
+
+// =========================================================================================
+// scene update: transform + BVH build, one CTA per env
+// =========================================================================================
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+hp2_update_scene_kernel(const __grid_constant__ AgxHp2Scene sc, const uint8_t* __restrict__ mask) {
+    const int e = blockIdx.x;
+    if (mask && !mask[e]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = sc.num_objects, P = sc.leaves_pow2, L = sc.tris_per_object;
+    float* s_nodes = reinterpret_cast<float*>(smem_raw);                      // [(2P-1)*8]
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_nodes + (size_t)(2 * P) * kNodeFloats);  // [P]
+    int32_t* s_val = reinterpret_cast<int32_t*>(s_key + P);                   // [P]
+    float* s_olo = reinterpret_cast<float*>(s_val + P);                       // [K*3] object AABBs
+    float* s_ohi = s_olo + (size_t)K * 3;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    float* tris = sc.tris + (size_t)e * K * L * kTriFloats;
+    // pass A: world-space triangle slabs (warp_env_manager.py:44-48 tf_apply over all vertices)
+    for (int i = tid; i < K * L; i += nt) {
+        int k = i / L, slot = i - k * L;
+        const float* p = sc.obj_pose + ((size_t)e * K + k) * sc.obj_pose_stride;
+        v3 t{p[0], p[1], p[2]};
+        q4 q{p[3], p[4], p[5], p[6]};
+        int tm = sc.obj_template[(size_t)e * K + k];
+        int f0 = sc.tmpl_tri_offset[tm], f1 = sc.tmpl_tri_offset[tm + 1];
+        float4 o0 = make_float4(0.f, 0.f, 0.f, __int_as_float(AGX_NO_HIT_SEG_VAL)), o1 = make_float4(0.f, 0.f, 0.f, 0.f), o2 = o1;
+        if (f0 + slot < f1) {
+            int f = f0 + slot;
+            const float* tv = sc.tmpl_tris + (size_t)f * 9;
+            v3 wa = quat_apply(q, v3{tv[0], tv[1], tv[2]});
+            v3 wb = quat_apply(q, v3{tv[3], tv[4], tv[5]});
+            v3 wc = quat_apply(q, v3{tv[6], tv[7], tv[8]});
+            wa.x += t.x; wa.y += t.y; wa.z += t.z;
+            wb.x += t.x; wb.y += t.y; wb.z += t.z;
+            wc.x += t.x; wc.y += t.y; wc.z += t.z;
+            v3 e1 = sub3(wb, wa), e2 = sub3(wc, wa);
+            int seg = sc.tmpl_seg_base[f] + sc.obj_seg_counter[(size_t)e * K + k] * sc.tmpl_seg_mask[f];
+            o0 = make_float4(wa.x, wa.y, wa.z, __int_as_float(seg));
+            o1 = make_float4(e1.x, e1.y, e1.z, 0.f);
+            o2 = make_float4(e2.x, e2.y, e2.z, 0.f);
+        }
+        float4* dst = reinterpret_cast<float4*>(tris + (size_t)i * kTriFloats);
+        dst[0] = o0; dst[1] = o1; dst[2] = o2;
+    }
+    __syncthreads();  // slabs of this CTA are read back below (same CTA wrote them)
+    // pass B: object AABBs from the slabs just written
+    for (int k = tid; k < K; k += nt) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        int tm = sc.obj_template[(size_t)e * K + k];
+        int n = min(L, sc.tmpl_tri_offset[tm + 1] - sc.tmpl_tri_offset[tm]);
+        for (int s = 0; s < n; ++s) {
+            const float4* src = reinterpret_cast<const float4*>(tris + ((size_t)k * L + s) * kTriFloats);
+            float4 a = src[0], b = src[1], c = src[2];
+            float vx[3] = {a.x, a.x + b.x, a.x + c.x}, vy[3] = {a.y, a.y + b.y, a.y + c.y}, vz[3] = {a.z, a.z + b.z, a.z + c.z};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                lo[0] = fminf(lo[0], vx[j]); hi[0] = fmaxf(hi[0], vx[j]);
+                lo[1] = fminf(lo[1], vy[j]); hi[1] = fmaxf(hi[1], vy[j]);
+                lo[2] = fminf(lo[2], vz[j]); hi[2] = fmaxf(hi[2], vz[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float pad = kAabbPad + 1e-6f * fmaxf(fabsf(lo[j]), fabsf(hi[j]));
+            s_olo[k * 3 + j] = lo[j] - pad;
+            s_ohi[k * 3 + j] = hi[j] + pad;
+        }
+    }
+    __syncthreads();
+    // Morton keys over the env bounds (parked objects at -1000 clamp to a corner)
+    float bl[3], bh[3];
+    if (sc.bounds_min && sc.bounds_max) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { bl[j] = sc.bounds_min[(size_t)e * 3 + j]; bh[j] = sc.bounds_max[(size_t)e * 3 + j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { bl[j] = -16.0f; bh[j] = 16.0f; }
+    }
+    for (int i = tid; i < P; i += nt) {
+        uint32_t key = 0xFFFFFFFFu;
+        int val = -1;
+        if (i < K) {
+            uint32_t c[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float ctr = 0.5f * (s_olo[i * 3 + j] + s_ohi[i * 3 + j]);
+                float u = (ctr - bl[j]) / fmaxf(bh[j] - bl[j], 1e-6f);
+                u = fminf(fmaxf(u, 0.0f), 1.0f);
+                c[j] = (uint32_t)fminf(u * 1023.0f, 1023.0f);
+            }
+            key = (expand_bits10(c[0]) << 2) | (expand_bits10(c[1]) << 1) | expand_bits10(c[2]);
+            val = i;
+        }
+        s_key[i] = key;
+        s_val[i] = val;
+    }
+    __syncthreads();
+    // bitonic sort of (key, val) -- P is a power of two; ties broken by val for determinism
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += nt) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t ka = s_key[i], kb = s_key[ixj];
+                    int va = s_val[i], vb = s_val[ixj];
+                    bool a_gt_b = (ka > kb) || (ka == kb && (uint32_t)va > (uint32_t)vb);
+                    bool up = ((i & k2) == 0);
+                    if (a_gt_b == up) {
+                        s_key[i] = kb; s_key[ixj] = ka;
+                        s_val[i] = vb; s_val[ixj] = va;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // leaves (heap index P-1+i)
+    for (int i = tid; i < P; i += nt) {
+        int obj = s_val[i];
+        float* nd = s_nodes + (size_t)(P - 1 + i) * kNodeFloats;
+        if (obj >= 0) {
+            nd[0] = s_olo[obj * 3]; nd[1] = s_olo[obj * 3 + 1]; nd[2] = s_olo[obj * 3 + 2]; nd[3] = 0.f;
+            nd[4] = s_ohi[obj * 3]; nd[5] = s_ohi[obj * 3 + 1]; nd[6] = s_ohi[obj * 3 + 2]; nd[7] = 0.f;
+        } else {
+            nd[0] = nd[1] = nd[2] = FLT_MAX; nd[3] = 0.f;
+            nd[4] = nd[5] = nd[6] = -FLT_MAX; nd[7] = 0.f;
+        }
+    }
+    __syncthreads();
+    // internal levels bottom-up
+    for (int width = P >> 1; width >= 1; width >>= 1) {
+        for (int i = tid; i < width; i += nt) {
+            int n = width - 1 + i;
+            const float* a = s_nodes + (size_t)(2 * n + 1) * kNodeFloats;
+            const float* b = s_nodes + (size_t)(2 * n + 2) * kNodeFloats;
+            float* d = s_nodes + (size_t)n * kNodeFloats;
+            d[0] = fminf(a[0], b[0]); d[1] = fminf(a[1], b[1]); d[2] = fminf(a[2], b[2]); d[3] = 0.f;
+            d[4] = fmaxf(a[4], b[4]); d[5] = fmaxf(a[5], b[5]); d[6] = fmaxf(a[6], b[6]); d[7] = 0.f;
+        }
+        __syncthreads();
+    }
+    float* gn = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
+    for (int i = tid; i < (2 * P - 1) * kNodeFloats; i += nt) gn[i] = s_nodes[i];
+    int32_t* gl = sc.leaf_object + (size_t)e * P;
+    for (int i = tid; i < P; i += nt) gl[i] = s_val[i];
+}
+
+// =========================================================================================
+// ray casting
+// =========================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct Hit {
+    float t;
+    int tri;
+};
+
+// Moller-Trumbore on one triangle slab (bit contract with oracle closest_hit)
+__device__ __forceinline__ void tri_test(const float4* __restrict__ tp, int tri_index, v3 o, v3 d, float max_t, Hit& best) {
+    float4 a = tp[0], b = tp[1], c = tp[2];
+    v3 v0{a.x, a.y, a.z}, e1{b.x, b.y, b.z}, e2{c.x, c.y, c.z};
+    v3 pv = cross3(d, e2);
+    float det = dot3(e1, pv);
+    if (fabsf(det) < 1e-20f) return;
+    float inv = 1.0f / det;
+    v3 tv = sub3(o, v0);
+    float u = dot3(tv, pv) * inv;
+    if (u < 0.0f || u > 1.0f) return;
+    v3 qv = cross3(tv, e1);
+    float v = dot3(d, qv) * inv;
+    if (v < 0.0f || u + v > 1.0f) return;
+    float t = dot3(e2, qv) * inv;
+    if (t < 0.0f || !(t < max_t)) return;
+    if (t < best.t || (t == best.t && tri_index < best.tri)) {
+        best.t = t;
+        best.tri = tri_index;
+    }
+}
+
+// conservative slab test; returns entry distance or a negative value for a miss
+__device__ __forceinline__ float aabb_entry(const float* nd, v3 o, v3 inv, float t_limit) {
+    float4 lo = *reinterpret_cast<const float4*>(nd);
+    float4 hi = *reinterpret_cast<const float4*>(nd + 4);
+    float tx1 = (lo.x - o.x) * inv.x, tx2 = (hi.x - o.x) * inv.x;
+    float ty1 = (lo.y - o.y) * inv.y, ty2 = (hi.y - o.y) * inv.y;
+    float tz1 = (lo.z - o.z) * inv.z, tz2 = (hi.z - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), 0.0f));
+    float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+    float slack = 1e-5f * (1.0f + fabsf(tmax));
+    bool hit = (tmin <= tmax + slack) && (tmin <= t_limit + 1e-5f * (1.0f + t_limit));
+    return hit ? tmin : -1.0f;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ Hit traverse(const float* __restrict__ nodes, const int32_t* __restrict__ leaf_obj,
+                                        const float* __restrict__ tris, int P, int L, v3 o, v3 d, float max_t) {
+    Hit best{max_t, 0x7fffffff};
+    v3 inv{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    int stack[24];
+    int sp = 0;
+    int node = 0;
+    if (P == 1) {
+        node = 0;
+    } else if (aabb_entry(nodes, o, inv, best.t) < 0.0f) {
+        return best;
+    }
+    while (true) {
+        if (node >= P - 1) {  // leaf
+            int obj = leaf_obj[node - (P - 1)];
+            if (obj >= 0) {
+                const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)obj * L * kTriFloats);
+                for (int s = 0; s < L; ++s) tri_test(tp + 3 * s, obj * L + s, o, d, max_t, best);
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+            continue;
+        }
+        int c0 = 2 * node + 1, c1 = c0 + 1;
+        float t0 = aabb_entry(nodes + (size_t)c0 * kNodeFloats, o, inv, best.t);
+        float t1 = aabb_entry(nodes + (size_t)c1 * kNodeFloats, o, inv, best.t);
+        if (t0 >= 0.0f && t1 >= 0.0f) {
+            if (t0 <= t1) { stack[sp++] = c1; node = c0; }
+            else { stack[sp++] = c0; node = c1; }
+        } else if (t0 >= 0.0f) {
+            node = c0;
+        } else if (t1 >= 0.0f) {
+            node = c1;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return best;
+}
+
+__device__ __forceinline__ float range_epilogue(const AgxHp2Sensor& s, float px) {
+    // warp_sensor.py:216-225: two sequential masked assignments, then the division
+    if (px > s.max_range) px = s.far_out_of_range_value;
+    if (px < s.min_range) px = s.near_out_of_range_value;
+    if (s.normalize_range && !s.pointcloud_in_world_frame) px = px / s.max_range;
+    return px;
+}
+
+constexpr int kCastThreads = 256;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kCastThreads)
+hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ AgxHp2Sensor sn, int rows_per_item,
+                int items_per_image, long long n_items) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int K = sc.num_objects, P = sc.leaves_pow2, L = sc.tris_per_object;
+    const int W = sn.width, H = sn.height, S = sn.num_sensors;
+    const uint32_t node_bytes = (uint32_t)((2 * P - 1) * kNodeFloats * 4);
+    const uint32_t leaf_bytes = (uint32_t)(P * 4);
+    const uint32_t tri_bytes = (uint32_t)((size_t)K * L * kTriFloats * 4);
+    float* s_nodes = reinterpret_cast<float*>(smem_raw);
+    int32_t* s_leaf = reinterpret_cast<int32_t*>(smem_raw + ((node_bytes + 15u) & ~15u));
+    float* s_tris = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_leaf) + ((leaf_bytes + 15u) & ~15u));
+    if (SMEM && threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    int staged_env = -1;
+    const q4 qf{sn.frame_quat[0], sn.frame_quat[1], sn.frame_quat[2], sn.frame_quat[3]};
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = (int)(item % items_per_image);
+        const long long es = item / items_per_image;
+        const int c = (int)(es % S);
+        const int e = (int)(es / S);
+        const float* g_nodes = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
+        const int32_t* g_leaf = sc.leaf_object + (size_t)e * P;
+        const float* g_tris = sc.tris + (size_t)e * K * L * kTriFloats;
+        const float* nodes = g_nodes;
+        const int32_t* leaf = g_leaf;
+        const float* tris = g_tris;
+        if (SMEM) {
+            if (e != staged_env) {
+                __syncthreads();  // everyone is done with the previous scene
+                if (threadIdx.x == 0) {
+                    // order prior generic-proxy smem reads before the async-proxy writes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&s_bar, node_bytes + leaf_bytes + tri_bytes);
+                    tma_bulk_g2s(s_nodes, g_nodes, node_bytes, &s_bar);
+                    tma_bulk_g2s(s_leaf, g_leaf, leaf_bytes, &s_bar);
+                    tma_bulk_g2s(s_tris, g_tris, tri_bytes, &s_bar);
+                }
+                mbar_wait(&s_bar, parity);
+                parity ^= 1u;
+                staged_env = e;
+            }
+            nodes = s_nodes;
+            leaf = s_leaf;
+            tris = s_tris;
+        }
+        // ---- sensor pose: warp_sensor.py:180-187 ------------------------------------------------
+        const float* rp = sn.robot_pose + (size_t)e * sn.robot_pose_stride;
+        const float* m = sn.mount + ((size_t)e * S + c) * 7;
+        q4 rq{rp[3], rp[4], rp[5], rp[6]};
+        v3 sp = quat_apply(rq, v3{m[0], m[1], m[2]});
+        sp.x += rp[0]; sp.y += rp[1]; sp.z += rp[2];
+        q4 sq = quat_mul(rq, quat_mul(q4{m[3], m[4], m[5], m[6]}, qf));
+        v3 rd_p{0.f, 0.f, 0.f};
+        if (sn.kind == AGX_SENSOR_CAMERA) {
+            v3 uvp = kinv_mul(sn.kinv, v3{(float)sn.c_x, (float)sn.c_y, 1.0f});
+            if (sn.return_pointcloud) uvp = normalize3(uvp);
+            rd_p = normalize3(quat_rotate(sq, uvp));
+        }
+        const int y0 = rb * rows_per_item;
+        const int y1 = min(H, y0 + rows_per_item);
+        const int n_pix = (y1 - y0) * W;
+        for (int i = threadIdx.x; i < n_pix; i += kCastThreads) {
+            const int y = y0 + i / W, x = i % W;
+            v3 uv, rd;
+            float mult = 1.0f, max_t = sn.far_plane;
+            if (sn.kind == AGX_SENSOR_CAMERA) {  // warp_camera_kernels.py:186-221
+                uv = kinv_mul(sn.kinv, v3{(float)x, (float)y, 1.0f});
+                if (sn.return_pointcloud) uv = normalize3(uv);
+                rd = normalize3(quat_rotate(sq, uv));
+                if (!sn.return_pointcloud && sn.calculate_depth) {
+                    mult = dot3(rd, rd_p);
+                    max_t = sn.far_plane / mult;
+                }
+            } else {  // warp_lidar_kernels.py:24-33
+                const float* rt = sn.ray_table + ((size_t)y * W + x) * 3;
+                uv = normalize3(v3{rt[0], rt[1], rt[2]});
+                rd = normalize3(quat_rotate(sq, uv));
+            }
+            Hit h = traverse<SMEM>(nodes, leaf, tris, P, L, sp, rd, max_t);
+            float dist = AGX_NO_HIT_RAY_VAL;
+            int segv = AGX_NO_HIT_SEG_VAL;
+            if (h.tri != 0x7fffffff) {
+                dist = mult * h.t;
+                segv = __float_as_int(tris[(size_t)h.tri * kTriFloats + 3]);
+            }
+            const size_t pix = (((size_t)e * S + c) * H + y) * W + x;
+            if (sn.return_pointcloud) {
+                v3 p;
+                if (sn.pointcloud_in_world_frame) p = v3{fmaf(dist, rd.x, sp.x), fmaf(dist, rd.y, sp.y), fmaf(dist, rd.z, sp.z)};
+                else p = v3{dist * uv.x, dist * uv.y, dist * uv.z};
+                if (sn.fuse_epilogue && !sn.pointcloud_in_world_frame) {  // warp_sensor.py:203-215
+                    float nrm = sqrtf(dot3(p, p));
+                    if (nrm > sn.max_range) p = v3{sn.far_out_of_range_value, sn.far_out_of_range_value, sn.far_out_of_range_value};
+                    nrm = sqrtf(dot3(p, p));
+                    if (nrm < sn.min_range) p = v3{sn.near_out_of_range_value, sn.near_out_of_range_value, sn.near_out_of_range_value};
+                    if (sn.normalize_range) p = v3{p.x / sn.max_range, p.y / sn.max_range, p.z / sn.max_range};
+                }
+                sn.pixels[pix * 3 + 0] = p.x; sn.pixels[pix * 3 + 1] = p.y; sn.pixels[pix * 3 + 2] = p.z;
+            } else {
+                sn.pixels[pix] = sn.fuse_epilogue ? range_epilogue(sn, dist) : dist;
+            }
+            if (sn.seg_pixels) sn.seg_pixels[pix] = segv;
+        }
+    }
+}
+
+inline int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+inline size_t scene_smem_bytes(int K, int P, int L) {
+    size_t nb = ((size_t)(2 * P - 1) * kNodeFloats * 4 + 15) & ~(size_t)15;
+    size_t lb = ((size_t)P * 4 + 15) & ~(size_t)15;
+    return nb + lb + (size_t)K * L * kTriFloats * 4;
+}
+
+int validate_scene(const AgxHp2Scene* sc) {
+    if (!sc) return agx_set_error(AGX_E_NULL, "scene is NULL");
+    if (sc->num_objects < 1 || sc->num_objects > AGX_HP2_MAX_OBJECTS)
+        return agx_set_error(AGX_E_INVALID, "num_objects must be in [1, %d]", AGX_HP2_MAX_OBJECTS);
+    if (sc->leaves_pow2 != next_pow2(sc->num_objects)) return agx_set_error(AGX_E_INVALID, "leaves_pow2 must be the next power of two >= num_objects");
+    if (sc->tris_per_object < 1 || sc->tris_per_object > 64) return agx_set_error(AGX_E_INVALID, "tris_per_object must be in [1, 64]");
+    if (!sc->tris || !sc->nodes || !sc->leaf_object) return agx_set_error(AGX_E_NULL, "scene storage (tris/nodes/leaf_object) is NULL");
+    if (((uintptr_t)sc->tris | (uintptr_t)sc->nodes | (uintptr_t)sc->leaf_object) & 15) return agx_set_error(AGX_E_INVALID, "scene storage must be 16-byte aligned");
+    return AGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which) {
+    int P = next_pow2(num_objects < 1 ? 1 : num_objects);
+    switch (which) {
+        case 0: return (uint64_t)num_objects * tris_per_object * kTriFloats * 4;
+        case 1: return (uint64_t)(2 * P - 1) * kNodeFloats * 4;
+        case 2: return (uint64_t)P * 4;
+        default: return 0;
+    }
+}
+
+int agx_hp2_update_scene(const AgxHp2Scene* sc, const uint8_t* mask, void* stream) {
+    int rc = validate_scene(sc);
+    if (rc) return rc;
+    if (sc->num_envs == 0) return AGX_OK;
+    if (!sc->tmpl_tri_offset || !sc->tmpl_tris || !sc->tmpl_seg_base || !sc->tmpl_seg_mask || !sc->obj_pose || !sc->obj_template ||
+        !sc->obj_seg_counter)
+        return agx_set_error(AGX_E_NULL, "scene templates / instances are NULL");
+    if (sc->obj_pose_stride < 7) return agx_set_error(AGX_E_INVALID, "obj_pose_stride < 7");
+    const int K = sc->num_objects, P = sc->leaves_pow2;
+    size_t smem = (size_t)(2 * P) * kNodeFloats * 4 + (size_t)P * 8 + (size_t)K * 6 * 4;
+    rc = agx_check_cuda(cudaFuncSetAttribute(hp2_update_scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(update_scene)");
+    if (rc) return rc;
+    hp2_update_scene_kernel<<<sc->num_envs, 256, smem, (cudaStream_t)stream>>>(*sc, mask);
+    return agx_check_launch("hp2_update_scene_kernel");
+}
+
+int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
+    int rc = validate_scene(sc);
+    if (rc) return rc;
+    if (!sn) return agx_set_error(AGX_E_NULL, "sensor is NULL");
+    if (sn->kind != AGX_SENSOR_CAMERA && sn->kind != AGX_SENSOR_LIDAR) return agx_set_error(AGX_E_INVALID, "unknown sensor kind %d", sn->kind);
+    if (sn->width < 1 || sn->height < 1 || sn->num_sensors < 1) return agx_set_error(AGX_E_INVALID, "sensor dims must be positive");
+    if (sc->num_envs == 0) return AGX_OK;
+    if (!sn->robot_pose || !sn->mount || !sn->pixels) return agx_set_error(AGX_E_NULL, "robot_pose/mount/pixels is NULL");
+    if (sn->kind == AGX_SENSOR_LIDAR && !sn->ray_table) return agx_set_error(AGX_E_NULL, "LiDAR needs ray_table");
+    if (sn->robot_pose_stride < 7) return agx_set_error(AGX_E_INVALID, "robot_pose_stride < 7");
+    int dev = 0, sms = 148, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int W = sn->width, H = sn->height;
+    // a work item = up to ~2048 rays of one (env, sensor) image
+    int rows_per_item = 2048 / W;
+    if (rows_per_item < 1) rows_per_item = 1;
+    if (rows_per_item > H) rows_per_item = H;
+    int items_per_image = (H + rows_per_item - 1) / rows_per_item;
+    long long n_items = (long long)sc->num_envs * sn->num_sensors * items_per_image;
+    size_t smem = scene_smem_bytes(sc->num_objects, sc->leaves_pow2, sc->tris_per_object);
+    bool use_smem = smem + 1024 <= (size_t)max_smem;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_smem) {
+        rc = agx_check_cuda(cudaFuncSetAttribute(hp2_cast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(cast)");
+        if (rc) return rc;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp2_cast_kernel<true>, kCastThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sms * per_sm;
+        if (grid > n_items) grid = n_items;
+        hp2_cast_kernel<true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+    } else {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp2_cast_kernel<false>, kCastThreads, 0);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sms * per_sm;
+        if (grid > n_items) grid = n_items;
+        hp2_cast_kernel<false><<<(int)grid, kCastThreads, 0, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+    }
+    return agx_check_launch("hp2_cast_kernel");
+}
+
+}  // extern "C"

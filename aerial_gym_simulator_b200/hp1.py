@@ -268,12 +268,15 @@ class Hp1Engine:
         _lib.check(self.lib.agx_hp1_physics_step(C.byref(self.cfg), C.byref(self._buf), self._stream()),
                    "agx_hp1_physics_step")
 
-    def position_task_step(self, actions, disturbance=None, physics_steps=None):
+    def position_task_step(self, actions, disturbance=None, physics_steps=None, mid_event=None):
+        """mid_event: optional torch.cuda.Event(enable_timing=True), already recorded once (so its
+        handle exists); the library records it between the main kernel and the refresh pass."""
         self._check_actions(actions)
         self._buf.disturbance = self._ptr(disturbance)
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
-        _lib.check(self.lib.agx_hp1_position_task_step(C.byref(self.cfg), C.byref(self._buf), self._stream()),
+        ev = C.c_void_p(mid_event.cuda_event) if mid_event is not None else None
+        _lib.check(self.lib.agx_hp1_position_task_step_profiled(C.byref(self.cfg), C.byref(self._buf), self._stream(), ev),
                    "agx_hp1_position_task_step")
 
     def reset(self, mask: torch.Tensor, draws: Optional[dict] = None):

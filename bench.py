@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the position_setpoint_task hot path (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 200 --warmup 10            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --steps 20 --warmup 3      # reference arm (CPU, see below)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one PositionSetpointTask.step over one batch of 65,536 envs per GPU (weak scaling:
+per-GPU work fixed): fused physics + reward + termination/truncation + in-kernel reset +
+observation, then (N > 1) one NCCL all-gather of the observation tensor.
+
+Timing: W >= 3 warm-up steps, then exactly K steps.  The 65,536-env working set (~20 MB) is
+smaller than the 126 MB L2, so L2 is FLUSHED before every timed step (a 256 MiB write) and each
+step is bracketed by its own CUDA-event pair on the launching stream; the flushes are outside
+the event pairs.  value = N_gpus * envs * K / sum(step times), max over ranks.  The whole region
+is additionally bracketed by barrier + synchronize on both sides.  `value_hot_l2` is the same
+loop without flushes (state resident in L2, the RL-loop situation).
+
+Reference arm (`--impl reference`): the reference's Isaac Gym sim_device=cpu pipeline cannot run
+here or on the GPU box (isaacgym is a closed binary, not installed; /root/reference does not
+travel).  It times the oracle port of the same step (oracle/hp1_oracle.py: the reference's torch
+control stack restated + our integrator spec) on the host cores with all torch threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+ALG_BYTES_PER_ENV_STEP = 210  # 84 B read + 126 B written, state-only, M = 4
+METRIC = "env-steps/sec (position_setpoint_task, base_quadrotor, lee_attitude_control, 65536 envs/GPU, state-only)"
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {
+        "workload": "position_setpoint_task/base_quadrotor/lee_attitude_control/empty_env",
+        "envs_per_gpu": ENVS_PER_GPU,
+        "global_envs": ENVS_PER_GPU * n_gpus,
+        "physics_steps_per_env_step": 1,
+        "dt": 0.01,
+        "episode_len_steps": 500,
+        "actions": "U(-1,1) resampled from 8 pre-generated batches",
+        "parallelism": f"env-sharded x{n_gpus}" + (" + NCCL all-gather(obs)" if n_gpus > 1 else ""),
+        "l2": "flushed before every timed step (256 MiB write, outside the event pair)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        # "under load" = samples in the top half of the observed clock range
+        load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU port (oracle) timing -- cpu_baseline leg and the reference arm
+# ------------------------------------------------------------------------------------------
+def time_cpu_port(n_envs, steps, warmup):
+    import torch
+
+    from oracle import hp1_oracle as O
+
+    model = O.Hp1Model()
+    g = torch.Generator().manual_seed(0)
+    st = O.make_state(model, n_envs)
+    O.reset_envs(model, st, torch.ones(n_envs, dtype=torch.bool), O.draw_reset_uniforms(model, n_envs, generator=g))
+    st.sim_steps = (torch.arange(n_envs) % 500).to(torch.int32)
+    tgt = torch.zeros(n_envs, 3)
+    acts = [torch.rand(n_envs, 4, generator=g) * 2 - 1 for _ in range(8)]
+    draw = lambda: O.draw_reset_uniforms(model, n_envs, generator=g)
+    for i in range(warmup):
+        O.position_task_step(model, st, acts[i % 8], tgt, draw_fn=draw)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.position_task_step(model, st, acts[i % 8], tgt, draw_fn=draw)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_envs = ENVS_PER_GPU
+    # bound the sample: keep the whole run within ~2 minutes of CPU time
+    v1, t1, cores = time_cpu_port(n_envs, 1, 1)
+    budget = 120.0
+    if (args.steps + args.warmup) * t1 > budget:
+        n_envs = max(1024, int(n_envs * budget / ((args.steps + args.warmup) * t1)) // 1024 * 1024)
+    value, per_step, cores = time_cpu_port(n_envs, args.steps, max(args.warmup, 1))
+    sample = f"{n_envs} envs x {args.steps} steps, torch CPU fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, {"l2": "n/a (CPU)", "sample_envs": n_envs,
+                                              "note": "oracle port of the reference step (reference torch control stack restated + integrator spec); "
+                                                      "NOT the Isaac Gym CPU pipeline, which cannot be installed"}),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    N = args.envs
+
+    spec = MultirotorSpec()
+    eng = Hp1Engine(spec, N, dev, seed=1, env_id_offset=rank * N, device_rng_reset=True, strict_stale_obs=True,
+                    materialize_derived=False)
+    eng.reset(torch.ones(N, dtype=torch.bool, device=dev))
+    eng.refresh()
+    eng.sim_steps.copy_((torch.arange(N, device=dev) % 500).int())  # de-synchronised episode phases
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
+    gathered = torch.empty(world * N, 13, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, mid=None):
+        eng.position_task_step(acts[i % 8], mid_event=mid)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, eng.obs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        step(i)
+    barrier()
+
+    # ---- timed region: K steps, L2 flushed before each, per-step event pairs ----------------
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    evm = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for e in evm:
+        e.record(stream)  # creates the handle the library records into
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(float(i))
+        ev0[i].record(stream)
+        step(i, evm[i])
+        ev1[i].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    main_ms = [a.elapsed_time(b) for a, b in zip(ev0, evm)]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    main_total = torch.tensor([sum(main_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(main_total, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = world * N * K / total_s
+
+    # ---- same loop, no flush (state L2-resident) ---------------------------------------------
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for i in range(K):
+        step(i)
+    a1.record(stream)
+    barrier()
+    hot_ms = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(hot_ms, op=dist.ReduceOp.MAX)
+    value_hot = world * N * K / (float(hot_ms.item()) * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region --------------
+    h_act = [a.cpu().pin_memory() for a in acts]
+    d_act = torch.empty(N, 4, device=dev)
+    h_obs = torch.empty(N, 13).pin_memory()
+    h_rew = torch.empty(N).pin_memory()
+    h_term = torch.empty(N, dtype=torch.bool).pin_memory()
+    h_trunc = torch.empty(N, dtype=torch.bool).pin_memory()
+
+    def e2e_step(i):
+        d_act.copy_(h_act[i % 8], non_blocking=True)
+        eng.position_task_step(d_act)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, eng.obs)
+        h_obs.copy_(eng.obs, non_blocking=True)
+        h_rew.copy_(eng.reward, non_blocking=True)
+        h_term.copy_(eng.terminations, non_blocking=True)
+        h_trunc.copy_(eng.truncations, non_blocking=True)
+        stream.synchronize()  # the user reads the result of every step
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * K / float(e2e_t.item())
+    h2d = N * 4 * 4
+    d2h = N * 13 * 4 + N * 4 + 2 * N
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        main_avg_s = float(main_total.item()) * 1e-3 / K
+        achieved = ALG_BYTES_PER_ENV_STEP * N / main_avg_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "hp1_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, per, cores = time_cpu_port(ENVS_PER_GPU, 40, 3)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                   "sample": f"{ENVS_PER_GPU} envs x 40 steps of the same step, oracle port, torch CPU fp32"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_s * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world}),
+            "value_hot_l2": value_hot,
+            "wall_s_timed_region_incl_flush": t_wall,
+            "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,
+                         "kernel_ms_avg": main_avg_s * 1e3,
+                         "note": "at 65,536 envs the launch is ~14 MB: FP32-issue / latency bound, not HBM bound (DESIGN.md)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "Hp1Engine.position_task_step (C ABI) with pinned host actions in, obs/reward/flags out"},
+            "gpu_launches": 2 * K,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -160,6 +160,10 @@ int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void
  * envs to reset are only flagged (reset_mask, any_reset[0]) and the caller follows with
  * agx_hp1_reset + agx_hp1_refresh. */
 int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream);
+/* Same call; additionally records the cudaEvent_t `ev_after_main` between the main kernel and the
+ * conditional refresh pass, so a caller can time the dominant kernel alone (bench.py roofline). */
+int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream,
+                                        void* ev_after_main);
 
 /* Masked re-initialisation, EnvManager.reset_idx for a robot-only scene
  * (env_manager/env_manager.py:273-301 -> IGE_env_manager.py:513-519, base_multirotor.py:177-205,
@@ -173,6 +177,81 @@ int agx_hp1_reset(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, const uint8
  * plus the position-task observation when buf->obs != NULL.  only_if_flag != 0: the pass is a
  * no-op unless buf->any_reset[0] != 0 (and it clears the flag). */
 int agx_hp1_refresh(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, int only_if_flag, void* stream);
+
+
+/* ======================================================================================
+ * HP2 -- depth / segmentation / LiDAR ray-caster
+ * ====================================================================================== */
+#define AGX_HAVE_HP2 1
+#define AGX_HP2_MAX_OBJECTS 2048      /* objects (triangle clusters) per env */
+#define AGX_NO_HIT_RAY_VAL 1000.0f    /* sensors/warp/warp_kernels/warp_camera_kernels.py:3 */
+#define AGX_NO_HIT_SEG_VAL (-2)       /* warp_camera_kernels.py:4 */
+
+/* Per-env triangle scene + BVH.  Replaces WarpEnv (env_manager/warp_env_manager.py:97-189):
+ * one wp.Mesh per env built from the concatenated asset meshes, vertices re-transformed by the
+ * asset root poses and the BVH refit on reset (:40-54).
+ * Geometry is instanced: every object of every env references a TEMPLATE (a triangle list in the
+ * object frame, <= tris_per_object triangles; larger meshes are split into several templates
+ * by the host) and carries a pose.  agx_hp2_update_scene writes the world-space triangles and
+ * builds the per-env BVH (Morton-sorted implicit balanced binary tree over objects). */
+typedef struct AgxHp2Scene {
+    int32_t num_envs;
+    int32_t num_objects;        /* K objects per env (same for all envs), 1..AGX_HP2_MAX_OBJECTS */
+    int32_t leaves_pow2;        /* P = smallest power of two >= K */
+    int32_t tris_per_object;    /* L triangle slots per object (padded with degenerate triangles) */
+    int32_t num_templates;
+    int32_t obj_pose_stride;    /* floats between consecutive object poses (13 for env_asset_state_tensor rows) */
+    const int32_t* tmpl_tri_offset; /* [T+1] first triangle of each template */
+    const float* tmpl_tris;     /* [Ft,9] object-frame v0,v1,v2 */
+    const int32_t* tmpl_seg_base; /* [Ft] asset_vertex_segmentation_value of the face's first vertex (assets/warp_asset.py:113) */
+    const int32_t* tmpl_seg_mask; /* [Ft] variable_segmentation_mask (assets/warp_asset.py:114-116) */
+    const float* obj_pose;      /* [E,K,stride] x y z qx qy qz qw ... (env_asset_state_tensor, IGE_env_manager.py:315-317) */
+    const int32_t* obj_template;    /* [E,K] */
+    const int32_t* obj_seg_counter; /* [E,K] segmentation counter of the instance (warp_env_manager.py:76-80) */
+    const float* bounds_min;    /* [E,3] env bounds used to normalise Morton codes, or NULL */
+    const float* bounds_max;
+    /* device storage owned by the caller, layout defined by the library: */
+    float* tris;                /* [E][K*L][12]  (v0.xyz, seg bits | e1.xyz, 0 | e2.xyz, 0) */
+    float* nodes;               /* [E][2P-1][8]  (lo.xyz, 0 | hi.xyz, 0), heap order, leaves last */
+    int32_t* leaf_object;       /* [E][P] object index of each Morton-sorted leaf, -1 = empty */
+} AgxHp2Scene;
+
+#define AGX_SENSOR_CAMERA 0
+#define AGX_SENSOR_LIDAR 1
+
+/* One sensor type on every robot.  Replaces WarpSensor.update (sensors/warp/warp_sensor.py:177-200)
+ * = pose compose (:180-187) + WarpCam/WarpLidar.capture (warp_cam.py:172-182, warp_lidar.py) +
+ * apply_range_limits (:202-220) + normalize_observation (:222-225). */
+typedef struct AgxHp2Sensor {
+    int32_t kind;               /* AGX_SENSOR_* */
+    int32_t width, height, num_sensors;
+    int32_t calculate_depth;    /* camera: depth image (1) or range image (0) */
+    int32_t return_pointcloud, pointcloud_in_world_frame, segmentation;
+    int32_t fuse_epilogue;      /* apply range limits + normalisation in the kernel (noise disabled) */
+    int32_t normalize_range;
+    int32_t c_x, c_y;           /* warp_cam.py:63-64 */
+    float kinv[9];              /* upper-left 3x3 of K^-1 (warp_cam.py:43-62) */
+    float far_plane;            /* = max_range (warp_cam.py:21) */
+    float max_range, min_range, far_out_of_range_value, near_out_of_range_value;
+    float frame_quat[4];        /* sensor data frame (warp_sensor.py:100-105) */
+    int32_t robot_pose_stride;  /* floats between robot poses (13 for robot_state_tensor rows) */
+    int32_t pad_;
+    const float* robot_pose;    /* [E,stride] x y z qx qy qz qw ... */
+    const float* mount;         /* [E,S,7] sensor_local_position + sensor_local_orientation */
+    const float* ray_table;     /* [H,W,3] LiDAR ray vectors (warp_lidar.py:40-64) or NULL */
+    float* pixels;              /* [E,S,H,W] or [E,S,H,W,3]  (depth_range_pixels) */
+    int32_t* seg_pixels;        /* [E,S,H,W] (segmentation_pixels) or NULL */
+} AgxHp2Sensor;
+
+/* bytes the caller must allocate for scene->tris / nodes / leaf_object (per env) */
+uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which /*0 tris, 1 nodes, 2 leaf_object*/);
+
+/* Re-transform triangles + rebuild the BVH of the envs selected by `mask` ([E] bool, NULL = all).
+ * Replaces WarpEnv.reset_idx (warp_env_manager.py:40-54). */
+int agx_hp2_update_scene(const AgxHp2Scene* scene, const uint8_t* mask, void* stream);
+
+/* Cast every ray of every sensor of every env.  Replaces WarpSensor.update. */
+int agx_hp2_cast(const AgxHp2Scene* scene, const AgxHp2Sensor* sensor, void* stream);
 
 #ifdef __cplusplus
 }

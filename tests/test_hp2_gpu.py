@@ -1,0 +1,196 @@
+"""HP2 parity tests proper: CUDA ray caster (through the C ABI) vs the brute-force oracle on the
+same scenes.  Bar: depth / range / pointcloud BIT-IDENTICAL, segmentation ids bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hp2_oracle as RO
+from aerial_gym_simulator_b200 import _lib
+from aerial_gym_simulator_b200.hp2 import RayScene, RaySensor
+from tests import _hp2_common as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(sc, cfg, seed=1, S=1, mount_seed=None):
+    pose_d = sc["pose"].to(DEV)
+    scene = RayScene(sc["templates"], [0] * len(sc["templates"]), [1] * len(sc["templates"]), sc["tm"], sc["ctr"], pose_d, DEV)
+    scene.update()
+    E = sc["E"]
+    robot = H.robot_poses(E, seed)
+    mount = H.mounts(E, S, mount_seed) if mount_seed is not None else None
+    pc = cfg.return_pointcloud
+    pix = torch.zeros((E, S, cfg.height, cfg.width, 3) if pc else (E, S, cfg.height, cfg.width), device=DEV)
+    seg = torch.zeros(E, S, cfg.height, cfg.width, dtype=torch.int32, device=DEV) if cfg.segmentation_camera else None
+    robot_d = robot.to(DEV)
+    sensor = RaySensor(cfg, scene, robot_d, pix, seg, mount.to(DEV) if mount is not None else None)
+    return scene, sensor, robot, mount, robot_d
+
+
+def oracle_cast(sc, cfg, sensor, robot, mount, S=1):
+    tris, segs, cnt = H.oracle_tris(sc)
+    so, table = H.oracle_sensor(cfg, fuse=not sensor.noise_enabled)
+    if sensor.ray_table is not None:
+        assert np.abs(table - sensor.ray_table.cpu().numpy()).max() <= 1.2e-7
+        table = sensor.ray_table.cpu().numpy()  # identical inputs on both sides
+    if mount is None:
+        m = np.zeros((sc["E"], S, 7), np.float32)
+        m[..., 6] = 1
+    else:
+        m = mount.numpy()
+    return RO.cast(so, robot[:, :7].numpy(), m, table, tris, segs, cnt)
+
+
+def check(sensor, ref_pix, ref_seg):
+    torch.cuda.synchronize()
+    got = sensor.pixels.cpu().numpy()
+    assert np.array_equal(got, ref_pix), f"{(got != ref_pix).sum()} / {got.size} pixels differ; max |d| {np.abs(got - ref_pix).max()}"
+    if ref_seg is not None:
+        assert np.array_equal(sensor.seg_pixels.cpu().numpy(), ref_seg)
+
+
+CAM_VARIANTS = {
+    "depth_seg_norm": dict(),
+    "range_seg": dict(calculate_depth=False),
+    "depth_noseg_raw": dict(segmentation_camera=False, normalize_range=False, far_out_of_range_value=-1.0,
+                            near_out_of_range_value=-1.0),
+    "pointcloud_sensor_frame": dict(return_pointcloud=True),
+    "pointcloud_world": dict(return_pointcloud=True, pointcloud_in_world_frame=True, normalize_range=False),
+    "odd_size": dict(height=37, width=53),
+}
+
+
+@pytest.mark.parametrize("variant", list(CAM_VARIANTS))
+def test_camera_matches_oracle(variant):
+    cfg = H.cfg_variant(H.CamCfg, **CAM_VARIANTS[variant])
+    sc = H.make_scene(6, 44, seed=11, parked=9)  # env_with_obstacles-sized scene, some obstacles parked
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=2, mount_seed=3)
+    sensor.capture()
+    ref_pix, ref_seg = oracle_cast(sc, cfg, sensor, robot, mount)
+    check(sensor, ref_pix, ref_seg)
+    if ref_seg is not None:
+        assert (ref_seg >= 100).mean() > 0.05  # the scene is actually visible
+
+
+@pytest.mark.parametrize("pc,world", [(False, False), (True, False), (True, True)])
+def test_lidar_matches_oracle(pc, world):
+    cfg = H.cfg_variant(H.LidarCfg, return_pointcloud=pc, pointcloud_in_world_frame=world,
+                        normalize_range=not (pc and world))
+    sc = H.make_scene(5, 30, seed=21, extent=6.0)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=4)
+    sensor.capture()
+    ref_pix, ref_seg = oracle_cast(sc, cfg, sensor, robot, mount)
+    check(sensor, ref_pix, ref_seg)
+
+
+def test_multiple_sensors_per_robot():
+    cfg = H.cfg_variant(H.CamCfg, num_sensors=3, height=20, width=24)
+    sc = H.make_scene(4, 20, seed=31)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=5, S=3, mount_seed=6)
+    sensor.capture()
+    ref_pix, ref_seg = oracle_cast(sc, cfg, sensor, robot, mount, S=3)
+    check(sensor, ref_pix, ref_seg)
+    assert not np.array_equal(ref_pix[:, 0], ref_pix[:, 1])
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 64, 65, 300])
+def test_object_counts_shared_memory_path(K):
+    cfg = H.cfg_variant(H.CamCfg, height=16, width=24)
+    sc = H.make_scene(3, K, seed=40 + K)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=7)
+    sensor.capture()
+    check(sensor, *oracle_cast(sc, cfg, sensor, robot, mount))
+
+
+def test_large_scene_global_memory_path():
+    """1024 boxes / env = 12,288 triangles (BASELINE config #3 stress scene): ~590 KB per env,
+    does not fit shared memory -> L2 traversal path."""
+    cfg = H.cfg_variant(H.CamCfg, height=12, width=16)
+    sc = H.make_scene(2, 1024, seed=50, extent=8.0)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=8)
+    sensor.capture()
+    check(sensor, *oracle_cast(sc, cfg, sensor, robot, mount))
+
+
+def test_masked_scene_update_after_reset():
+    """Only the masked envs are re-transformed / rebuilt (WarpEnv.reset_idx refits env_ids only)."""
+    cfg = H.cfg_variant(H.CamCfg, height=16, width=24)
+    sc = H.make_scene(4, 12, seed=60)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=9)
+    sensor.capture()
+    before = sensor.pixels.clone()
+    g = torch.Generator().manual_seed(1)
+    new_pose = sc["pose"].clone()
+    new_pose[..., 0:3] = (torch.rand(4, 12, 3, generator=g) * 2 - 1) * 5
+    scene.obj_pose.copy_(new_pose.to(DEV))
+    mask = torch.tensor([True, False, True, False], device=DEV)
+    scene.update(mask)
+    sensor.capture()
+    torch.cuda.synchronize()
+    assert torch.equal(sensor.pixels[1], before[1]) and torch.equal(sensor.pixels[3], before[3])
+    sc2 = dict(sc)
+    mixed = sc["pose"].clone()
+    mixed[0], mixed[2] = new_pose[0], new_pose[2]
+    sc2["pose"] = mixed
+    check(sensor, *oracle_cast(sc2, cfg, sensor, robot, mount))
+
+
+def test_robot_state_view_and_determinism():
+    """robot_pose is read straight from the [N,13] robot_state_tensor rows; two captures are
+    bit-identical."""
+    cfg = H.cfg_variant(H.CamCfg, height=24, width=32)
+    sc = H.make_scene(8, 44, seed=70)
+    scene, sensor, robot, mount, robot_d = build(sc, cfg, seed=10)
+    sensor.capture()
+    a = sensor.pixels.clone()
+    sensor.capture()
+    torch.cuda.synchronize()
+    assert torch.equal(a, sensor.pixels)
+    robot_d[:, 0:3] += 0.5  # sensor holds the view: next capture sees the new pose
+    sensor.capture()
+    robot2 = robot.clone()
+    robot2[:, 0:3] += 0.5
+    check(sensor, *oracle_cast(sc, cfg, sensor, robot2, mount))
+
+
+def test_full_size_properties():
+    """North-star depth config (8192 envs x 64x48, 44-box scenes): invariants that do not need the
+    oracle at that size -- value ranges, miss value, seg ids from the env's own objects only,
+    bit determinism, and agreement with the oracle on a sampled subset of envs."""
+    E, K = 8192, 44
+    cfg = H.CamCfg
+    sc = H.make_scene(E, K, seed=80, parked=6)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=11)
+    sensor.capture()
+    torch.cuda.synchronize()
+    pix, seg = sensor.pixels, sensor.seg_pixels
+    assert torch.isfinite(pix).all()
+    hit = seg >= 0
+    assert ((pix[hit] >= 0.02 - 1e-7) & (pix[hit] <= 1.0)).all() or ((pix[hit] == -1.0) | (pix[hit] >= 0.02 - 1e-7)).all()
+    assert (pix[~hit] == 1.0).all() and (seg[~hit] == -2).all()
+    lo = torch.tensor(sc["ctr"].min(axis=1), device=DEV).view(E, 1, 1, 1)
+    hi = torch.tensor(sc["ctr"].max(axis=1), device=DEV).view(E, 1, 1, 1)
+    assert ((seg >= lo) & (seg <= hi))[hit].all()
+    a = pix.clone()
+    sensor.capture()
+    torch.cuda.synchronize()
+    assert torch.equal(a, sensor.pixels)
+    sub = [0, 1, 4095, 8191]
+    sc_sub = dict(sc, E=len(sub), pose=sc["pose"][sub], tm=sc["tm"][sub], ctr=sc["ctr"][sub])
+    tris, segs, cnt = H.oracle_tris(sc_sub)
+    so, _ = H.oracle_sensor(cfg)
+    m = np.zeros((len(sub), 1, 7), np.float32)
+    m[..., 6] = 1
+    ref_pix, ref_seg = RO.cast(so, robot[sub, :7].numpy(), m, None, tris, segs, cnt)
+    assert np.array_equal(pix[sub].cpu().numpy(), ref_pix) and np.array_equal(seg[sub].cpu().numpy(), ref_seg)
+
+
+def test_error_paths():
+    sc = H.make_scene(2, 4, seed=90)
+    with pytest.raises(ValueError):
+        RayScene([np.zeros((13, 9), np.float32)], [0], [1], sc["tm"] * 0, sc["ctr"], sc["pose"].to(DEV), DEV, tris_per_object=12)
+    scene = RayScene(sc["templates"], [0] * 5, [1] * 5, sc["tm"], sc["ctr"], sc["pose"].to(DEV), DEV)
+    scene.c.leaves_pow2 = 3
+    with pytest.raises(_lib.AgxError, match="leaves_pow2"):
+        scene.update()
