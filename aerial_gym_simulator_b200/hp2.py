@@ -199,54 +199,3 @@ class RaySensor:
 
     def rays_per_frame(self):
         return self.scene.E * self.cfg.num_sensors * self.cfg.height * self.cfg.width
-
-
-def _smoke(dev="cuda:0"):
-    """Tiny HP2 invocation checked against the brute-force oracle (called by __graft_entry__.smoke)."""
-    from oracle import hp2_oracle as RO  # checker only
-
-    E, K = 4, 6
-    g = torch.Generator().manual_seed(0)
-    pose = torch.zeros(E, K, 13)
-    pose[..., 0:3] = torch.rand(E, K, 3, generator=g) * 6 - 3
-    q = torch.randn(E, K, 4, generator=g)
-    pose[..., 3:7] = q / q.norm(dim=-1, keepdim=True)
-    templates = [box_triangles((0.8, 0.6, 1.0)), box_triangles((0.3, 2.0, 0.4))]
-    tm = (torch.arange(E * K).reshape(E, K) % 2).numpy()
-    ctr = (100 + torch.arange(E * K).reshape(E, K)).numpy()
-    pose_d = pose.to(dev)
-    scene = RayScene(templates, [0, 0], [1, 1], tm, ctr, pose_d, dev)
-    scene.update()
-
-    class cam:
-        sensor_type, num_sensors, height, width = "camera", 1, 24, 32
-        horizontal_fov_deg, max_range, min_range = 87.0, 10.0, 0.2
-        calculate_depth, return_pointcloud, pointcloud_in_world_frame = True, False, False
-        segmentation_camera, normalize_range = True, True
-        far_out_of_range_value, near_out_of_range_value = 10.0, -10.0
-        euler_frame_rot_deg = [-90.0, 0, -90.0]
-
-    robot = torch.zeros(E, 13)
-    robot[:, 0:3] = torch.tensor([-5.0, 0.0, 0.0])
-    robot[:, 6] = 1.0
-    robot_d = robot.to(dev)
-    pix = torch.zeros(E, 1, 24, 32, device=dev)
-    seg = torch.zeros(E, 1, 24, 32, dtype=torch.int32, device=dev)
-    sensor = RaySensor(cam, scene, robot_d, pix, seg)
-    sensor.capture()
-    torch.cuda.synchronize()
-    offs = np.array([0, 12, 24], np.int32)
-    tris, segs, cnt = RO.build_world_tris(pose[..., :7].numpy(), tm, ctr, offs, np.concatenate(templates), np.zeros(24, np.int32),
-                                          np.ones(24, np.int32), K * 12)
-    so = RO.Hp2oSensor()
-    for f, _ in RO.Hp2oSensor._fields_:
-        if hasattr(sensor.c, f):
-            setattr(so, f, getattr(sensor.c, f))
-    mount = np.zeros((E, 1, 7), np.float32)
-    mount[..., 6] = 1
-    ref_pix, ref_seg = RO.cast(so, robot[:, :7].numpy(), mount, None, tris, segs, cnt)
-    assert np.array_equal(pix.cpu().numpy(), ref_pix), "HP2 smoke: depth not bit-identical to the oracle"
-    assert np.array_equal(seg.cpu().numpy(), ref_seg), "HP2 smoke: segmentation mismatch"
-    hits = int((ref_seg >= 0).sum())
-    assert hits > 0
-    print(f"smoke HP2 ok: {ref_pix.size} rays, {hits} hits, bit-identical to the oracle")
