@@ -1,0 +1,81 @@
+"""config/asset_config/env_object_config.py -- obstacle asset parameter classes (the box-shaped
+families the navigation envs ship: panels, objects, six walls)."""
+import numpy as np
+
+from . import RESOURCES_DIRECTORY
+
+PI = np.pi
+_ENV_ASSETS = f"{RESOURCES_DIRECTORY}/models/environment_assets"
+
+THIN_SEMANTIC_ID, TREE_SEMANTIC_ID, OBJECT_SEMANTIC_ID, PANEL_SEMANTIC_ID = 1, 2, 3, 20
+FRONT_WALL_SEMANTIC_ID, BACK_WALL_SEMANTIC_ID, LEFT_WALL_SEMANTIC_ID = 9, 10, 11
+RIGHT_WALL_SEMANTIC_ID, BOTTOM_WALL_SEMANTIC_ID, TOP_WALL_SEMANTIC_ID = 12, 13, 14
+
+
+def _ratio(pos_lo, pos_hi, eul_lo=(0, 0, 0), eul_hi=(0, 0, 0)):
+    lo = list(pos_lo) + list(eul_lo) + [1.0] + [0.0] * 6
+    hi = list(pos_hi) + list(eul_hi) + [1.0] + [0.0] * 6
+    return lo, hi
+
+
+class asset_state_params:
+    num_assets = 1
+    asset_folder = _ENV_ASSETS
+    file = None  # None -> files are picked at random from the folder
+    min_position_ratio = [0.5, 0.5, 0.5]
+    max_position_ratio = [0.5, 0.5, 0.5]
+    collision_mask = 1
+    disable_gravity = False
+    density = 0.001
+    angular_damping = 0.1
+    linear_damping = 0.1
+    max_angular_velocity = 100.0
+    max_linear_velocity = 100.0
+    collapse_fixed_joints = True
+    fix_base_link = True
+    specific_filepath = None
+    color = None
+    keep_in_env = False
+    body_semantic_label = 0
+    link_semantic_label = 0
+    per_link_semantic = False
+    semantic_masked_links = {}
+    semantic_id = -1
+    use_collision_mesh_instead_of_visual = False
+    min_state_ratio, max_state_ratio = _ratio((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+
+
+class panel_asset_params(asset_state_params):
+    num_assets = 3
+    asset_folder = f"{_ENV_ASSETS}/panels"
+    min_position_ratio, max_position_ratio = [0.3, 0.05, 0.05], [0.85, 0.95, 0.95]
+    min_euler_angles, max_euler_angles = [0.0, 0.0, -PI / 3.0], [0.0, 0.0, PI / 3.0]
+    min_state_ratio, max_state_ratio = _ratio((0.3, 0.05, 0.05), (0.85, 0.95, 0.95), (0, 0, -PI / 3.0), (0, 0, PI / 3.0))
+    keep_in_env = True
+    semantic_id = -1  # assigned incrementally per instance
+    color = [170, 66, 66]
+
+
+class object_asset_params(asset_state_params):
+    num_assets = 35
+    asset_folder = f"{_ENV_ASSETS}/objects"
+    min_state_ratio, max_state_ratio = _ratio((0.30, 0.05, 0.05), (0.85, 0.9, 0.9), (-PI, -PI, -PI), (PI, PI, PI))
+    keep_in_env = False
+    semantic_id = -1
+    color = [80, 255, 100]
+
+
+def _wall(fname, ratio, sem):
+    lo, hi = _ratio(ratio, ratio)
+    return type(fname.replace(".urdf", ""), (asset_state_params,), dict(
+        num_assets=1, asset_folder=f"{_ENV_ASSETS}/walls", file=fname, min_position_ratio=list(ratio),
+        max_position_ratio=list(ratio), min_state_ratio=lo, max_state_ratio=hi, keep_in_env=True,
+        semantic_id=sem, color=[100, 200, 210]))
+
+
+left_wall = _wall("left_wall.urdf", (0.5, 1.0, 0.5), LEFT_WALL_SEMANTIC_ID)
+right_wall = _wall("right_wall.urdf", (0.5, 0.0, 0.5), RIGHT_WALL_SEMANTIC_ID)
+top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_ID)
+bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID)
+front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID)
+back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID)

@@ -1,0 +1,65 @@
+"""config/env_config/{empty_env,env_with_obstacles}.py"""
+from .asset_config import (back_wall, bottom_wall, front_wall, left_wall, object_asset_params, panel_asset_params,
+                           right_wall, top_wall)
+
+
+class EmptyEnvCfg:
+    class env:
+        num_envs = 3
+        num_env_actions = 0
+        env_spacing = 1.0
+        num_physics_steps_per_env_step_mean = 1
+        num_physics_steps_per_env_step_std = 0
+        render_viewer_every_n_steps = 10
+        collision_force_threshold = 0.010
+        manual_camera_trigger = False
+        reset_on_collision = True
+        create_ground_plane = False
+        sample_timestep_for_latency = True
+        perturb_observations = True
+        keep_same_env_for_num_episodes = 1
+        write_to_sim_at_every_timestep = False
+        use_warp = False
+        e_s = env_spacing
+        lower_bound_min = [-e_s, -e_s, -e_s]
+        lower_bound_max = [-e_s, -e_s, -e_s]
+        upper_bound_min = [e_s, e_s, e_s]
+        upper_bound_max = [e_s, e_s, e_s]
+
+    class env_config:
+        include_asset_type = {}
+        asset_type_to_dict_map = {}
+
+
+class EnvWithObstaclesCfg:
+    class env:
+        num_envs = 64
+        num_env_actions = 4
+        env_spacing = 5.0
+        num_physics_steps_per_env_step_mean = 10
+        num_physics_steps_per_env_step_std = 0
+        render_viewer_every_n_steps = 1
+        reset_on_collision = True
+        collision_force_threshold = 0.05
+        create_ground_plane = False
+        sample_timestep_for_latency = True
+        perturb_observations = True
+        keep_same_env_for_num_episodes = 1
+        write_to_sim_at_every_timestep = False
+        use_warp = True
+        lower_bound_min = [-2.0, -4.0, -3.0]
+        lower_bound_max = [-1.0, -2.5, -2.0]
+        upper_bound_min = [9.0, 2.5, 2.0]
+        upper_bound_max = [10.0, 4.0, 3.0]
+
+    class env_config:
+        include_asset_type = {
+            "panels": True, "tiles": False, "thin": False, "trees": False, "objects": True,
+            "left_wall": True, "right_wall": True, "back_wall": True, "front_wall": True,
+            "top_wall": True, "bottom_wall": True,
+        }
+        asset_type_to_dict_map = {
+            "panels": panel_asset_params, "objects": object_asset_params,
+            "left_wall": left_wall, "right_wall": right_wall, "back_wall": back_wall,
+            "front_wall": front_wall, "bottom_wall": bottom_wall, "top_wall": top_wall,
+        }

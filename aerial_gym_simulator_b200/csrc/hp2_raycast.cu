@@ -236,8 +236,9 @@ hp2_update_scene_kernel(const __grid_constant__ AgxHp2Scene sc, const uint8_t* _
     }
     float* gn = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
     for (int i = tid; i < (2 * P - 1) * kNodeFloats; i += nt) gn[i] = s_nodes[i];
-    int32_t* gl = sc.leaf_object + (size_t)e * P;
-    for (int i = tid; i < P; i += nt) gl[i] = s_val[i];
+    const int leaf_stride = P < 4 ? 4 : P;
+    int32_t* gl = sc.leaf_object + (size_t)e * leaf_stride;
+    for (int i = tid; i < leaf_stride; i += nt) gl[i] = (i < P) ? s_val[i] : -1;
 }
 
 // =========================================================================================
@@ -250,14 +251,20 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded spin: a mis-programmed copy must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
 }
 // TMA 1-D bulk copy global -> shared, completion on mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -368,7 +375,8 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
     const int K = sc.num_objects, P = sc.leaves_pow2, L = sc.tris_per_object;
     const int W = sn.width, H = sn.height, S = sn.num_sensors;
     const uint32_t node_bytes = (uint32_t)((2 * P - 1) * kNodeFloats * 4);
-    const uint32_t leaf_bytes = (uint32_t)(P * 4);
+    const int leaf_stride = P < 4 ? 4 : P;  // 16-byte granularity of cp.async.bulk
+    const uint32_t leaf_bytes = (uint32_t)(leaf_stride * 4);
     const uint32_t tri_bytes = (uint32_t)((size_t)K * L * kTriFloats * 4);
     float* s_nodes = reinterpret_cast<float*>(smem_raw);
     int32_t* s_leaf = reinterpret_cast<int32_t*>(smem_raw + ((node_bytes + 15u) & ~15u));
@@ -388,7 +396,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         const int c = (int)(es % S);
         const int e = (int)(es / S);
         const float* g_nodes = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
-        const int32_t* g_leaf = sc.leaf_object + (size_t)e * P;
+        const int32_t* g_leaf = sc.leaf_object + (size_t)e * leaf_stride;
         const float* g_tris = sc.tris + (size_t)e * K * L * kTriFloats;
         const float* nodes = g_nodes;
         const int32_t* leaf = g_leaf;
@@ -480,7 +488,7 @@ inline int next_pow2(int v) {
 }
 inline size_t scene_smem_bytes(int K, int P, int L) {
     size_t nb = ((size_t)(2 * P - 1) * kNodeFloats * 4 + 15) & ~(size_t)15;
-    size_t lb = ((size_t)P * 4 + 15) & ~(size_t)15;
+    size_t lb = (size_t)(P < 4 ? 4 : P) * 4;
     return nb + lb + (size_t)K * L * kTriFloats * 4;
 }
 
@@ -504,7 +512,7 @@ uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which) {
     switch (which) {
         case 0: return (uint64_t)num_objects * tris_per_object * kTriFloats * 4;
         case 1: return (uint64_t)(2 * P - 1) * kNodeFloats * 4;
-        case 2: return (uint64_t)P * 4;
+        case 2: return (uint64_t)(P < 4 ? 4 : P) * 4;
         default: return 0;
     }
 }

@@ -1,0 +1,14 @@
+"""EnvManager: the orchestrator surface of the reference (env_manager/env_manager.py) over the
+B200 engines.  Registers the env / sim configs (env_manager/__init__.py, sim/__init__.py)."""
+from ..config import env_config as _ec
+from ..config import sim_config as _sc
+from ..registry import env_config_registry, sim_config_registry
+
+env_config_registry.register("empty_env", _ec.EmptyEnvCfg)
+env_config_registry.register("env_with_obstacles", _ec.EnvWithObstaclesCfg)
+sim_config_registry.register("base_sim", _sc.BaseSimConfig)
+sim_config_registry.register("base_sim_headless", _sc.BaseSimHeadlessConfig)
+sim_config_registry.register("base_sim_2ms", _sc.SimCfg2Ms)
+sim_config_registry.register("base_sim_4ms", _sc.SimCfg4Ms)
+
+from .env_manager import EnvManager  # noqa: E402,F401

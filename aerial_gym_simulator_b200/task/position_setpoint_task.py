@@ -1,0 +1,99 @@
+"""PositionSetpointTask (task/position_setpoint_task/position_setpoint_task.py:20-282).
+
+step() is ONE C-ABI call (agx_hp1_position_task_step): physics, sim_steps, reward + crash,
+truncation, reset of finished envs and the 13-D observation are fused in the HP1 kernel; the
+tensors returned are the same objects every call, mutated in place, like the reference.
+
+task_config.args:
+  {"reset_rng": "device"}  (default) in-kernel Philox resets -> single launch, no host sync;
+  {"reset_rng": "torch"}   reference-order torch draws; the host reads the any-reset flag each
+                           step exactly where the reference syncs (env_manager.py:364-375)."""
+import numpy as np
+import torch
+
+from ..sim import SimBuilder
+from .base_task import BaseTask
+from .spaces import Box, Dict
+
+
+class PositionSetpointTask(BaseTask):
+    def __init__(self, task_config, seed=None, num_envs=None, headless=None, device=None, use_warp=None):
+        for k, v in (("seed", seed), ("num_envs", num_envs), ("headless", headless), ("device", device), ("use_warp", use_warp)):
+            if v is not None:
+                setattr(task_config, k, v)
+        super().__init__(task_config)
+        self.device = self.task_config.device
+        for key in list(self.task_config.reward_parameters.keys()):
+            self.task_config.reward_parameters[key] = torch.as_tensor(self.task_config.reward_parameters[key], device=self.device)
+        args = dict(self.task_config.args or {})
+        args.setdefault("seed", self._seed)
+        self.sim_env = SimBuilder().build_env(
+            sim_name=self.task_config.sim_name, env_name=self.task_config.env_name, robot_name=self.task_config.robot_name,
+            controller_name=self.task_config.controller_name, args=args, device=self.device,
+            num_envs=self.task_config.num_envs, use_warp=self.task_config.use_warp, headless=self.task_config.headless)
+        env, eng = self.sim_env, self.sim_env.engine
+        if env.spec.num_actions != self.task_config.action_space_dim:
+            raise ValueError("task action_space_dim does not match the controller's action count")
+        eng.cfg.episode_len_steps = int(self.task_config.episode_len_steps)
+        self.num_envs = env.num_envs
+        self.actions = torch.zeros((self.num_envs, self.task_config.action_space_dim), device=self.device)
+        self.prev_actions = torch.zeros_like(self.actions)
+        self.counter = 0
+        self.target_position = eng.target_position  # [N,3], read by the kernel
+        self.obs_dict = env.get_obs()
+        self.obs_dict["num_obstacles_in_env"] = 1
+        self.terminations = self.obs_dict["crashes"]
+        self.truncations = self.obs_dict["truncations"]
+        self.rewards = eng.reward
+        self.observation_space = Dict({"observations": Box(low=-1.0, high=1.0, shape=(13,), dtype=np.float32)})
+        self.action_space = Box(low=-1.0, high=1.0, shape=(self.task_config.action_space_dim,), dtype=np.float32)
+        self.task_obs = {
+            "observations": eng.obs,
+            "priviliged_obs": torch.zeros((self.num_envs, self.task_config.privileged_observation_space_dim), device=self.device),
+            "collisions": torch.zeros((self.num_envs, 1), device=self.device),
+            "rewards": self.rewards,
+            "terminations": self.terminations,
+            "truncations": self.truncations,
+        }
+        self.infos = {}
+
+    def close(self):
+        self.sim_env.delete_env()
+
+    def reset(self):
+        self.target_position[:, 0:3] = 0.0
+        self.infos = {}
+        self.sim_env.reset()
+        return self.get_return_tuple()
+
+    def reset_idx(self, env_ids):
+        self.target_position[:, 0:3] = 0.0
+        self.infos = {}
+        self.sim_env.reset_idx(env_ids)
+
+    def render(self):
+        return None
+
+    def step(self, actions):
+        self.counter += 1
+        env, eng = self.sim_env, self.sim_env.engine
+        if actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.float().contiguous()
+        self.prev_actions, self.actions = self.actions, actions  # the reference copies; nobody reads prev afterwards
+        n = env.sample_physics_steps()  # consumes random.gauss like env_manager.py:417-425
+        dist = env._draw_disturbance() if (env.spec.enable_disturbance and n == 1) else None
+        if env.spec.enable_disturbance and n != 1:
+            raise NotImplementedError("fused task step with per-substep disturbance draws: use EnvManager.step")
+        eng.position_task_step(actions, disturbance=dist, physics_steps=n)
+        env.step_counter += 1
+        if env.reset_rng == "torch":
+            # reference flow: host decides, draws only when some env resets (env_manager.py:364-375)
+            if int(eng.any_reset[0].item()) != 0:
+                eng.any_reset.zero_()
+                env.reset_idx(eng.reset_mask.nonzero(as_tuple=False).squeeze(-1))  # ends with the all-env refresh + obs
+        env.render(render_components="sensors")
+        self.infos = {}
+        return self.get_return_tuple()
+
+    def get_return_tuple(self):
+        return (self.task_obs, self.rewards, self.terminations, self.truncations, self.infos)

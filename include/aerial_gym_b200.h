@@ -213,7 +213,7 @@ typedef struct AgxHp2Scene {
     /* device storage owned by the caller, layout defined by the library: */
     float* tris;                /* [E][K*L][12]  (v0.xyz, seg bits | e1.xyz, 0 | e2.xyz, 0) */
     float* nodes;               /* [E][2P-1][8]  (lo.xyz, 0 | hi.xyz, 0), heap order, leaves last */
-    int32_t* leaf_object;       /* [E][P] object index of each Morton-sorted leaf, -1 = empty */
+    int32_t* leaf_object;       /* [E][max(P,4)] object index of each Morton-sorted leaf, -1 = empty */
 } AgxHp2Scene;
 
 #define AGX_SENSOR_CAMERA 0

@@ -1,0 +1,82 @@
+"""CPU tests of the host-side mirror of the reference surface: registries, configs, URDF-derived
+robot constants, the MultirotorSpec -> AgxHp1Config packing.  No GPU, no compute calls."""
+import os
+
+import numpy as np
+import pytest
+
+from aerial_gym_simulator_b200 import _lib, urdf
+from aerial_gym_simulator_b200.config import RESOURCES_DIRECTORY
+from aerial_gym_simulator_b200.config.env_config import EmptyEnvCfg, EnvWithObstaclesCfg
+from aerial_gym_simulator_b200.config.sim_config import BaseSimConfig
+from aerial_gym_simulator_b200.hp1 import build_config
+from aerial_gym_simulator_b200.registry import (controller_registry, env_config_registry, robot_registry,
+                                                sim_config_registry, task_registry)
+import aerial_gym_simulator_b200.task  # noqa: F401  (registers everything)
+
+
+def test_registry_surface_matches_reference_names():
+    # control/__init__.py:42-99 of the reference registers these 22 names
+    want = {"no_control", "rov_fully_actuated_control"}
+    for fam in ("lee", "magpie", "lmf2", "octarotor"):
+        want |= {f"{fam}_{k}_control" for k in ("position", "velocity", "attitude", "rates", "acceleration")}
+    assert want <= set(controller_registry.get_controller_names())
+    assert {"base_quadrotor", "base_octarotor", "base_quad_root_link_control", "lmf2", "x500"} <= set(robot_registry.get_robot_names())
+    assert "position_setpoint_task" in task_registry.get_task_names()
+    assert {"empty_env", "env_with_obstacles"} <= set(env_config_registry.get_env_names())
+    assert "base_sim" in sim_config_registry.get_sim_names()
+    with pytest.raises(ValueError):
+        controller_registry.make_controller("nope", 4, "cpu")
+    with pytest.raises(ValueError):
+        robot_registry.make_robot("nope", "lee_attitude_control", EmptyEnvCfg, "cpu")
+
+
+def test_urdf_composite_inertia_quad():
+    """SURVEY 8c hand derivation: m = 0.25 kg, J = diag(8.45e-4, 8.45e-4, 1.69e-3) about a centred COM."""
+    m = urdf.parse_urdf(os.path.join(RESOURCES_DIRECTORY, "robots/quad/quad.urdf"))
+    mass, com, J = m.composite_inertia()
+    assert abs(mass - 0.25) < 1e-12 and np.abs(com).max() < 1e-12
+    assert np.allclose(np.diag(J), [8.45e-4, 8.45e-4, 1.69e-3], rtol=1e-9) and np.abs(J - np.diag(np.diag(J))).max() < 1e-15
+    order = m.body_order()
+    assert order[0] == "base_link" and order[5:9] == ["motor_0", "motor_1", "motor_2", "motor_3"]  # application_mask 5..8
+
+
+def test_wrench_map_reproduces_quad_allocation_matrix():
+    """Appendix B: for base_quadrotor the per-link force/torque reduction equals the config's
+    allocation matrix (base_quad_config.py:166-173)."""
+    robot, cfg = robot_registry.make_robot("base_quadrotor", "lee_attitude_control", EmptyEnvCfg, "cpu")
+    spec = robot.make_spec(BaseSimConfig, EmptyEnvCfg)
+    assert np.allclose(spec.wrench_map(), np.asarray(cfg.control_allocator_config.allocation_matrix), atol=1e-12)
+    # tilted octarotor: thrust axes come from the URDF joint rotations
+    robot8, cfg8 = robot_registry.make_robot("base_octarotor", "octarotor_velocity_control", EmptyEnvCfg, "cpu")
+    spec8 = robot8.make_spec(BaseSimConfig, EmptyEnvCfg)
+    W = spec8.wrench_map()
+    assert np.allclose(W[0:3], np.asarray(cfg8.control_allocator_config.allocation_matrix)[0:3], atol=1e-6)
+    assert spec8.randomize_params and spec8.num_actions == 4 and not spec8.use_rps
+
+
+def test_spec_to_abi_config_packing():
+    robot, _ = robot_registry.make_robot("base_quadrotor", "lee_position_control", EnvWithObstaclesCfg, "cpu")
+    spec = robot.make_spec(BaseSimConfig, EnvWithObstaclesCfg)
+    c = build_config(spec, 128, physics_steps=10, seed=0x1_0000_0002, env_id_offset=256)
+    assert (c.num_envs, c.num_motors, c.controller, c.num_actions, c.physics_steps) == (128, 4, _lib.CTRL_POSITION, 4, 10)
+    assert c.seed == 0x1_0000_0002 and c.env_id_offset == 256
+    assert c.flags & _lib.F_USE_RPS and c.flags & _lib.F_MOTOR_RK4 and c.flags & _lib.F_DISCRETE_MIX
+    assert abs(c.mass - 0.25) < 1e-7 and abs(c.inertia[8] - 1.69e-3) < 1e-9 and abs(c.inertia_inv[0] - 1 / 8.45e-4) < 1e-2
+    # pinv of the rank-4 quad allocation matrix: f = pinv(A) w reproduces collective thrust
+    P = np.array(list(c.alloc_pinv)[:24]).reshape(4, 6)
+    assert np.allclose(P @ np.array([0, 0, 4.0, 0, 0, 0]), [1, 1, 1, 1], atol=1e-5)
+    assert list(c.bounds_lo_min) == [-2.0, -4.0, -3.0] and list(c.bounds_hi_max) == [10.0, 4.0, 3.0]
+    assert abs(c.K_rot[2] - 0.5) < 1e-7  # mid-point of [0.4, 0.6]
+
+
+def test_fused_controllers_refuse_direct_calls():
+    ctrl, cfg = controller_registry.make_controller("lee_velocity_control", 8, "cpu")
+    assert ctrl.CONTROLLER_ID == _lib.CTRL_VELOCITY and cfg.num_actions == 4
+    with pytest.raises(RuntimeError, match="fused"):
+        ctrl(None)
+
+
+def test_root_link_no_control_is_rejected():
+    with pytest.raises(ValueError, match="root_link"):
+        robot_registry.make_robot("base_quad_root_link_control", "no_control", EmptyEnvCfg, "cpu")
