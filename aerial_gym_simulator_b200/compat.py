@@ -1,0 +1,67 @@
+"""Drop-in import names.  ``install()`` makes the reference's import paths resolve to this
+package so its trainers / examples run unchanged:
+
+    import aerial_gym_simulator_b200.compat as compat; compat.install()
+    import isaacgym                                   # shim: gymapi / gymutil / gymtorch names only
+    from aerial_gym.registry.task_registry import task_registry
+    from aerial_gym.sim.sim_builder import SimBuilder
+    from aerial_gym.utils.helpers import parse_arguments
+
+(reference: aerial_gym/__init__.py imports isaacgym first; rl_training/* import the paths above.)"""
+import sys
+import types
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    if getattr(sys.modules.get("aerial_gym"), "_b200_compat", False):
+        return
+    from . import config, control, env_manager, registry, robots, sim, task, utils
+    from .config import (PACKAGE_DIRECTORY, asset_config, controller_config, env_config, robot_config, sensor_config,
+                         sim_config, task_config)
+    import importlib
+
+    R = {n: importlib.import_module(f"{__package__}.registry.{n}") for n in
+         ("task_registry", "robot_registry", "controller_registry", "env_registry", "sim_registry")}
+    from .sim import sim_builder
+    from .utils import helpers, logging, math
+
+    # ---- isaacgym shim -----------------------------------------------------------------------
+    gymapi = _module("isaacgym.gymapi", SIM_PHYSX=1, SIM_FLEX=0, LOCAL_SPACE=1, ENV_SPACE=0, GLOBAL_SPACE=2,
+                     UP_AXIS_Y=0, UP_AXIS_Z=1, STATE_ALL=3)
+    gymutil = _module("isaacgym.gymutil", parse_device_str=helpers.parse_device_str)
+    gymtorch = _module("isaacgym.gymtorch", wrap_tensor=lambda t: t, unwrap_tensor=lambda t: t)
+    _module("isaacgym", gymapi=gymapi, gymutil=gymutil, gymtorch=gymtorch, __path__=[])
+    # ---- aerial_gym alias ----------------------------------------------------------------------
+    pkg = _module("aerial_gym", AERIAL_GYM_DIRECTORY=PACKAGE_DIRECTORY, _b200_compat=True, __path__=[])
+    table = {
+        "registry": registry, "registry.task_registry": R["task_registry"], "registry.robot_registry": R["robot_registry"],
+        "registry.controller_registry": R["controller_registry"], "registry.env_registry": R["env_registry"],
+        "registry.sim_registry": R["sim_registry"], "sim": sim, "sim.sim_builder": sim_builder, "task": task,
+        "env_manager": env_manager, "robots": robots, "control": control, "utils": utils, "utils.helpers": helpers,
+        "utils.logging": logging, "utils.math": math, "config": config, "config.sim_config": sim_config,
+        "config.env_config": env_config, "config.robot_config": robot_config, "config.controller_config": controller_config,
+        "config.sensor_config": sensor_config, "config.asset_config": asset_config, "config.task_config": task_config,
+    }
+    for name, mod in table.items():
+        sys.modules["aerial_gym." + name] = mod
+        if "." not in name:
+            setattr(pkg, name, mod)
+    # reference-style deep config paths
+    deep = {
+        "config.task_config.position_setpoint_task_config": _module(
+            "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
+        "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),
+        "config.env_config.empty_env": _module("aerial_gym.config.env_config.empty_env", EmptyEnvCfg=env_config.EmptyEnvCfg),
+        "config.env_config.env_with_obstacles": _module("aerial_gym.config.env_config.env_with_obstacles",
+                                                        EnvWithObstaclesCfg=env_config.EnvWithObstaclesCfg),
+        "config.robot_config.base_quad_config": _module("aerial_gym.config.robot_config.base_quad_config",
+                                                        **{k: v for k, v in vars(robot_config).items() if k.startswith("BaseQuad")}),
+    }
+    del deep

@@ -5,7 +5,7 @@ AGX_CTRL_* id that selects the fused code path of the HP1 kernel (csrc/hp1.cu: c
 Calling one directly raises -- the arithmetic only exists on the GPU."""
 from .. import _lib
 from ..config import controller_config as cc
-from ..registry import controller_registry
+from ..registry._core import controller_registry
 
 
 class FusedController:

@@ -451,8 +451,9 @@ __device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3
 // =========================================================================================
 // main kernel
 // =========================================================================================
+// 8 CTAs/SM -> <= 128 registers: all 1024 CTAs of the 65,536-env launch are resident in one wave
 template <int M, bool TASK>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
     __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

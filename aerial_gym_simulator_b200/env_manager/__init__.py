@@ -2,7 +2,7 @@
 B200 engines.  Registers the env / sim configs (env_manager/__init__.py, sim/__init__.py)."""
 from ..config import env_config as _ec
 from ..config import sim_config as _sc
-from ..registry import env_config_registry, sim_config_registry
+from ..registry._core import env_config_registry, sim_config_registry
 
 env_config_registry.register("empty_env", _ec.EmptyEnvCfg)
 env_config_registry.register("env_with_obstacles", _ec.EnvWithObstaclesCfg)

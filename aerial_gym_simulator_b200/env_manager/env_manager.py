@@ -23,7 +23,7 @@ from .. import robots  # noqa: F401  (registers robots + controllers)
 from .. import urdf
 from ..hp1 import Hp1Engine
 from ..hp2 import RayScene, RaySensor
-from ..registry import env_config_registry, robot_registry, sim_config_registry
+from ..registry._core import env_config_registry, robot_registry, sim_config_registry
 
 
 def _lerp(lo, hi, u):  # utils/math.py:51-54 torch_rand_float_tensor arithmetic

@@ -1,1 +1,1 @@
-from . import controller_registry  # noqa: F401  (reference import path: aerial_gym.registry.controller_registry)
+from ._core import controller_registry  # noqa: F401

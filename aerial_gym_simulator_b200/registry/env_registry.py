@@ -1,1 +1,1 @@
-from . import env_config_registry  # noqa: F401  (reference import path: aerial_gym.registry.env_registry)
+from ._core import env_config_registry  # noqa: F401

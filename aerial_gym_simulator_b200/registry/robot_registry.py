@@ -1,1 +1,1 @@
-from . import robot_registry  # noqa: F401  (reference import path: aerial_gym.registry.robot_registry)
+from ._core import robot_registry  # noqa: F401

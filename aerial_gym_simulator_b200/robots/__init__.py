@@ -8,7 +8,7 @@ from .. import control  # noqa: F401  (registers controllers)
 from .. import urdf
 from ..config import robot_config as rc
 from ..hp1 import MultirotorSpec
-from ..registry import controller_registry, robot_registry
+from ..registry._core import controller_registry, robot_registry
 
 
 class BaseMultirotor:

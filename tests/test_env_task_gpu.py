@@ -7,7 +7,7 @@ import torch
 from oracle import hp1_oracle as O
 from oracle import hp2_oracle as RO
 import aerial_gym_simulator_b200.task  # noqa: F401
-from aerial_gym_simulator_b200.registry import task_registry
+from aerial_gym_simulator_b200.registry._core import task_registry
 from aerial_gym_simulator_b200.sim import SimBuilder
 from tests import _hp1_common as H
 from tests import _hp2_common as H2

@@ -10,7 +10,7 @@ from aerial_gym_simulator_b200.config import RESOURCES_DIRECTORY
 from aerial_gym_simulator_b200.config.env_config import EmptyEnvCfg, EnvWithObstaclesCfg
 from aerial_gym_simulator_b200.config.sim_config import BaseSimConfig
 from aerial_gym_simulator_b200.hp1 import build_config
-from aerial_gym_simulator_b200.registry import (controller_registry, env_config_registry, robot_registry,
+from aerial_gym_simulator_b200.registry._core import (controller_registry, env_config_registry, robot_registry,
                                                 sim_config_registry, task_registry)
 import aerial_gym_simulator_b200.task  # noqa: F401  (registers everything)
 
@@ -80,3 +80,24 @@ def test_fused_controllers_refuse_direct_calls():
 def test_root_link_no_control_is_rejected():
     with pytest.raises(ValueError, match="root_link"):
         robot_registry.make_robot("base_quad_root_link_control", "no_control", EmptyEnvCfg, "cpu")
+
+
+def test_compat_import_paths_of_the_reference():
+    """rl_training/* and examples/* import these paths; compat.install()
+    makes them resolve to this package, including the isaacgym shim."""
+    import aerial_gym_simulator_b200.compat as compat
+
+    compat.install()
+    import isaacgym  # noqa: F401
+    from isaacgym import gymutil
+    from aerial_gym.registry.task_registry import task_registry as tr
+    from aerial_gym.registry.robot_registry import robot_registry as rr
+    from aerial_gym.sim.sim_builder import SimBuilder  # noqa: F401
+    from aerial_gym.utils.helpers import parse_arguments  # noqa: F401
+    from aerial_gym.utils.logging import CustomLogger
+    from aerial_gym.config.task_config.position_setpoint_task_config import task_config
+
+    assert tr is task_registry and rr is robot_registry
+    assert gymutil.parse_device_str("cuda:3") == ("cuda", 3)
+    assert task_config.controller_name == "lee_attitude_control" and task_config.episode_len_steps == 500
+    CustomLogger("t").setLoggerLevel("INFO")
