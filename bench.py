@@ -164,6 +164,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from aerial_gym_simulator_b200.distributed import ObsAllGather
     from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,14 +187,14 @@ def run_ours(args):
     eng.sim_steps.copy_((torch.arange(N, device=dev) % 500).int())  # de-synchronised episode phases
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
-    gathered = torch.empty(world * N, 13, device=dev) if world > 1 else None
+    gather = ObsAllGather(N, 13, world * N, dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def step(i, mid=None):
         eng.position_task_step(acts[i % 8], mid_event=mid)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, eng.obs)
+            gather(eng.obs)
 
     def barrier():
         if world > 1:
@@ -258,7 +259,7 @@ def run_ours(args):
         d_act.copy_(h_act[i % 8], non_blocking=True)
         eng.position_task_step(d_act)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, eng.obs)
+            gather(eng.obs)
         h_obs.copy_(eng.obs, non_blocking=True)
         h_rew.copy_(eng.reward, non_blocking=True)
         h_term.copy_(eng.terminations, non_blocking=True)
@@ -278,6 +279,10 @@ def run_ours(args):
     e2e_value = world * N * K / float(e2e_t.item())
     h2d = N * 4 * 4
     d2h = N * 13 * 4 + N * 4 + 2 * N
+
+    hp2 = None
+    if not args.no_hp2:
+        hp2 = run_hp2_depth(dev, world, rank, args)
 
     if rank == 0:
         peaks = {}
@@ -316,11 +321,88 @@ def run_ours(args):
                     "api": "Hp1Engine.position_task_step (C ABI) with pinned host actions in, obs/reward/flags out"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
+            "hp2_depth": hp2,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_hp2_depth(dev, world, rank, args):
+    """Second headline of BASELINE.json: depth rays/sec, 64x48 depth+segmentation camera, 8192 envs
+    per GPU, 44-box scenes (the shipped env_with_obstacles count).  Synthetic randomly posed boxes;
+    the 8192 scenes (~240 MB) exceed L2, so no flush is needed between frames."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from aerial_gym_simulator_b200.hp2 import RayScene, RaySensor, box_triangles
+
+    E, K, H, W = args.hp2_envs, 44, 48, 64
+    g = torch.Generator().manual_seed(7 + rank)
+    sizes = torch.rand(5, 3, generator=g) * 1.2 + 0.15
+    templates = [box_triangles(s.tolist()) for s in sizes]
+    pose = torch.zeros(E, K, 13)
+    pose[..., 0:3] = (torch.rand(E, K, 3, generator=g) * 2 - 1) * 5.0
+    q = torch.randn(E, K, 4, generator=g)
+    pose[..., 3:7] = q / q.norm(dim=-1, keepdim=True)
+    tm = torch.randint(0, 5, (E, K), generator=g).numpy()
+    ctr = (100 + torch.arange(E * K).reshape(E, K)).numpy()
+    scene = RayScene(templates, [0] * 5, [1] * 5, tm, ctr, pose.to(dev), dev)
+
+    class cam:
+        sensor_type, num_sensors, height, width = "camera", 1, H, W
+        horizontal_fov_deg, max_range, min_range = 87.0, 10.0, 0.2
+        calculate_depth, return_pointcloud, pointcloud_in_world_frame = True, False, False
+        segmentation_camera, normalize_range = True, True
+        far_out_of_range_value, near_out_of_range_value = 10.0, -10.0
+        euler_frame_rot_deg = [-90.0, 0, -90.0]
+
+    robot = torch.zeros(E, 13)
+    robot[:, 0:3] = (torch.rand(E, 3, generator=g) * 2 - 1) * 4.0
+    rq = torch.randn(E, 4, generator=g)
+    robot[:, 3:7] = rq / rq.norm(dim=-1, keepdim=True)
+    robot_d = robot.to(dev)
+    pix = torch.zeros(E, 1, H, W, device=dev)
+    seg = torch.zeros(E, 1, H, W, dtype=torch.int32, device=dev)
+    sensor = RaySensor(cam, scene, robot_d, pix, seg)
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    scene.update()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    build_ms = e0.elapsed_time(e1)
+    frames = max(5, min(args.steps, 50))
+    for _ in range(3):
+        sensor.capture()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(frames):
+        sensor.capture()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) * 1e-3
+    rays = E * H * W
+    hit_frac = float((seg >= 0).float().mean())
+    out_bytes = rays * 8
+    scene_bytes = E * (K * 12 * 48 + (2 * scene.P - 1) * 32 + max(scene.P, 4) * 4)
+    return {
+        "metric": "depth rays/sec (64x48 depth+seg camera, 44-box scene)", "value": world * rays * frames / sec,
+        "unit": "rays/s", "envs_per_gpu": E, "frames": frames, "ms_per_frame": sec * 1e3 / frames, "hit_fraction": hit_frac,
+        "scene_update_ms_all_envs": build_ms, "gpu_launches": frames,
+        "roofline": {"bound": "hbm (nominal; FP32 traversal binds)", "achieved": (out_bytes + scene_bytes) * frames / sec / 1e9,
+                     "unit": "GB/s", "algorithmic_bytes_per_frame": out_bytes + scene_bytes,
+                     "note": "8 B/ray written + every env's scene (slabs+BVH) staged once per frame"},
+    }
 
 
 def main():
@@ -331,6 +413,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hp2", action="store_true", help="skip the secondary depth rays/sec measurement")
+    ap.add_argument("--hp2-envs", type=int, default=8192)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
