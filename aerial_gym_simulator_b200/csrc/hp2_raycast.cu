@@ -356,6 +356,97 @@ __device__ __forceinline__ Hit traverse(const float* __restrict__ nodes, const i
     return best;
 }
 
+// ---- a14: sphere vs triangle mesh (bit contract with oracle point_tri_dist2) ----------------
+__device__ __forceinline__ float point_tri_dist2(v3 p, v3 a, v3 ab, v3 ac) {
+    v3 ap = sub3(p, a);
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) return dot3(ap, ap);
+    v3 b{a.x + ab.x, a.y + ab.y, a.z + ab.z};
+    v3 bp = sub3(p, b);
+    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) return dot3(bp, bp);
+    float vc = fmaf(d1, d4, -(d3 * d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float v = d1 / (d1 - d3);
+        v3 d = sub3(p, v3{fmaf(v, ab.x, a.x), fmaf(v, ab.y, a.y), fmaf(v, ab.z, a.z)});
+        return dot3(d, d);
+    }
+    v3 c{a.x + ac.x, a.y + ac.y, a.z + ac.z};
+    v3 cp = sub3(p, c);
+    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) return dot3(cp, cp);
+    float vb = fmaf(d5, d2, -(d1 * d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2 / (d2 - d6);
+        v3 d = sub3(p, v3{fmaf(w, ac.x, a.x), fmaf(w, ac.y, a.y), fmaf(w, ac.z, a.z)});
+        return dot3(d, d);
+    }
+    float va = fmaf(d3, d6, -(d5 * d4));
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        v3 bc = sub3(c, b);
+        v3 d = sub3(p, v3{fmaf(w, bc.x, b.x), fmaf(w, bc.y, b.y), fmaf(w, bc.z, b.z)});
+        return dot3(d, d);
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float v = vb * denom, w = vc * denom;
+    v3 d = sub3(p, v3{fmaf(w, ac.x, fmaf(v, ab.x, a.x)), fmaf(w, ac.y, fmaf(v, ab.y, a.y)), fmaf(w, ac.z, fmaf(v, ab.z, a.z))});
+    return dot3(d, d);
+}
+
+// one thread per env: BVH descent with a sphere/AABB overlap test, exact min distance over the
+// triangles of every leaf the sphere of the CURRENT best radius can reach
+__global__ void __launch_bounds__(128)
+hp2_collide_kernel(const __grid_constant__ AgxHp2Scene sc, const float* __restrict__ robot_pose, int stride, float radius,
+                   uint8_t* __restrict__ crashes, float* __restrict__ min_dist) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= sc.num_envs) return;
+    const int K = sc.num_objects, P = sc.leaves_pow2, L = sc.tris_per_object;
+    const float* nodes = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
+    const int32_t* leaf = sc.leaf_object + (size_t)e * (P < 4 ? 4 : P);
+    const float* tris = sc.tris + (size_t)e * K * L * kTriFloats;
+    const float* rp = robot_pose + (size_t)e * stride;
+    const v3 c{rp[0], rp[1], rp[2]};
+    // search radius: exact min distance is only needed when min_dist is requested; otherwise the
+    // collision radius bounds the search
+    float best = 3.0e38f;
+    const float r2 = radius * radius;
+    const float search = min_dist ? 3.0e38f : r2;
+    int stack[24];
+    int sp = 0, node = 0;
+    while (true) {
+        const float* nd = nodes + (size_t)node * kNodeFloats;
+        float dx = fmaxf(fmaxf(nd[0] - c.x, c.x - nd[4]), 0.0f);
+        float dy = fmaxf(fmaxf(nd[1] - c.y, c.y - nd[5]), 0.0f);
+        float dz = fmaxf(fmaxf(nd[2] - c.z, c.z - nd[6]), 0.0f);
+        float box_d2 = dx * dx + dy * dy + dz * dz;
+        float lim = fminf(best, search);
+        bool reach = box_d2 <= lim * 1.0001f + 1e-6f;  // padded boxes + slack: culling only
+        if (reach) {
+            if (node >= P - 1) {
+                int obj = leaf[node - (P - 1)];
+                if (obj >= 0) {
+                    const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)obj * L * kTriFloats);
+                    for (int s = 0; s < L; ++s) {
+                        float4 a = tp[3 * s], b = tp[3 * s + 1], cc = tp[3 * s + 2];
+                        if (b.x == 0.f && b.y == 0.f && b.z == 0.f && cc.x == 0.f && cc.y == 0.f && cc.z == 0.f) continue;  // padding slot
+                        float d2 = point_tri_dist2(c, v3{a.x, a.y, a.z}, v3{b.x, b.y, b.z}, v3{cc.x, cc.y, cc.z});
+                        best = fminf(best, d2);
+                    }
+                }
+            } else {
+                stack[sp++] = 2 * node + 2;
+                node = 2 * node + 1;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    if (best <= r2) crashes[e] = 1;
+    if (min_dist) min_dist[e] = sqrtf(best);
+}
+
 __device__ __forceinline__ float range_epilogue(const AgxHp2Sensor& s, float px) {
     // warp_sensor.py:216-225: two sequential masked assignments, then the division
     if (px > s.max_range) px = s.far_out_of_range_value;
@@ -532,6 +623,19 @@ int agx_hp2_update_scene(const AgxHp2Scene* sc, const uint8_t* mask, void* strea
     if (rc) return rc;
     hp2_update_scene_kernel<<<sc->num_envs, 256, smem, (cudaStream_t)stream>>>(*sc, mask);
     return agx_check_launch("hp2_update_scene_kernel");
+}
+
+int agx_hp2_collide(const AgxHp2Scene* sc, const float* robot_pose, int robot_pose_stride, float radius, uint8_t* crashes,
+                    float* min_dist, void* stream) {
+    int rc = validate_scene(sc);
+    if (rc) return rc;
+    if (sc->num_envs == 0) return AGX_OK;
+    if (!robot_pose || !crashes) return agx_set_error(AGX_E_NULL, "robot_pose/crashes is NULL");
+    if (robot_pose_stride < 3) return agx_set_error(AGX_E_INVALID, "robot_pose_stride < 3");
+    if (!(radius >= 0.0f)) return agx_set_error(AGX_E_INVALID, "radius must be >= 0");
+    hp2_collide_kernel<<<(sc->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sc, robot_pose, robot_pose_stride, radius, crashes,
+                                                                                  min_dist);
+    return agx_check_launch("hp2_collide_kernel");
 }
 
 int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {

@@ -7,7 +7,8 @@ Differences that are deliberate and documented:
     view of ``vec_root_tensor``); obstacles live in ``env_asset_state_tensor`` [N,K,13];
   * construction is array-native (no O(N) actor loop), except asset-file selection which keeps the
     reference's per-env ``random.choices`` / ``random.shuffle`` order;
-  * contact-force collision flags (a14) are not produced yet -> ``robot_contact_force_tensor`` is 0.
+  * collision flags (a14) come from a geometric sphere-vs-mesh overlap test, not PhysX contact
+    forces; ``robot_contact_force_tensor`` stays 0.
 """
 from __future__ import annotations
 
@@ -356,18 +357,22 @@ class EnvManager:
         gtd["robot_prev_actions"][:] = gtd["robot_actions"]  # robot_manager.py:486-488
         gtd["robot_actions"][:] = actions
         a = gtd["robot_actions"]
-        if self.spec.enable_disturbance:
-            for _ in range(n):  # fresh draws every physics step, like the reference
+        if self.spec.enable_disturbance or self.scene is not None:
+            # per-physics-step launches: fresh disturbance draws and a collision check after every
+            # physics step, like the reference loop (env_manager.py:426-428)
+            for _ in range(n):
                 self.engine.physics_step(a, disturbance=self._draw_disturbance(), physics_steps=1)
+                self.compute_observations()
         elif n > 0:
             self.engine.physics_step(a, physics_steps=n)  # n sub-steps fused in one launch
-        self.compute_observations()
         self.engine.sim_steps += 1
         self.step_counter += 1
 
     def compute_observations(self):
-        # a14 (collision flag from contact forces) needs geometry queries: not built yet
-        return
+        """crashes += contact (env_manager.py:358-362).  PhysX contact forces are replaced by a
+        geometric test: the base-link collision sphere overlaps the env mesh (agx_hp2_collide)."""
+        if self.scene is not None:
+            self.scene.collide(self.engine.root_state, self.robot.collision_radius, self.collision_tensor)
 
     def reset_terminated_and_truncated_envs(self):
         flags = self.collision_tensor * int(self.cfg.env.reset_on_collision) + self.truncation_tensor

@@ -99,6 +99,18 @@ class RayScene:
         _lib.check(self.lib.agx_hp2_update_scene(C.byref(self.c), m, self._stream()), "agx_hp2_update_scene")
 
 
+    def collide(self, robot_state: torch.Tensor, radius: float, crashes: torch.Tensor, min_dist: Optional[torch.Tensor] = None):
+        """crashes (bool [E]) |= robot collision sphere overlaps the env mesh (row a14)."""
+        if crashes.dtype != torch.bool or crashes.shape != (self.E,):
+            raise ValueError("crashes must be bool [E]")
+        if robot_state.shape[0] != self.E or robot_state.stride(1) != 1:
+            raise ValueError("robot_state must be [E,>=3] with contiguous rows")
+        md = C.c_void_p(min_dist.data_ptr()) if min_dist is not None else None
+        _lib.check(self.lib.agx_hp2_collide(C.byref(self.c), C.c_void_p(robot_state.data_ptr()), robot_state.stride(0),
+                                            C.c_float(radius), C.c_void_p(crashes.data_ptr()), md, self._stream()),
+                   "agx_hp2_collide")
+
+
 def camera_intrinsics(width, height, horizontal_fov_deg):
     """WarpCam.initialize_camera_matrices (sensors/warp/warp_cam.py:31-64): fp32 K, its inverse."""
     hf = math.radians(horizontal_fov_deg)

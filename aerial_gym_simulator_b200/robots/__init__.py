@@ -33,6 +33,14 @@ class BaseMultirotor:
         self.urdf_model = urdf.parse_urdf(path)
         self.robot_mass, self.robot_com, self.robot_inertia = self.urdf_model.composite_inertia()
         self.num_bodies = len(self.urdf_model.links)
+        # collision proxy of body 0 (a14): bounding sphere of the root link's collision shapes
+        root = self.urdf_model.links[self.urdf_model.root]
+        rad = 0.0
+        for c in root.collisions or root.visuals:
+            ext = {"sphere": lambda v: v.size[0], "box": lambda v: 0.5 * float(np.linalg.norm(v.size)),
+                   "cylinder": lambda v: float(np.hypot(v.size[0], 0.5 * v.size[1]))}.get(c.kind, lambda v: 0.0)(c)
+            rad = max(rad, float(np.linalg.norm(c.p)) + ext)
+        self.collision_radius = rad if rad > 0 else 0.1
 
     def make_spec(self, sim_config, env_config) -> MultirotorSpec:
         cfg, cc_, ca = self.cfg, self.controller_config, self.cfg.control_allocator_config

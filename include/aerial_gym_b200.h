@@ -253,6 +253,15 @@ int agx_hp2_update_scene(const AgxHp2Scene* scene, const uint8_t* mask, void* st
 /* Cast every ray of every sensor of every env.  Replaces WarpSensor.update. */
 int agx_hp2_cast(const AgxHp2Scene* scene, const AgxHp2Sensor* sensor, void* stream);
 
+/* Collision flag.  Replaces EnvManager.compute_observations
+ * (env_manager/env_manager.py:358-362: crashes += |PhysX contact force on body 0| > threshold).
+ * PhysX contacts are not reproducible; the flag is geometric: the robot's collision sphere
+ * (centre = robot position, `radius`) overlaps the env's triangle mesh.
+ *   crashes  [E] bool : OR-ed with the overlap flag (the reference accumulates with +=)
+ *   min_dist [E] f32  : distance from the sphere centre to the closest triangle, or NULL */
+int agx_hp2_collide(const AgxHp2Scene* scene, const float* robot_pose, int robot_pose_stride, float radius,
+                    uint8_t* crashes, float* min_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

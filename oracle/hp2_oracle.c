@@ -275,4 +275,73 @@ void hp2o_cast(const Hp2oSensor* s, int n_envs, const float* robot_pose, const f
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * a14: collision flag.  Reference: EnvManager.compute_observations (env_manager/env_manager.py:358-362)
+ * thresholds the PhysX contact force on body 0; PhysX is not in the tree, so the flag is restated
+ * geometrically: the robot's base-link collision sphere overlaps the env's triangle
+ * mesh  <=>  min over triangles of |closest_point(tri, c) - c|^2 <= r^2.  Closest point on a
+ * triangle: Ericson, Real-Time Collision Detection 5.1.5 (Voronoi-region form).
+ * Same explicit-fmaf arithmetic contract as the ray path => flags are bit-exact.
+ * ------------------------------------------------------------------------------------------ */
+static float point_tri_dist2(v3 p, v3 a, v3 ab, v3 ac) {
+    v3 ap = sub3(p, a);
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) return dot3(ap, ap);
+    v3 b = {a.x + ab.x, a.y + ab.y, a.z + ab.z};
+    v3 bp = sub3(p, b);
+    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) return dot3(bp, bp);
+    float vc = fmaf(d1, d4, -(d3 * d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float v = d1 / (d1 - d3);
+        v3 q = {fmaf(v, ab.x, a.x), fmaf(v, ab.y, a.y), fmaf(v, ab.z, a.z)};
+        v3 d = sub3(p, q);
+        return dot3(d, d);
+    }
+    v3 c = {a.x + ac.x, a.y + ac.y, a.z + ac.z};
+    v3 cp = sub3(p, c);
+    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) return dot3(cp, cp);
+    float vb = fmaf(d5, d2, -(d1 * d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2 / (d2 - d6);
+        v3 q = {fmaf(w, ac.x, a.x), fmaf(w, ac.y, a.y), fmaf(w, ac.z, a.z)};
+        v3 d = sub3(p, q);
+        return dot3(d, d);
+    }
+    float va = fmaf(d3, d6, -(d5 * d4));
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        v3 bc = sub3(c, b);
+        v3 q = {fmaf(w, bc.x, b.x), fmaf(w, bc.y, b.y), fmaf(w, bc.z, b.z)};
+        v3 d = sub3(p, q);
+        return dot3(d, d);
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float v = vb * denom, w = vc * denom;
+    v3 q = {fmaf(w, ac.x, fmaf(v, ab.x, a.x)), fmaf(w, ac.y, fmaf(v, ab.y, a.y)), fmaf(w, ac.z, fmaf(v, ab.z, a.z))};
+    v3 d = sub3(p, q);
+    return dot3(d, d);
+}
+
+/* robot_pose [E,7]; flags [E] u8 (1 = overlap); min_dist2 [E] (FLT_MAX-like 3.0e38 when no triangle) */
+void hp2o_collide(int n_envs, const float* robot_pose, float radius, const float* tris, const int32_t* tri_count,
+                  int max_tris, uint8_t* flags, float* min_dist2) {
+    float r2 = radius * radius;
+    for (int e = 0; e < n_envs; ++e) {
+        const float* rp = robot_pose + (size_t)e * 7;
+        v3 c = {rp[0], rp[1], rp[2]};
+        const float* T = tris + (size_t)e * max_tris * 9;
+        float best = 3.0e38f;
+        for (int i = 0; i < tri_count[e]; ++i) {
+            const float* p = T + (size_t)i * 9;
+            v3 a = {p[0], p[1], p[2]}, ab = {p[3], p[4], p[5]}, ac = {p[6], p[7], p[8]};
+            float d2 = point_tri_dist2(c, a, ab, ac);
+            if (d2 < best) best = d2;
+        }
+        flags[e] = best <= r2 ? 1 : 0;
+        if (min_dist2) min_dist2[e] = best;
+    }
+}
+
 int hp2o_sizeof_sensor(void) { return (int)sizeof(Hp2oSensor); }

@@ -117,3 +117,15 @@ def cast(sensor: Hp2oSensor, robot_pose, mount, ray_table, tris, seg_ids, tri_co
                     _p(tris, C.c_float), _p(seg_ids, C.c_int32), _p(tri_count, C.c_int32), tris.shape[1],
                     _p(pix, C.c_float), _p(seg, C.c_int32))
     return pix, seg
+
+
+def collide(robot_pose, radius, tris, tri_count):
+    E = robot_pose.shape[0]
+    rp = np.ascontiguousarray(robot_pose, np.float32)
+    tris = np.ascontiguousarray(tris, np.float32)
+    tri_count = np.ascontiguousarray(tri_count, np.int32)
+    flags = np.zeros(E, np.uint8)
+    d2 = np.zeros(E, np.float32)
+    lib().hp2o_collide(E, _p(rp, C.c_float), C.c_float(radius), _p(tris, C.c_float), _p(tri_count, C.c_int32),
+                       tris.shape[1], _p(flags, C.c_uint8), _p(d2, C.c_float))
+    return flags.astype(bool), d2

@@ -194,3 +194,29 @@ def test_error_paths():
     scene.c.leaves_pow2 = 3
     with pytest.raises(_lib.AgxError, match="leaves_pow2"):
         scene.update()
+
+
+@pytest.mark.parametrize("K", [1, 44, 300])
+def test_collision_flags_match_oracle(K):
+    """a14: sphere-vs-mesh overlap flags bit-exact, min distance bit-exact."""
+    E = 512
+    sc = H.make_scene(E, K, seed=100 + K, extent=2.0, parked=min(5, K - 1))
+    scene = RayScene(sc["templates"], [0] * 5, [1] * 5, sc["tm"], sc["ctr"], sc["pose"].to(DEV), DEV)
+    scene.update()
+    robot = H.robot_poses(E, 12, extent=2.0)
+    crashes = torch.zeros(E, dtype=torch.bool, device=DEV)
+    crashes[3] = True  # accumulates (+=), never clears
+    md = torch.zeros(E, device=DEV)
+    scene.collide(robot.to(DEV), 0.18384776, crashes, md)
+    tris, segs, cnt = H.oracle_tris(sc)
+    ref_hit, ref_d2 = RO.collide(robot[:, :7].numpy(), 0.18384776, tris, cnt)
+    ref_hit[3] = True
+    torch.cuda.synchronize()
+    assert np.array_equal(crashes.cpu().numpy(), ref_hit)
+    assert np.array_equal(md.cpu().numpy(), np.sqrt(ref_d2))
+    assert 0 < ref_hit.sum() < E
+    # flag-only path (search bounded by the radius) gives the same flags
+    c2 = torch.zeros(E, dtype=torch.bool, device=DEV)
+    c2[3] = True
+    scene.collide(robot.to(DEV), 0.18384776, c2, None)
+    assert torch.equal(c2, crashes)

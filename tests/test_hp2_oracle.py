@@ -92,3 +92,16 @@ def test_lidar_table_and_intrinsics_match_product_host_code():
     kb, cxb, cyb = hp2.camera_intrinsics(64, 48, 87.0)
     assert np.array_equal(ka, kb) and (cxa, cya) == (cxb, cyb) == (32, 24)
     assert np.array_equal(RO.box_template((1, 2, 3)), hp2.box_triangles((1, 2, 3)))
+
+
+def test_collision_oracle_known_answers():
+    """a14 oracle: sphere vs unit box at the origin."""
+    tris = RO.box_template((1.0, 1.0, 1.0))[None].copy()  # world == object frame; stored as v0,v1,v2
+    T = tris.reshape(1, 12, 3, 3)
+    slabs = np.concatenate([T[:, :, 0], T[:, :, 1] - T[:, :, 0], T[:, :, 2] - T[:, :, 0]], axis=-1).astype(np.float32)
+    cnt = np.array([12], np.int32)
+    for pos, want_d in [((2.0, 0, 0), 1.5), ((0.5 + 0.1, 0.2, -0.3), 0.1), ((1.0, 1.0, 1.0), np.sqrt(0.75)), ((0, 0, 0), 0.5)]:
+        pose = np.array([[*pos, 0, 0, 0, 1]], np.float32)
+        hit, d2 = RO.collide(pose, 0.18, slabs, cnt)
+        assert abs(np.sqrt(d2[0]) - want_d) < 1e-6, (pos, np.sqrt(d2[0]), want_d)
+        assert bool(hit[0]) == (want_d <= 0.18)
