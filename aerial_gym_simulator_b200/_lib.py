@@ -71,7 +71,7 @@ class AgxHp2Scene(C.Structure):
         ("tris_per_object", C.c_int32), ("num_templates", C.c_int32), ("obj_pose_stride", C.c_int32),
         ("tmpl_tri_offset", fp), ("tmpl_tris", fp), ("tmpl_seg_base", fp), ("tmpl_seg_mask", fp),
         ("obj_pose", fp), ("obj_template", fp), ("obj_seg_counter", fp), ("bounds_min", fp), ("bounds_max", fp),
-        ("tris", fp), ("nodes", fp), ("leaf_object", fp),
+        ("tris", fp), ("nodes", fp), ("leaf_object", fp), ("face_offset", fp),
     ]
 
 
@@ -82,12 +82,13 @@ class AgxHp2Sensor(C.Structure):
         ("segmentation", C.c_int32), ("fuse_epilogue", C.c_int32), ("normalize_range", C.c_int32),
         ("c_x", C.c_int32), ("c_y", C.c_int32), ("kinv", f32 * 9), ("far_plane", f32),
         ("max_range", f32), ("min_range", f32), ("far_out_of_range_value", f32), ("near_out_of_range_value", f32),
-        ("frame_quat", f32 * 4), ("robot_pose_stride", C.c_int32), ("pad_", C.c_int32),
+        ("frame_quat", f32 * 4), ("baseline", f32), ("normal_in_world_frame", C.c_int32),
+        ("robot_pose_stride", C.c_int32), ("pad_", C.c_int32),
         ("robot_pose", fp), ("mount", fp), ("ray_table", fp), ("pixels", fp), ("seg_pixels", fp),
     ]
 
 
-SENSOR_CAMERA, SENSOR_LIDAR = 0, 1
+SENSOR_CAMERA, SENSOR_LIDAR, SENSOR_STEREO_CAMERA, SENSOR_NORMAL_FACEID_CAMERA, SENSOR_NORMAL_FACEID_LIDAR = 0, 1, 2, 3, 4
 
 
 class AgxError(RuntimeError):

@@ -137,6 +137,14 @@ hp2_update_scene_kernel(const __grid_constant__ AgxHp2Scene sc, const uint8_t* _
         float4* dst = reinterpret_cast<float4*>(tris + (size_t)i * kTriFloats);
         dst[0] = o0; dst[1] = o1; dst[2] = o2;
     }
+    if (sc.face_offset && tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < K; ++k) {
+            sc.face_offset[(size_t)e * K + k] = acc;
+            int tm = sc.obj_template[(size_t)e * K + k];
+            acc += min(L, sc.tmpl_tri_offset[tm + 1] - sc.tmpl_tri_offset[tm]);
+        }
+    }
     __syncthreads();  // slabs of this CTA are read back below (same CTA wrote them)
     // pass B: object AABBs from the slabs just written
     for (int k = tid; k < K; k += nt) {
@@ -519,9 +527,17 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         sp.x += rp[0]; sp.y += rp[1]; sp.z += rp[2];
         q4 sq = quat_mul(rq, quat_mul(q4{m[3], m[4], m[5], m[6]}, qf));
         v3 rd_p{0.f, 0.f, 0.f};
-        if (sn.kind == AGX_SENSOR_CAMERA) {
+        const bool is_cam = sn.kind == AGX_SENSOR_CAMERA || sn.kind == AGX_SENSOR_STEREO_CAMERA || sn.kind == AGX_SENSOR_NORMAL_FACEID_CAMERA;
+        const bool is_normal = sn.kind == AGX_SENSOR_NORMAL_FACEID_CAMERA || sn.kind == AGX_SENSOR_NORMAL_FACEID_LIDAR;
+        const bool norm_uv = sn.return_pointcloud || sn.kind == AGX_SENSOR_NORMAL_FACEID_CAMERA;
+        v3 stereo_pos = sp;
+        if (sn.kind == AGX_SENSOR_STEREO_CAMERA) {  // warp_stereo_camera_kernels.py:180-181
+            v3 ro = quat_rotate(sq, v3{-sn.baseline, 0.0f, 0.0f});
+            stereo_pos = v3{sp.x + ro.x, sp.y + ro.y, sp.z + ro.z};
+        }
+        if (is_cam) {
             v3 uvp = kinv_mul(sn.kinv, v3{(float)sn.c_x, (float)sn.c_y, 1.0f});
-            if (sn.return_pointcloud) uvp = normalize3(uvp);
+            if (norm_uv) uvp = normalize3(uvp);
             rd_p = normalize3(quat_rotate(sq, uvp));
         }
         const int y0 = rb * rows_per_item;
@@ -531,11 +547,11 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
             const int y = y0 + i / W, x = i % W;
             v3 uv, rd;
             float mult = 1.0f, max_t = sn.far_plane;
-            if (sn.kind == AGX_SENSOR_CAMERA) {  // warp_camera_kernels.py:186-221
+            if (is_cam) {  // warp_camera_kernels.py:186-221
                 uv = kinv_mul(sn.kinv, v3{(float)x, (float)y, 1.0f});
-                if (sn.return_pointcloud) uv = normalize3(uv);
+                if (norm_uv) uv = normalize3(uv);
                 rd = normalize3(quat_rotate(sq, uv));
-                if (!sn.return_pointcloud && sn.calculate_depth) {
+                if (sn.kind != AGX_SENSOR_NORMAL_FACEID_CAMERA && !sn.return_pointcloud && sn.calculate_depth) {
                     mult = dot3(rd, rd_p);
                     max_t = sn.far_plane / mult;
                 }
@@ -547,11 +563,50 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
             Hit h = traverse<SMEM>(nodes, leaf, tris, P, L, sp, rd, max_t);
             float dist = AGX_NO_HIT_RAY_VAL;
             int segv = AGX_NO_HIT_SEG_VAL;
-            if (h.tri != 0x7fffffff) {
+            const bool hit = h.tri != 0x7fffffff;
+            const size_t pix = (((size_t)e * S + c) * H + y) * W + x;
+            if (is_normal) {  // warp_camera_kernels.py:70-121, warp_lidar_kernels.py:90-126
+                v3 o{0.f, 0.f, 0.f};
+                int face = -1;
+                if (hit) {
+                    const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)h.tri * kTriFloats);
+                    float4 b = tp[1], cc = tp[2];
+                    v3 nrm = normalize3(cross3(v3{b.x, b.y, b.z}, v3{cc.x, cc.y, cc.z}));
+                    if (sn.normal_in_world_frame) o = nrm;
+                    else if (sn.kind == AGX_SENSOR_NORMAL_FACEID_CAMERA)
+                        o = v3{dot3(nrm, rd_p), dot3(nrm, cross3(rd_p, v3{0.f, 0.f, 1.f})), dot3(nrm, cross3(rd_p, v3{0.f, 1.f, 0.f}))};
+                    else
+                        o = normalize3(quat_rotate(q4{-sq.x, -sq.y, -sq.z, sq.w}, nrm));
+                    int obj = h.tri / L;
+                    face = (sc.face_offset ? sc.face_offset[(size_t)e * K + obj] : obj * L) + (h.tri - obj * L);
+                }
+                sn.pixels[pix * 3 + 0] = o.x; sn.pixels[pix * 3 + 1] = o.y; sn.pixels[pix * 3 + 2] = o.z;
+                if (sn.seg_pixels) sn.seg_pixels[pix] = face;
+                continue;
+            }
+            if (sn.kind == AGX_SENSOR_STEREO_CAMERA) {  // warp_stereo_camera_kernels.py:205-222
+                dist = -1.0f;  // INVALID_PIXEL_VAL
+                v3 ep;
+                if (hit) ep = v3{fmaf(rd.x * h.t, 0.999f, sp.x), fmaf(rd.y * h.t, 0.999f, sp.y), fmaf(rd.z * h.t, 0.999f, sp.z)};
+                else ep = v3{sp.x + (rd.x * sn.far_plane) / mult, sp.y + (rd.y * sn.far_plane) / mult, sp.z + (rd.z * sn.far_plane) / mult};
+                v3 dv = sub3(stereo_pos, ep);
+                float dl = sqrtf(dot3(dv, dv));
+                Hit h2 = traverse<SMEM>(nodes, leaf, tris, P, L, ep, normalize3(dv), dl);
+                const bool visible = h2.tri == 0x7fffffff;
+                if (hit && visible) {
+                    dist = h.t * mult;
+                    segv = __float_as_int(tris[(size_t)h.tri * kTriFloats + 3]);
+                } else if (!hit && visible) {
+                    dist = AGX_NO_HIT_RAY_VAL;
+                }
+                sn.pixels[pix] = sn.fuse_epilogue ? range_epilogue(sn, dist) : dist;
+                if (sn.seg_pixels) sn.seg_pixels[pix] = segv;
+                continue;
+            }
+            if (hit) {
                 dist = mult * h.t;
                 segv = __float_as_int(tris[(size_t)h.tri * kTriFloats + 3]);
             }
-            const size_t pix = (((size_t)e * S + c) * H + y) * W + x;
             if (sn.return_pointcloud) {
                 v3 p;
                 if (sn.pointcloud_in_world_frame) p = v3{fmaf(dist, rd.x, sp.x), fmaf(dist, rd.y, sp.y), fmaf(dist, rd.z, sp.z)};
@@ -604,6 +659,7 @@ uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which) {
         case 0: return (uint64_t)num_objects * tris_per_object * kTriFloats * 4;
         case 1: return (uint64_t)(2 * P - 1) * kNodeFloats * 4;
         case 2: return (uint64_t)(P < 4 ? 4 : P) * 4;
+        case 3: return (uint64_t)((num_objects + 3) / 4 * 4) * 4;
         default: return 0;
     }
 }
@@ -642,11 +698,12 @@ int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
     int rc = validate_scene(sc);
     if (rc) return rc;
     if (!sn) return agx_set_error(AGX_E_NULL, "sensor is NULL");
-    if (sn->kind != AGX_SENSOR_CAMERA && sn->kind != AGX_SENSOR_LIDAR) return agx_set_error(AGX_E_INVALID, "unknown sensor kind %d", sn->kind);
+    if (sn->kind < AGX_SENSOR_CAMERA || sn->kind > AGX_SENSOR_NORMAL_FACEID_LIDAR) return agx_set_error(AGX_E_INVALID, "unknown sensor kind %d", sn->kind);
     if (sn->width < 1 || sn->height < 1 || sn->num_sensors < 1) return agx_set_error(AGX_E_INVALID, "sensor dims must be positive");
     if (sc->num_envs == 0) return AGX_OK;
     if (!sn->robot_pose || !sn->mount || !sn->pixels) return agx_set_error(AGX_E_NULL, "robot_pose/mount/pixels is NULL");
-    if (sn->kind == AGX_SENSOR_LIDAR && !sn->ray_table) return agx_set_error(AGX_E_NULL, "LiDAR needs ray_table");
+    if ((sn->kind == AGX_SENSOR_LIDAR || sn->kind == AGX_SENSOR_NORMAL_FACEID_LIDAR) && !sn->ray_table)
+        return agx_set_error(AGX_E_NULL, "LiDAR needs ray_table");
     if (sn->robot_pose_stride < 7) return agx_set_error(AGX_E_INVALID, "robot_pose_stride < 7");
     int dev = 0, sms = 148, max_smem = 0;
     cudaGetDevice(&dev);

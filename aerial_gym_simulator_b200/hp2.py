@@ -78,11 +78,12 @@ class RayScene:
         self.tris = torch.zeros(E * nb(0) // 4, dtype=torch.float32, device=dev)
         self.nodes = torch.zeros(E * nb(1) // 4, dtype=torch.float32, device=dev)
         self.leaf_object = torch.full((E * nb(2) // 4,), -1, dtype=torch.int32, device=dev)
+        self.face_offset = torch.zeros(E * K, dtype=torch.int32, device=dev)
         s = AgxHp2Scene()
         s.num_envs, s.num_objects, s.leaves_pow2, s.tris_per_object = E, K, self.P, L
         s.num_templates, s.obj_pose_stride = len(templates), obj_pose.stride(1)
         for name in ("tmpl_tri_offset", "tmpl_tris", "tmpl_seg_base", "tmpl_seg_mask", "obj_pose", "obj_template",
-                     "obj_seg_counter", "tris", "nodes", "leaf_object"):
+                     "obj_seg_counter", "tris", "nodes", "leaf_object", "face_offset"):
             setattr(s, name, getattr(self, name).data_ptr())
         s.bounds_min = bounds_min.data_ptr() if bounds_min is not None else None
         s.bounds_max = bounds_max.data_ptr() if bounds_max is not None else None
@@ -155,9 +156,12 @@ class RaySensor:
         dev = scene.device
         E, S, H, W = scene.E, cfg.num_sensors, cfg.height, cfg.width
         st = cfg.sensor_type
-        if st not in ("camera", "lidar"):
+        kinds = {"camera": _lib.SENSOR_CAMERA, "lidar": _lib.SENSOR_LIDAR, "stereo_camera": _lib.SENSOR_STEREO_CAMERA,
+                 "normal_faceID_camera": _lib.SENSOR_NORMAL_FACEID_CAMERA, "normal_faceID_lidar": _lib.SENSOR_NORMAL_FACEID_LIDAR}
+        if st not in kinds:
             raise NotImplementedError(f"sensor_type {st}")
-        pc = bool(getattr(cfg, "return_pointcloud", False))
+        is_normal = st.startswith("normal_faceID")
+        pc = bool(getattr(cfg, "return_pointcloud", False)) or is_normal
         want = (E, S, H, W, 3) if pc else (E, S, H, W)
         if tuple(pixels.shape) != want or pixels.dtype != torch.float32 or not pixels.is_contiguous():
             raise ValueError(f"pixels must be contiguous float32 {want}")
@@ -173,16 +177,18 @@ class RaySensor:
         noise = getattr(cfg, "sensor_noise", None)
         self.noise_enabled = bool(noise is not None and getattr(noise, "enable_sensor_noise", False))
         s = AgxHp2Sensor()
-        s.kind = _lib.SENSOR_CAMERA if st == "camera" else _lib.SENSOR_LIDAR
+        s.kind = kinds[st]
+        s.baseline = float(getattr(cfg, "baseline", 0.0))
+        s.normal_in_world_frame = int(bool(getattr(cfg, "normal_in_world_frame", getattr(cfg, "pointcloud_in_world_frame", True))))
         s.width, s.height, s.num_sensors = W, H, S
         s.calculate_depth = int(bool(getattr(cfg, "calculate_depth", False)))
-        s.return_pointcloud = int(pc)
+        s.return_pointcloud = int(pc and not is_normal)
         s.pointcloud_in_world_frame = int(bool(getattr(cfg, "pointcloud_in_world_frame", False)))
         s.segmentation = int(seg_pixels is not None)
-        s.fuse_epilogue = int(not self.noise_enabled)
+        s.fuse_epilogue = int(not self.noise_enabled and not is_normal)  # limits only for camera/lidar/stereo (warp_sensor.py:198-200)
         s.normalize_range = int(bool(cfg.normalize_range))
         self.ray_table = None
-        if st == "camera":
+        if "camera" in st:
             kinv, cx, cy = camera_intrinsics(W, H, cfg.horizontal_fov_deg)
             for i, v in enumerate(kinv.reshape(-1)):
                 s.kinv[i] = float(v)

@@ -214,10 +214,15 @@ typedef struct AgxHp2Scene {
     float* tris;                /* [E][K*L][12]  (v0.xyz, seg bits | e1.xyz, 0 | e2.xyz, 0) */
     float* nodes;               /* [E][2P-1][8]  (lo.xyz, 0 | hi.xyz, 0), heap order, leaves last */
     int32_t* leaf_object;       /* [E][max(P,4)] object index of each Morton-sorted leaf, -1 = empty */
+    int32_t* face_offset;       /* [E][K] index of each object's first triangle in the env's concatenated mesh
+                                   (the face id of the normal+faceID sensors); may be NULL if those are unused */
 } AgxHp2Scene;
 
-#define AGX_SENSOR_CAMERA 0
-#define AGX_SENSOR_LIDAR 1
+#define AGX_SENSOR_CAMERA 0              /* warp_camera_kernels.py:125-282 */
+#define AGX_SENSOR_LIDAR 1               /* warp_lidar_kernels.py:13-86,130-194 */
+#define AGX_SENSOR_STEREO_CAMERA 2       /* warp_stereo_camera_kernels.py (depth/range +- seg with occlusion re-cast) */
+#define AGX_SENSOR_NORMAL_FACEID_CAMERA 3 /* warp_camera_kernels.py:70-121 */
+#define AGX_SENSOR_NORMAL_FACEID_LIDAR 4  /* warp_lidar_kernels.py:90-126 */
 
 /* One sensor type on every robot.  Replaces WarpSensor.update (sensors/warp/warp_sensor.py:177-200)
  * = pose compose (:180-187) + WarpCam/WarpLidar.capture (warp_cam.py:172-182, warp_lidar.py) +
@@ -234,17 +239,19 @@ typedef struct AgxHp2Sensor {
     float far_plane;            /* = max_range (warp_cam.py:21) */
     float max_range, min_range, far_out_of_range_value, near_out_of_range_value;
     float frame_quat[4];        /* sensor data frame (warp_sensor.py:100-105) */
+    float baseline;             /* stereo baseline (stereo_camera_config.py:9) */
+    int32_t normal_in_world_frame; /* normal+faceID sensors */
     int32_t robot_pose_stride;  /* floats between robot poses (13 for robot_state_tensor rows) */
     int32_t pad_;
     const float* robot_pose;    /* [E,stride] x y z qx qy qz qw ... */
     const float* mount;         /* [E,S,7] sensor_local_position + sensor_local_orientation */
     const float* ray_table;     /* [H,W,3] LiDAR ray vectors (warp_lidar.py:40-64) or NULL */
-    float* pixels;              /* [E,S,H,W] or [E,S,H,W,3]  (depth_range_pixels) */
-    int32_t* seg_pixels;        /* [E,S,H,W] (segmentation_pixels) or NULL */
+    float* pixels;              /* [E,S,H,W], or [E,S,H,W,3] for pointclouds / normals (depth_range_pixels) */
+    int32_t* seg_pixels;        /* [E,S,H,W] segmentation ids (or face ids for the normal+faceID kinds), or NULL */
 } AgxHp2Sensor;
 
 /* bytes the caller must allocate for scene->tris / nodes / leaf_object (per env) */
-uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which /*0 tris, 1 nodes, 2 leaf_object*/);
+uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which /*0 tris, 1 nodes, 2 leaf_object, 3 face_offset*/);
 
 /* Re-transform triangles + rebuild the BVH of the envs selected by `mask` ([E] bool, NULL = all).
  * Replaces WarpEnv.reset_idx (warp_env_manager.py:40-54). */

@@ -163,7 +163,7 @@ static int closest_hit(const float* T, int n, v3 o, v3 d, float max_t, float* t_
 }
 
 typedef struct Hp2oSensor {
-    int32_t kind;            /* 0 camera, 1 lidar */
+    int32_t kind;            /* 0 camera, 1 lidar, 2 stereo camera, 3 normal+faceID camera, 4 normal+faceID lidar */
     int32_t width, height, num_sensors;
     int32_t calculate_depth; /* camera: depth (1) or range (0) image */
     int32_t return_pointcloud, pointcloud_in_world_frame, segmentation;
@@ -174,6 +174,8 @@ typedef struct Hp2oSensor {
     float far_plane;         /* = max_range (warp_cam.py:21) */
     float max_range, min_range, far_out_of_range_value, near_out_of_range_value;
     float frame_quat[4];     /* quat_from_euler(euler_frame_rot_deg) (warp_sensor.py:100-105) */
+    float baseline;          /* stereo: config/sensor_config/camera_config/stereo_camera_config.py:9 */
+    int32_t normal_in_world_frame; /* normal+faceID sensors (base_normal_faceID_camera_config.py) */
 } Hp2oSensor;
 
 static inline v3 kinv_mul(const float* k, v3 c) {
@@ -215,22 +217,30 @@ void hp2o_cast(const Hp2oSensor* s, int n_envs, const float* robot_pose, const f
             sp.x += rpos.x; sp.y += rpos.y; sp.z += rpos.z;
             q4 sq = quat_mul(rq, quat_mul(lq, qf));
             v3 rd_p = {0, 0, 0};
-            if (s->kind == 0) {
+            const int is_cam = (s->kind == 0 || s->kind == 2 || s->kind == 3);
+            const int norm_uv = s->return_pointcloud || s->kind == 3; /* pointcloud + normal kernels normalise uv */
+            v3 stereo_pos = sp;
+            if (s->kind == 2) {
+                v3 off = {-s->baseline, 0.0f, 0.0f};
+                v3 ro = quat_rotate(sq, off);
+                stereo_pos.x = sp.x + ro.x; stereo_pos.y = sp.y + ro.y; stereo_pos.z = sp.z + ro.z;
+            }
+            if (is_cam) {
                 v3 cp = {(float)s->c_x, (float)s->c_y, 1.0f};
                 v3 uvp = kinv_mul(s->kinv, cp);
-                if (s->return_pointcloud) uvp = normalize3(uvp);
+                if (norm_uv) uvp = normalize3(uvp);
                 rd_p = normalize3(quat_rotate(sq, uvp));
             }
             for (int y = 0; y < H; ++y) {
                 for (int x = 0; x < W; ++x) {
                     v3 uv, rd;
                     float mult = 1.0f, max_t = s->far_plane;
-                    if (s->kind == 0) {
+                    if (is_cam) {
                         v3 cc = {(float)x, (float)y, 1.0f};
                         uv = kinv_mul(s->kinv, cc);
-                        if (s->return_pointcloud) uv = normalize3(uv); /* quirk: only the pointcloud kernels normalise uv */
+                        if (norm_uv) uv = normalize3(uv); /* quirk: only the pointcloud / normal kernels normalise uv */
                         rd = normalize3(quat_rotate(sq, uv));
-                        if (!s->return_pointcloud && s->calculate_depth) {
+                        if (s->kind != 3 && !s->return_pointcloud && s->calculate_depth) {
                             mult = dot3(rd, rd_p);
                             max_t = s->far_plane / mult; /* warp_camera_kernels.py:221,275 */
                         }
@@ -241,14 +251,54 @@ void hp2o_cast(const Hp2oSensor* s, int n_envs, const float* robot_pose, const f
                         rd = normalize3(quat_rotate(sq, uv));
                     }
                     float t = 0.0f;
-                    int hit = closest_hit(T, nt, sp, rd, max_t, &t, NULL);
+                    v3 nrm = {0.0f, 0.0f, 0.0f};
+                    int hit = closest_hit(T, nt, sp, rd, max_t, &t, &nrm);
                     float dist = NO_HIT_RAY_VAL;
                     int32_t sv = NO_HIT_SEG_VAL;
+                    size_t pix = (((size_t)e * S + c) * H + y) * W + x;
+                    if (s->kind == 3 || s->kind == 4) {
+                        /* normal + face id: warp_camera_kernels.py:70-121, warp_lidar_kernels.py:90-126 */
+                        v3 o = {0.0f, 0.0f, 0.0f};
+                        if (hit >= 0) {
+                            if (s->normal_in_world_frame) o = nrm;
+                            else if (s->kind == 3) {
+                                v3 ez = {0.0f, 0.0f, 1.0f}, ey = {0.0f, 1.0f, 0.0f};
+                                o.x = dot3(nrm, rd_p); o.y = dot3(nrm, cross3(rd_p, ez)); o.z = dot3(nrm, cross3(rd_p, ey));
+                            } else {
+                                q4 qi = {-sq.x, -sq.y, -sq.z, sq.w};
+                                o = normalize3(quat_rotate(qi, nrm));
+                            }
+                        }
+                        pixels[pix * 3 + 0] = o.x; pixels[pix * 3 + 1] = o.y; pixels[pix * 3 + 2] = o.z;
+                        if (seg) seg[pix] = hit;  /* face index, -1 on a miss */
+                        continue;
+                    }
+                    if (s->kind == 2) {
+                        /* stereo occlusion: warp_stereo_camera_kernels.py:205-222 */
+                        float t2;
+                        v3 ep, dv, rrev;
+                        dist = -1.0f; /* INVALID_PIXEL_VAL */
+                        if (hit >= 0) {
+                            ep.x = fmaf(rd.x * t, 0.999f, sp.x); ep.y = fmaf(rd.y * t, 0.999f, sp.y); ep.z = fmaf(rd.z * t, 0.999f, sp.z);
+                            dv = sub3(stereo_pos, ep);
+                            float dl = sqrtf(dot3(dv, dv));
+                            rrev = normalize3(dv);
+                            if (closest_hit(T, nt, ep, rrev, dl, &t2, NULL) < 0) { dist = t * mult; sv = SG[hit]; }
+                        } else {
+                            ep.x = sp.x + (rd.x * s->far_plane) / mult; ep.y = sp.y + (rd.y * s->far_plane) / mult; ep.z = sp.z + (rd.z * s->far_plane) / mult;
+                            dv = sub3(stereo_pos, ep);
+                            float dl = sqrtf(dot3(dv, dv));
+                            rrev = normalize3(dv);
+                            if (closest_hit(T, nt, ep, rrev, dl, &t2, NULL) < 0) dist = NO_HIT_RAY_VAL;
+                        }
+                        pixels[pix] = s->fuse_epilogue ? range_epilogue(s, dist) : dist;
+                        if (seg) seg[pix] = sv;
+                        continue;
+                    }
                     if (hit >= 0) {
                         dist = mult * t;
                         sv = SG[hit];
                     }
-                    size_t pix = (((size_t)e * S + c) * H + y) * W + x;
                     if (s->return_pointcloud) {
                         v3 p;
                         if (s->pointcloud_in_world_frame) {
@@ -258,10 +308,10 @@ void hp2o_cast(const Hp2oSensor* s, int n_envs, const float* robot_pose, const f
                         }
                         if (s->fuse_epilogue && !s->pointcloud_in_world_frame) {
                             /* warp_sensor.py:203-215: norm-based clipping of the whole point */
-                            float nrm = sqrtf(dot3(p, p));
-                            if (nrm > s->max_range) { p.x = p.y = p.z = s->far_out_of_range_value; }
-                            nrm = sqrtf(dot3(p, p));
-                            if (nrm < s->min_range) { p.x = p.y = p.z = s->near_out_of_range_value; }
+                            float nrm2 = sqrtf(dot3(p, p));
+                            if (nrm2 > s->max_range) { p.x = p.y = p.z = s->far_out_of_range_value; }
+                            nrm2 = sqrtf(dot3(p, p));
+                            if (nrm2 < s->min_range) { p.x = p.y = p.z = s->near_out_of_range_value; }
                             if (s->normalize_range) { p.x /= s->max_range; p.y /= s->max_range; p.z /= s->max_range; }
                         }
                         pixels[pix * 3 + 0] = p.x; pixels[pix * 3 + 1] = p.y; pixels[pix * 3 + 2] = p.z;

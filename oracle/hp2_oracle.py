@@ -19,6 +19,7 @@ class Hp2oSensor(C.Structure):
         ("c_x", C.c_int32), ("c_y", C.c_int32), ("kinv", C.c_float * 9), ("far_plane", C.c_float),
         ("max_range", C.c_float), ("min_range", C.c_float), ("far_out_of_range_value", C.c_float),
         ("near_out_of_range_value", C.c_float), ("frame_quat", C.c_float * 4),
+        ("baseline", C.c_float), ("normal_in_world_frame", C.c_int32),
     ]
 
 
@@ -104,9 +105,9 @@ def build_world_tris(obj_pose, obj_template, obj_seg_counter, tmpl_tri_offset, t
 def cast(sensor: Hp2oSensor, robot_pose, mount, ray_table, tris, seg_ids, tri_count):
     E = robot_pose.shape[0]
     S, H, W = sensor.num_sensors, sensor.height, sensor.width
-    shape = (E, S, H, W, 3) if sensor.return_pointcloud else (E, S, H, W)
+    shape = (E, S, H, W, 3) if (sensor.return_pointcloud or sensor.kind in (3, 4)) else (E, S, H, W)
     pix = np.zeros(shape, np.float32)
-    seg = np.zeros((E, S, H, W), np.int32) if sensor.segmentation else None
+    seg = np.zeros((E, S, H, W), np.int32) if (sensor.segmentation or sensor.kind in (3, 4)) else None
     rp = np.ascontiguousarray(robot_pose, np.float32)
     mt = np.ascontiguousarray(mount, np.float32)
     rt = np.ascontiguousarray(ray_table, np.float32) if ray_table is not None else None

@@ -90,16 +90,18 @@ def cfg_variant(base, **kw):
 
 def oracle_sensor(cfg, fuse=True):
     s = RO.Hp2oSensor()
-    s.kind = 0 if cfg.sensor_type == "camera" else 1
+    s.kind = {"camera": 0, "lidar": 1, "stereo_camera": 2, "normal_faceID_camera": 3, "normal_faceID_lidar": 4}[cfg.sensor_type]
+    s.baseline = float(getattr(cfg, "baseline", 0.0))
+    s.normal_in_world_frame = int(getattr(cfg, "normal_in_world_frame", getattr(cfg, "pointcloud_in_world_frame", True)))
     s.width, s.height, s.num_sensors = cfg.width, cfg.height, cfg.num_sensors
     s.calculate_depth = int(getattr(cfg, "calculate_depth", False))
-    s.return_pointcloud = int(cfg.return_pointcloud)
+    s.return_pointcloud = int(cfg.return_pointcloud and s.kind < 3)
     s.pointcloud_in_world_frame = int(cfg.pointcloud_in_world_frame)
     s.segmentation = int(cfg.segmentation_camera)
-    s.fuse_epilogue = int(fuse)
+    s.fuse_epilogue = int(fuse and s.kind < 3)
     s.normalize_range = int(cfg.normalize_range)
     table = None
-    if s.kind == 0:
+    if s.kind in (0, 2, 3):
         kinv, cx, cy = RO.camera_kinv(cfg.width, cfg.height, cfg.horizontal_fov_deg)
         for i, v in enumerate(kinv.reshape(-1)):
             s.kinv[i] = float(v)

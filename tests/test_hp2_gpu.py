@@ -220,3 +220,39 @@ def test_collision_flags_match_oracle(K):
     c2[3] = True
     scene.collide(robot.to(DEV), 0.18384776, c2, None)
     assert torch.equal(c2, crashes)
+
+
+def test_stereo_camera_matches_oracle():
+    """b5: depth + occlusion re-cast towards the stereo partner (invalid -1 / miss 1000 rules)."""
+    cfg = H.cfg_variant(H.CamCfg, sensor_type="stereo_camera", baseline=-0.095, height=40, width=56)
+    sc = H.make_scene(6, 44, seed=130, extent=3.0)
+    scene, sensor, robot, mount, _ = build(sc, cfg, seed=13, mount_seed=14)
+    sensor.capture()
+    ref_pix, ref_seg = oracle_cast(sc, cfg, sensor, robot, mount)
+    check(sensor, ref_pix, ref_seg)
+    near = cfg.near_out_of_range_value / cfg.max_range
+    assert (ref_pix == near).mean() > 0.001  # some pixels are occluded from the partner camera
+
+
+@pytest.mark.parametrize("kind,world", [("normal_faceID_camera", True), ("normal_faceID_camera", False),
+                                        ("normal_faceID_lidar", True), ("normal_faceID_lidar", False)])
+def test_normal_faceid_sensors_match_oracle(kind, world):
+    """b3: hit normal (world / sensor frame) + face index of the env's concatenated mesh."""
+    base = H.CamCfg if "camera" in kind else H.LidarCfg
+    cfg = H.cfg_variant(base, sensor_type=kind, return_pointcloud=True, normal_in_world_frame=world,
+                        pointcloud_in_world_frame=world, height=24, width=40)
+    sc = H.make_scene(5, 30, seed=140, extent=4.0)
+    pose_d = sc["pose"].to(DEV)
+    scene = RayScene(sc["templates"], [0] * 5, [1] * 5, sc["tm"], sc["ctr"], pose_d, DEV)
+    scene.update()
+    robot = H.robot_poses(5, 15)
+    pix = torch.zeros(5, 1, 24, 40, 3, device=DEV)
+    face = torch.zeros(5, 1, 24, 40, dtype=torch.int32, device=DEV)
+    sensor = RaySensor(cfg, scene, robot.to(DEV), pix, face)
+    sensor.capture()
+    ref_pix, ref_face = oracle_cast(sc, cfg, sensor, robot, None)
+    check(sensor, ref_pix, ref_face)
+    hit = ref_face >= 0
+    assert hit.any() and (ref_face[~hit] == -1).all() and ref_face.max() < 30 * 12
+    nrm = np.linalg.norm(ref_pix[hit], axis=-1)
+    assert np.allclose(nrm, 1.0, atol=1e-5)
