@@ -491,9 +491,11 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = fminf(fmaxf(act[i], -10.0f), 10.0f);
 
-            d = update_states(s);  // also covers physics_steps == 0
+            // every iteration runs the same instruction sequence, so n fused sub-steps are
+            // bit-identical to n single-step launches
+#pragma unroll 1
             for (int step = 0; step < cfg.physics_steps; ++step) {
-                if (step > 0) d = update_states(s);
+                d = update_states(s);
                 float ref[M];
                 if (cfg.controller == AGX_CTRL_NONE) {  // update_motor_thrusts_with_forces
 #pragma unroll
@@ -538,6 +540,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 Fx = F.x; Fy = F.y; Fz = F.z; Tx = T.x; Ty = T.y; Tz = T.z;
                 integrate(cfg, s, F, T);
             }
+            if (cfg.physics_steps == 0) d = update_states(s);
         }
 
         float o[13];

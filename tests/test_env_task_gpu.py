@@ -32,15 +32,16 @@ def test_task_surface_and_in_place_semantics():
     assert (pos0[:, 0] >= -0.8 - 1e-6).all() and (pos0[:, 0] <= -0.6 + 1e-6).all()  # ratio 0.1..0.2 of [-1,1]
     g = torch.Generator(device=DEV).manual_seed(0)
     for i in range(505):
-        a = torch.rand(300, 4, device=DEV, generator=g) * 2 - 1
+        a = (torch.rand(300, 4, device=DEV, generator=g) * 2 - 1) * 0.05  # near hover: nobody leaves the 8 m ball
         out = task.step(a)
         assert out[0] is obs and out[1] is rew and out[2] is term and out[3] is trunc  # same objects, mutated in place
         if i == 499:
-            assert not trunc.any() and (task.sim_env.sim_steps[~term] == 500).any()
+            assert not trunc.any() and not term.any() and (task.sim_env.sim_steps == 500).all()
     torch.cuda.synchronize()
     assert torch.isfinite(obs["observations"]).all() and torch.isfinite(rew).all()
     assert (task.sim_env.sim_steps <= 501).all()
-    assert int(task.sim_env.engine.episode_count.min()) >= 2  # initial reset + truncation at step 501
+    assert int(task.sim_env.engine.episode_count.min()) == 2  # initial reset + truncation at step 501
+    assert (task.sim_env.sim_steps == 4).all()
     assert torch.equal(obs["observations"][:, 3:7], gtd["robot_orientation"])
 
 
@@ -55,18 +56,36 @@ def test_task_torch_rng_mode_follows_reference_call_order():
     finally:
         cfg.args = old
     N = 64
-    torch.manual_seed(1234)
-    task.reset()
+    # record every torch.rand the reset makes: shapes + order must be the reference's call order
+    # (IGE bounds x2 [N,3] -> robot state [N,13] -> motor tau_inc, tau_dec, thrust, k [N,M])
+    calls, orig = [], torch.rand
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        calls.append(out.clone())
+        return out
+
+    torch.rand = spy
+    try:
+        torch.manual_seed(1234)
+        task.reset()
+    finally:
+        torch.rand = orig
+    assert [tuple(c.shape) for c in calls] == [(N, 3), (N, 3), (N, 13), (N, 4), (N, 4), (N, 4), (N, 4)]
     eng = task.sim_env.engine
-    torch.manual_seed(1234)
-    r = lambda *s: torch.rand(*s, device=DEV).cpu()
     model = H.oracle_model_from_spec(task.sim_env.spec)
-    draws = O.ResetDraws(r(N, 3), r(N, 3), r(N, 13), None, None, None, None, r(N, 4), r(N, 4), r(N, 4), r(N, 4))
+    c = [x.cpu() for x in calls]
+    draws = O.ResetDraws(c[0], c[1], c[2], None, None, None, None, c[3], c[4], c[5], c[6])
     st = O.make_state(model, N)
     O.reset_envs(model, st, torch.ones(N, dtype=torch.bool), draws)
     H.assert_close(eng.root_state, st.root, "reset state (torch rng order)", scale=1.0)
     H.assert_close(eng.motor_thrust, st.thrust, "reset thrust")
     H.assert_close(eng.k_thrust, st.k_thrust, "reset k", scale=1e-5)
+    # same seed -> same episode start (determinism of the torch-RNG mode)
+    first = eng.root_state.clone()
+    torch.manual_seed(1234)
+    task.reset()
+    assert torch.equal(eng.root_state, first)
     # a step without resets must not consume the generator
     s0 = torch.cuda.get_rng_state(0).clone()
     task.step(torch.zeros(N, 4, device=DEV))

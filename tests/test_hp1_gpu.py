@@ -170,10 +170,17 @@ def test_fused_position_task_step(case, strict):
                     strict_stale_obs=strict)
     episodes = np.zeros(N, dtype=np.int64)
     target = torch.zeros(N, 3)
-    n_resets = 0
+    n_resets = n_ill = 0
     for step in range(30):
         actions = torch.rand(N, spec.num_actions, generator=g) * 2 - 1
         H.sync_engine_from_oracle(eng, st)
+        # conditioning: asin() in get_euler_xyz has slope 1/sqrt(1-x^2); within ~0.6 deg of gimbal lock a
+        # 1-ulp difference in sin(pitch) moves the Euler angles (and the torque built on them) by far
+        # more than 1e-5 in ANY two fp32 implementations.  Such envs (expected ~1 per 10^4 uniformly
+        # random attitudes) are checked for boundedness only.
+        q0 = st.root[:, 3:7]
+        sinp = 2.0 * (q0[:, 3] * q0[:, 1] - q0[:, 2] * q0[:, 0])
+        ok = (sinp.abs() < 0.99995).numpy()
         eng.position_task_step(actions.to(DEV))
         draws = _philox_draws(seed, off + np.arange(N), episodes, M)
         st_ref = st
@@ -190,15 +197,19 @@ def test_fused_position_task_step(case, strict):
         assert torch.equal(eng.sim_steps.cpu(), st.sim_steps), f"step {step} sim_steps"
         assert np.array_equal(eng.episode_count.cpu().numpy(), episodes), f"step {step} episode counters"
         H.assert_close(eng.reward, rew, f"step {step} reward", scale=1.0)
-        H.assert_close(eng.root_state, st.root, f"step {step} root", scale=1.0)
-        H.assert_close(eng.obs, obs, f"step {step} obs", scale=1.0)
-        H.assert_close(eng.motor_thrust, st.thrust, f"step {step} thrust")
+        assert torch.isfinite(eng.root_state).all() and torch.isfinite(eng.motor_thrust).all()
+        n_ill += int((~ok).sum())
+        for nm, sl in (("pos", slice(0, 3)), ("quat", slice(3, 7)), ("linvel", slice(7, 10)), ("angvel", slice(10, 13))):
+            H.assert_close(eng.root_state[:, sl].cpu()[ok], st.root[:, sl][ok], f"step {step} root {nm}")
+            H.assert_close(eng.obs[:, sl].cpu()[ok], obs[:, sl][ok], f"step {step} obs {nm}")
+        H.assert_close(eng.motor_thrust.cpu()[ok], st.thrust[ok], f"step {step} thrust")
         if eng.k_thrust is not None and spec.use_rps:
             H.assert_close(eng.k_thrust, st.k_thrust, f"step {step} k", scale=1e-5)
         H.assert_close(eng.tau_inc, st.tau_inc, f"step {step} tau_inc", scale=0.01)
         if spec.randomize_params:
             H.assert_close(eng.K_rot, st.K_rot, f"step {step} K_rot")
     assert n_resets >= N  # every env truncated at least once in the window
+    assert n_ill <= 8  # ill-conditioned samples are rare
 
 
 def test_stale_observation_quirk():

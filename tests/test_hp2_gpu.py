@@ -254,5 +254,6 @@ def test_normal_faceid_sensors_match_oracle(kind, world):
     check(sensor, ref_pix, ref_face)
     hit = ref_face >= 0
     assert hit.any() and (ref_face[~hit] == -1).all() and ref_face.max() < 30 * 12
-    nrm = np.linalg.norm(ref_pix[hit], axis=-1)
-    assert np.allclose(nrm, 1.0, atol=1e-5)
+    if world or "lidar" in kind:  # the camera-frame basis (rd_p, rd_p x ez, rd_p x ey) is not orthonormal
+        nrm = np.linalg.norm(ref_pix[hit], axis=-1)
+        assert np.allclose(nrm, 1.0, atol=1e-5)
