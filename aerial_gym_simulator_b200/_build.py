@@ -13,7 +13,9 @@ LIB = os.path.join(PKG, "libaerial_gym_b200.so")
 # fmaf() so that the C oracle (oracle/hp2_oracle.c, -ffp-contract=off) is bit-reproducible.
 UNITS = [
     ("agx_common.cu", []),
-    ("hp1.cu", []),
+    # hp1: 2-ulp division / sqrt (no slow-path branches): the step is instruction-fetch bound at
+    # 65,536 envs (profiles/hp1_step_r1.md: stall_no_instruction dominates), every instruction counts
+    ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false", "-DAGX_FAST_TRIG"]),
     ("hp2_raycast.cu", ["-fmad=false"]),
 ]
 NVCC_FLAGS = [

@@ -7,6 +7,14 @@
 
 namespace agx {
 
+// sin/cos of an angle in [-2pi, 2pi].  AGX_FAST_TRIG: MUFU.SIN/COS (__sincosf, abs error <= 2^-21.4
+// on [-pi, pi], CUDA C Programming Guide table 9) instead of the ~40-instruction libdevice path.
+#ifdef AGX_FAST_TRIG
+__device__ __forceinline__ void sincos_(float x, float* s, float* c) { __sincosf(x, s, c); }
+#else
+__device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+#endif
+
 #define AGX_PI_F 3.14159265358979323846f
 #define AGX_TWO_PI_F 6.28318530717958647692f
 
@@ -117,9 +125,9 @@ __device__ __forceinline__ V3 euler_xyz_0_2pi(Q4 q) {
 // utils/math.py:155-172 quat_from_euler_xyz
 __device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw) {
     float sy, cy, sr, cr, sp, cp;
-    sincosf(yaw * 0.5f, &sy, &cy);
-    sincosf(roll * 0.5f, &sr, &cr);
-    sincosf(pitch * 0.5f, &sp, &cp);
+    sincos_(yaw * 0.5f, &sy, &cy);
+    sincos_(roll * 0.5f, &sr, &cr);
+    sincos_(pitch * 0.5f, &sp, &cp);
     Q4 q;
     q.w = cy * cr * cp + sy * sr * sp;
     q.x = cy * sr * cp - sy * cr * sp;
@@ -131,7 +139,7 @@ __device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw
 // cos(0)=1, sin(0)=0 make the products exact, so only the yaw half-angle survives.
 __device__ __forceinline__ Q4 quat_from_yaw(float yaw) {
     float sy, cy;
-    sincosf(yaw * 0.5f, &sy, &cy);
+    sincos_(yaw * 0.5f, &sy, &cy);
     return Q4{0.0f, 0.0f, sy, cy};
 }
 

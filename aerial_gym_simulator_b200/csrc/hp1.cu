@@ -157,8 +157,8 @@ __device__ __forceinline__ V3 compute_acceleration(const EnvState& s, const Deri
 // plus the generic roll/pitch entries the reference writes) --------------------------------
 __device__ __forceinline__ V3 euler_rates_to_body_rates(V3 euler, V3 rates) {
     float sp, cp, sr, cr;
-    sincosf(euler.y, &sp, &cp);
-    sincosf(euler.x, &sr, &cr);
+    sincos_(euler.y, &sp, &cp);
+    sincos_(euler.x, &sr, &cr);
     // T = [[1,0,-sp],[0,cr,sr*cp],[0,-sr,cr*cp]]
     return V3{rates.x + (-sp) * rates.z, cr * rates.y + (sr * cp) * rates.z, (-sr) * rates.y + (cr * cp) * rates.z};
 }
@@ -183,7 +183,7 @@ __device__ __forceinline__ Q4 desired_orientation_pos_vel(V3 f, float yaw) {
     float fn = norm3(f);
     V3 b3{f.x / fn, f.y / fn, f.z / fn};
     float sy, cy;
-    sincosf(yaw, &sy, &cy);
+    sincos_(yaw, &sy, &cy);
     V3 b2 = cross(b3, V3{cy, sy, 0.0f});
     float n2 = norm3(b2);
     b2 = V3{b2.x / n2, b2.y / n2, b2.z / n2};
@@ -313,7 +313,7 @@ __device__ __forceinline__ void integrate(const AgxHp1Config& cfg, EnvState& s, 
     }
     s.x = s.x + v * dt;
     float sh, ch;
-    sincosf(0.5f * dt * wn, &sh, &ch);
+    sincos_(0.5f * dt * wn, &sh, &ch);
     float so = (wn > 0.0f) ? sh / wn : 0.0f;
     Q4 dq{w.x * so, w.y * so, w.z * so, ch};
     Q4 qn = quat_mul(dq, s.q);
@@ -571,7 +571,13 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
                 if (do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET)) {
                     uint32_t ep = buf.episode_count[env];
-                    device_rng_reset<M>(cfg, (uint32_t)(cfg.env_id_offset + env), ep, s, p);
+                    // temporaries: only they have their address taken by the out-of-line reset, so the
+                    // hot path keeps s / p in registers
+                    EnvState s2 = s;
+                    EnvParams<M> p2 = p;
+                    device_rng_reset<M>(cfg, (uint32_t)(cfg.env_id_offset + env), ep, s2, p2);
+                    s = s2;
+                    p = p2;
                     buf.episode_count[env] = ep + 1u;
                     store_reset_params<M>(buf, env, p);
                     steps = 0;  // env_manager.py:301
@@ -580,6 +586,13 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 buf.sim_steps[env] = steps;
                 if (fresh) d = update_states(s);
                 make_obs(s, d, tgt, o);
+                if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
+                    V3 vb = fresh ? d.vb : quat_rotate_inverse(s.q, s.v);
+                    V3 wb = fresh ? d.wb : quat_rotate_inverse(s.q, s.w);
+                    const size_t Ns = (size_t)N;
+                    buf.fresh_vel[env] = vb.x; buf.fresh_vel[Ns + env] = vb.y; buf.fresh_vel[2 * Ns + env] = vb.z;
+                    buf.fresh_vel[3 * Ns + env] = wb.x; buf.fresh_vel[4 * Ns + env] = wb.y; buf.fresh_vel[5 * Ns + env] = wb.z;
+                }
             }
             unsigned any = __ballot_sync(0xffffffffu, do_reset);
             if (any && lane == 0) atomicOr(buf.any_reset, 1);
@@ -640,6 +653,30 @@ hp1_refresh_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_consta
         }
         if (buf.obs) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
     }
+}
+
+// light variant of the refresh pass for the fused task step without materialised derived states:
+// if any env reset this step, obs[:,7:13] <- fresh body velocities written by the main kernel.
+__global__ void __launch_bounds__(256)
+hp1_obs_patch_kernel(int N, const float* __restrict__ fresh_vel, float* __restrict__ obs, int* any_reset) {
+    __shared__ int s_flag;
+    if (threadIdx.x == 0) {
+        int f = *reinterpret_cast<volatile int*>(any_reset);
+        s_flag = f;
+        __threadfence();
+        int arrived = atomicAdd(any_reset + 1, 1);
+        if (arrived == (int)gridDim.x - 1) {
+            any_reset[0] = 0;
+            any_reset[1] = 0;
+        }
+    }
+    __syncthreads();
+    if (s_flag == 0) return;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N) return;
+    float* o = obs + (size_t)env * 13 + 7;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[j] = fresh_vel[(size_t)j * N + env];
 }
 
 // masked reset with caller-supplied uniforms (torch RNG, reference call order) or device RNG
@@ -758,8 +795,14 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     // stale-derived-state quirk: if ANY env reset this step the reference refreshes
     // the derived states of ALL envs before the observation is read (base_multirotor.py:204-205).
     if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS)) {
-        hp1_refresh_kernel<<<g, kThreads, 0, st>>>(*cfg, *buf, 1, v);
-        rc = agx_check_launch("hp1_refresh_kernel");
+        const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
+        if (buf->fresh_vel && !derived) {
+            hp1_obs_patch_kernel<<<(cfg->num_envs + 255) / 256, 256, 0, st>>>(cfg->num_envs, buf->fresh_vel, buf->obs, buf->any_reset);
+            rc = agx_check_launch("hp1_obs_patch_kernel");
+        } else {
+            hp1_refresh_kernel<<<g, kThreads, 0, st>>>(*cfg, *buf, 1, v);
+            rc = agx_check_launch("hp1_refresh_kernel");
+        }
     }
     return rc;
 }

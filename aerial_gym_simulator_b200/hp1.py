@@ -234,6 +234,8 @@ class Hp1Engine:
         self.body_linvel = z(N, 3) if materialize_derived else None
         self.body_angvel = z(N, 3) if materialize_derived else None
         self.body_wrench = z(N, 6) if debug_wrench else None
+        # scratch for the light obs patch (only useful when derived states are not materialised)
+        self.fresh_vel = z(6, N) if (strict_stale_obs and not materialize_derived) else None
         self._actions = None
         self._buf = AgxHp1Buffers()
         self._sync_buffers()

@@ -124,6 +124,9 @@ typedef struct AgxHp1Buffers {
     uint8_t* reset_mask;      /* [N] bool, envs reset (or to be reset) this step; may be NULL */
     int32_t* any_reset;       /* [2] device scratch: [0] flag, [1] block-arrival counter; zero-initialised by caller once */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
+    float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
+                                 when the stale-observation quirk is on and no derived array is materialised; the
+                                 conditional pass then only patches obs[:,7:13] instead of recomputing.  May be NULL. */
 } AgxHp1Buffers;
 
 /* explicit uniform draws u in [0,1) for agx_hp1_reset, in the reference's call order */

@@ -170,3 +170,25 @@ ALL_CASES = [
     "quad_velocity_steering", "quadroot_attitude_euler", "octa_velocity", "octa_fully_actuated",
     "octa_position_continuous",
 ]
+
+
+def well_conditioned(model, st, actions):
+    """bool [N]: envs whose step is well conditioned in fp32.  Two places in the REFERENCE's own
+    arithmetic have unbounded slope, so two correct fp32 implementations may differ by much more than
+    1e-5 there (and the reference would differ from itself under a 1-ulp input change):
+      * get_euler_xyz: asin(sin_pitch) near |sin_pitch| = 1 (gimbal lock), utils/math.py:135;
+      * MotorModel (use_rps): sqrt(ref_thrust / k) as ref_thrust -> 0+, motor_model.py:213-242.
+    Such envs (~1e-4 of uniformly random inputs) are checked for finiteness only."""
+    q = st.root[:, 3:7]
+    sinp = 2.0 * (q[:, 3] * q[:, 1] - q[:, 2] * q[:, 0])
+    ok = sinp.abs() < 0.99995
+    if model.use_rps:
+        d = O.update_states(st.root)
+        cmd = O.controller_wrench(model, st, d, torch.clamp(actions, -10.0, 10.0))
+        if model.controller == O.CTRL_NONE:
+            ref = cmd
+        else:
+            ref = (model.pinv_allocation(cmd.dtype) @ cmd.T).T
+        thr = 5e-3 * model.max_thrust
+        ok &= ~((ref > 0) & (ref < thr)).any(dim=1)
+    return ok
