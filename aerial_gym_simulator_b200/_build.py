@@ -15,7 +15,7 @@ UNITS = [
     ("agx_common.cu", []),
     # hp1: 2-ulp division / sqrt (no slow-path branches): the step is instruction-fetch bound at
     # 65,536 envs (profiles/hp1_step_r1.md: stall_no_instruction dominates), every instruction counts
-    ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false", "-DAGX_FAST_TRIG"]),
+    ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
     ("hp2_raycast.cu", ["-fmad=false"]),
 ]
 NVCC_FLAGS = [

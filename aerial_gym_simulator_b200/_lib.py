@@ -99,7 +99,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    # AGX_LIB_PATH: A/B experiments against an alternative build of the same ABI
+    return os.environ.get("AGX_LIB_PATH", _build.LIB)
 
 
 def load():

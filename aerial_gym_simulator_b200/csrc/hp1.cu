@@ -370,10 +370,10 @@ __device__ __forceinline__ void apply_reset(const AgxHp1Config& cfg, const float
 //   block 0..2 -> state[0..11]; block 3 -> state[12], bounds_lo[0..2]; block 4 -> bounds_hi[0..2], -
 //   block 5..8 -> K_pos, K_vel, K_rot, K_angvel (xyz, -); block 9+i -> motor i: tau_inc, tau_dec, thrust, k
 template <int M>
-__device__ __noinline__ void device_rng_reset(const AgxHp1Config& cfg, uint32_t env_gid, uint32_t episode, EnvState& s,
-                                              EnvParams<M>& p) {
+__device__ __forceinline__ void device_rng_reset(const AgxHp1Config& cfg, uint32_t env_gid, uint32_t episode, EnvState& s,
+                                                 EnvParams<M>& p) {
     const uint32_t k0 = (uint32_t)(cfg.seed & 0xffffffffu), k1 = (uint32_t)(cfg.seed >> 32);
-    float us[13], ubl[3], ubh[3], ug[12], um[4 * M];
+    float us[13], ubl[3] = {0.f, 0.f, 0.f}, ubh[3] = {0.f, 0.f, 0.f}, ug[12], um[4 * M];
     U4 b;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -382,12 +382,21 @@ __device__ __noinline__ void device_rng_reset(const AgxHp1Config& cfg, uint32_t 
     }
     b = philox4x32_10(U4{env_gid, episode, 3u, 0u}, k0, k1);
     us[12] = u01(b.x); ubl[0] = u01(b.y); ubl[1] = u01(b.z); ubl[2] = u01(b.w);
-    b = philox4x32_10(U4{env_gid, episode, 4u, 0u}, k0, k1);
-    ubh[0] = u01(b.x); ubh[1] = u01(b.y); ubh[2] = u01(b.z);
+    // blocks whose draws cannot matter are skipped (a degenerate range maps every u to the same value)
+    const bool bounds_hi_random = cfg.bounds_hi_min[0] != cfg.bounds_hi_max[0] || cfg.bounds_hi_min[1] != cfg.bounds_hi_max[1] ||
+                                  cfg.bounds_hi_min[2] != cfg.bounds_hi_max[2];
+    if (bounds_hi_random) {
+        b = philox4x32_10(U4{env_gid, episode, 4u, 0u}, k0, k1);
+        ubh[0] = u01(b.x); ubh[1] = u01(b.y); ubh[2] = u01(b.z);
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        b = philox4x32_10(U4{env_gid, episode, (uint32_t)(5 + i), 0u}, k0, k1);
-        ug[3 * i] = u01(b.x); ug[3 * i + 1] = u01(b.y); ug[3 * i + 2] = u01(b.z);
+    for (int i = 0; i < 12; ++i) ug[i] = 0.0f;
+    if (cfg.flags & AGX_F_RANDOMIZE_GAINS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            b = philox4x32_10(U4{env_gid, episode, (uint32_t)(5 + i), 0u}, k0, k1);
+            ug[3 * i] = u01(b.x); ug[3 * i + 1] = u01(b.y); ug[3 * i + 2] = u01(b.z);
+        }
     }
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -468,16 +477,21 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         const int env = env0 + lane;
         const bool valid = lane < n_valid;
 
-        float r[13];
-        load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        // every global load of the step is issued here, before the first use, so their DRAM
+        // latencies overlap (the kernel is latency bound at 65,536 envs)
         EnvState s;
         EnvParams<M> p;
         Derived d;
         float act[AGX_MAX_MOTORS];
         float Fx = 0, Fy = 0, Fz = 0, Tx = 0, Ty = 0, Tz = 0;
+        int steps_in = 0;
+        V3 tgt{0.f, 0.f, 0.f};
         if (valid) {
-            s = unpack(r);
             load_params<M>(cfg, buf, env, p);
+            if constexpr (TASK) {
+                steps_in = buf.sim_steps[env];
+                if (buf.target_position) tgt = ld3(buf.target_position + (size_t)env * 3);
+            }
             if (A == 4) {
                 float4 a4 = reinterpret_cast<const float4*>(buf.actions)[env];
                 act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
@@ -490,6 +504,11 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             // clip_actions, robots/base_multirotor.py:207-211
 #pragma unroll
             for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = fminf(fmaxf(act[i], -10.0f), 10.0f);
+        }
+        float r[13];
+        load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        if (valid) {
+            s = unpack(r);
 
             // every iteration runs the same instruction sequence, so n fused sub-steps are
             // bit-identical to n single-step launches
@@ -548,8 +567,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         if constexpr (TASK) {
             if (valid) {
                 // ---- a16 reward + flags: position_setpoint_task.py:205-282 (stale derived) -----
-                int steps = buf.sim_steps[env] + 1;  // env_manager.py:429
-                V3 tgt = buf.target_position ? ld3(buf.target_position + (size_t)env * 3) : V3{0, 0, 0};
+                int steps = steps_in + 1;  // env_manager.py:429
                 V3 e = quat_apply(quat_conj(d.qveh), tgt - s.x);
                 float dist = norm3(e);
                 float pos_reward = 3.0f * expf(-8.0f * dist * dist) + 2.0f * expf(-4.0f * dist * dist);
