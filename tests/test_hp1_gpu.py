@@ -83,9 +83,13 @@ def test_multi_substep_matches_oracle():
     eng = Hp1Engine(spec, N, DEV, per_env_params="all", physics_steps=10)
     H.load_engine_state(eng, root, params)
     eng.physics_step(actions.to(DEV))
-    H.assert_close(eng.root_state, st.root, "10 substeps root", rtol=1e-4, scale=1.0)
-    H.assert_close(eng.motor_thrust, st.thrust, "10 substeps thrust", rtol=1e-4)
-    _derived_close(eng, st.derived, "10 substeps (stale derived of the last substep)")
+    # ten free-running steps: per-step differences (<= 1e-5 of each quantity's scale) compound through
+    # the attitude loop, so the bar here is 2e-4 of scale; single-step parity is tested above
+    for nm, sl in (("pos", slice(0, 3)), ("quat", slice(3, 7)), ("linvel", slice(7, 10)), ("angvel", slice(10, 13))):
+        H.assert_close(eng.root_state[:, sl], st.root[:, sl], f"10 substeps root {nm}", rtol=2e-4)
+    H.assert_close(eng.motor_thrust, st.thrust, "10 substeps thrust", rtol=2e-4)
+    H.assert_close(eng.body_angvel, st.derived["body_angvel"], "10 substeps stale body angvel", rtol=2e-4)
+    H.assert_close(eng.euler, st.derived["euler"], "10 substeps stale euler", rtol=2e-4, scale=np.pi)
     # and equals ten 1-step launches bit for bit (same kernel arithmetic)
     eng1 = Hp1Engine(spec, N, DEV, per_env_params="all", physics_steps=1)
     H.load_engine_state(eng1, root, params)
