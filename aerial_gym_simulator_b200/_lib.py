@@ -129,6 +129,7 @@ def load():
         "agx_hp1_refresh": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_int, C.c_void_p],
         "agx_hp2_update_scene": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_void_p],
         "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
+        "agx_p2p_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     }.items():
         fn = getattr(lib, name)

@@ -60,3 +60,58 @@ class ObsAllGather:
             for r, (o, c) in enumerate(zip(self.offs, self.counts)):
                 self.out[o:o + c].copy_(self.pad_out[r * mc: r * mc + c])
         return self.out
+
+
+class P2PObsAllGather:
+    """Same contract as ObsAllGather (equal shards only), but the collective is ONE hand-written
+    kernel of NVLink peer stores + a flag handshake (csrc/p2p_allgather.cu) over buffers obtained
+    from a torch symmetric-memory rendezvous -- no NCCL call on the step path."""
+
+    def __init__(self, local_count: int, feat: int, device, group=None, dtype=torch.float32):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib.load()
+        self._check = _lib.check
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if dtype != torch.float32:
+            raise ValueError("float32 only")
+        self.bytes = local_count * feat * 4
+        if self.bytes % 16:
+            raise ValueError("shard bytes must be a multiple of 16")
+        self.device = torch.device(device)
+        # two gathered buffers, alternated by epoch parity: a peer can run at most one epoch ahead of
+        # the slowest reader (everybody waits for everybody's flag), so epoch e+1 never overwrites
+        # data of epoch e that a slower rank may still be consuming
+        self.outs, self.buf_ptrs = [], []
+        for _ in range(2):
+            o = symm_mem.empty(self.world * local_count, feat, dtype=dtype, device=self.device)
+            h = symm_mem.rendezvous(o, group)
+            self.outs.append(o)
+            self.buf_ptrs.append(torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=self.device))
+            setattr(self, f"_h{len(self.outs)}", h)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        self.h_flags = symm_mem.rendezvous(self.flags, group)
+        self.flag_ptrs = torch.tensor(list(self.h_flags.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self.scratch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)  # every rank's flags are zeroed before anybody publishes epoch 1
+
+    def __call__(self, obs_local: torch.Tensor) -> torch.Tensor:
+        C = self._C
+        if obs_local.numel() * 4 != self.bytes or not obs_local.is_contiguous():
+            raise ValueError("obs_local must be the contiguous local shard")
+        self.epoch += 1
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        b = self.epoch & 1
+        self._check(self._lib.agx_p2p_allgather(
+            C.c_void_p(obs_local.data_ptr()), C.c_void_p(self.buf_ptrs[b].data_ptr()), C.c_void_p(self.flag_ptrs.data_ptr()),
+            self.world, self.rank, C.c_uint64(self.bytes), C.c_uint32(self.epoch), C.c_void_p(self.scratch.data_ptr()), stream),
+            "agx_p2p_allgather")
+        return self.outs[b]

@@ -48,7 +48,7 @@ def workload_config(n_gpus, extra=None):
         "dt": 0.01,
         "episode_len_steps": 500,
         "actions": "U(-1,1) resampled from 8 pre-generated batches",
-        "parallelism": f"env-sharded x{n_gpus}" + (" + NCCL all-gather(obs)" if n_gpus > 1 else ""),
+        "parallelism": f"env-sharded x{n_gpus}" + (" + all-gather(obs) every step" if n_gpus > 1 else ""),
         "l2": "inputs larger than L2: timed loop rotates over 16 replicas of the env batch (~190 MB)",
     }
     if extra:
@@ -180,7 +180,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from aerial_gym_simulator_b200.distributed import ObsAllGather
+    from aerial_gym_simulator_b200.distributed import ObsAllGather, P2PObsAllGather
     from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,6 +191,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
     N = args.envs
@@ -208,7 +210,9 @@ def run_ours(args):
     eng = engines[0]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
-    gather = ObsAllGather(N, 13, world * N, dev) if world > 1 else None
+    gather = None
+    if world > 1:
+        gather = P2PObsAllGather(N, 13, dev) if args.gather == "p2p" else ObsAllGather(N, 13, world * N, dev)
     stream = torch.cuda.current_stream(dev)
 
     def step(i, mid=None, rotate=True):
@@ -336,7 +340,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_s * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world}),
+            "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world,
+                                              "obs_all_gather": (args.gather if world > 1 else None)}),
             "value_hot_l2": value_hot,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true>", "achieved": achieved, "peak": peak,
@@ -441,6 +446,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 observation all-gather: hand-written NVLink P2P kernel (default) or NCCL")
     ap.add_argument("--no-hp2", action="store_true", help="skip the secondary depth rays/sec measurement")
     ap.add_argument("--hp2-envs", type=int, default=8192)
     args = ap.parse_args()

@@ -272,6 +272,25 @@ int agx_hp2_cast(const AgxHp2Scene* scene, const AgxHp2Sensor* sensor, void* str
 int agx_hp2_collide(const AgxHp2Scene* scene, const float* robot_pose, int robot_pose_stride, float radius,
                     uint8_t* crashes, float* min_dist, void* stream);
 
+
+/* ======================================================================================
+ * Multi-GPU: observation all-gather over NVLink peer memory
+ * ====================================================================================== */
+#define AGX_MAX_PEERS 16
+
+/* One-shot all-gather written as ONE kernel of P2P stores (no NCCL on the step path): every rank
+ * copies its `bytes` (multiple of 16) of `local` into slot `rank` of EVERY peer's gathered buffer
+ * (peer_bufs[p] + rank*bytes, pointers obtained from a symmetric-memory rendezvous), publishes
+ * `epoch` into each peer's flag word `peer_flags[p][rank]` with system-scope release semantics, and
+ * the kernel does not retire before the flags of all peers show `epoch` for this rank -- so work
+ * queued behind it on the stream sees the complete [world*bytes] buffer.  The reference has no
+ * distributed code; this replaces what would be torch.distributed.all_gather_into_tensor.
+ *   peer_bufs / peer_flags : DEVICE arrays of `world` device pointers
+ *   scratch                : device uint32 (zero-initialised once), block-arrival counter
+ *   epoch                  : strictly increasing per call, starting at 1 */
+int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const* peer_flags, int world, int rank,
+                      uint64_t bytes, uint32_t epoch, uint32_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
