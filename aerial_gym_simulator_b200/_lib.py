@@ -71,7 +71,7 @@ class AgxHp2Scene(C.Structure):
         ("tris_per_object", C.c_int32), ("num_templates", C.c_int32), ("obj_pose_stride", C.c_int32),
         ("tmpl_tri_offset", fp), ("tmpl_tris", fp), ("tmpl_seg_base", fp), ("tmpl_seg_mask", fp),
         ("obj_pose", fp), ("obj_template", fp), ("obj_seg_counter", fp), ("bounds_min", fp), ("bounds_max", fp),
-        ("tris", fp), ("nodes", fp), ("leaf_object", fp), ("face_offset", fp),
+        ("tris", fp), ("nodes", fp), ("leaf_object", fp), ("face_offset", fp), ("tmpl_obb", fp), ("obb", fp),
     ]
 
 

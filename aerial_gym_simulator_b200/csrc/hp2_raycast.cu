@@ -84,6 +84,7 @@ __device__ __forceinline__ v3 kinv_mul(const float* k, v3 c) {
 constexpr float kAabbPad = 1e-4f;  // metres; culling only
 constexpr int kNodeFloats = 8;     // lo.xyz,0 | hi.xyz,0
 constexpr int kTriFloats = 12;     // v0.xyz,seg | e1.xyz,0 | e2.xyz,0
+constexpr int kObbFloats = 16;     // c.xyz | a0.xyz | a1.xyz | a2.xyz | half.xyz | valid
 
 // =========================================================================================
 // scene update: transform + BVH build, one CTA per env
@@ -143,6 +144,25 @@ hp2_update_scene_kernel(const __grid_constant__ AgxHp2Scene sc, const uint8_t* _
             sc.face_offset[(size_t)e * K + k] = acc;
             int tm = sc.obj_template[(size_t)e * K + k];
             acc += min(L, sc.tmpl_tri_offset[tm + 1] - sc.tmpl_tri_offset[tm]);
+        }
+    }
+    if (sc.obb) {  // world-frame oriented boxes of box-shaped objects (culling aid)
+        for (int k = tid; k < K; k += nt) {
+            const float* p = sc.obj_pose + ((size_t)e * K + k) * sc.obj_pose_stride;
+            v3 t{p[0], p[1], p[2]};
+            q4 q{p[3], p[4], p[5], p[6]};
+            const float* to = sc.tmpl_obb + (size_t)sc.obj_template[(size_t)e * K + k] * kObbFloats;
+            float* o = sc.obb + ((size_t)e * K + k) * kObbFloats;
+            v3 c = quat_apply(q, v3{to[0], to[1], to[2]});
+            v3 a0 = quat_apply(q, v3{to[3], to[4], to[5]});
+            v3 a1 = quat_apply(q, v3{to[6], to[7], to[8]});
+            v3 a2 = quat_apply(q, v3{to[9], to[10], to[11]});
+            o[0] = c.x + t.x; o[1] = c.y + t.y; o[2] = c.z + t.z;
+            o[3] = a0.x; o[4] = a0.y; o[5] = a0.z; o[6] = a1.x; o[7] = a1.y; o[8] = a1.z; o[9] = a2.x; o[10] = a2.y; o[11] = a2.z;
+            const float scale = fabsf(o[0]) + fabsf(o[1]) + fabsf(o[2]) + to[12] + to[13] + to[14];
+            const float pad = 2e-4f + 4e-6f * scale;  // conservative: never cull a true hit
+            o[12] = to[12] + pad; o[13] = to[13] + pad; o[14] = to[14] + pad;
+            o[15] = to[15];
         }
     }
     __syncthreads();  // slabs of this CTA are read back below (same CTA wrote them)
@@ -322,9 +342,32 @@ __device__ __forceinline__ float aabb_entry(const float* nd, v3 o, v3 inv, float
     return hit ? tmin : -1.0f;
 }
 
+// ray vs padded oriented box (object frame slabs); culling only
+__device__ __forceinline__ bool obb_may_hit(const float* __restrict__ b, v3 o, v3 d, float t_limit) {
+    v3 r{o.x - b[0], o.y - b[1], o.z - b[2]};
+    float tmin = 0.0f, tmax = t_limit + 1e-5f * (1.0f + t_limit);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ax = b[3 + 3 * a], ay = b[4 + 3 * a], az = b[5 + 3 * a];
+        const float oa = r.x * ax + r.y * ay + r.z * az;
+        const float da = d.x * ax + d.y * ay + d.z * az;
+        const float h = b[12 + a];
+        if (fabsf(da) < 1e-12f) {
+            if (fabsf(oa) > h) return false;
+        } else {
+            const float inv = 1.0f / da;
+            float t1 = (-h - oa) * inv, t2 = (h - oa) * inv;
+            tmin = fmaxf(tmin, fminf(t1, t2));
+            tmax = fminf(tmax, fmaxf(t1, t2));
+        }
+    }
+    return tmin <= tmax + 1e-5f * (1.0f + fabsf(tmax));
+}
+
 template <bool SMEM>
 __device__ __forceinline__ Hit traverse(const float* __restrict__ nodes, const int32_t* __restrict__ leaf_obj,
-                                        const float* __restrict__ tris, int P, int L, v3 o, v3 d, float max_t) {
+                                        const float* __restrict__ tris, const float* __restrict__ obb, int P, int L, v3 o, v3 d,
+                                        float max_t) {
     Hit best{max_t, 0x7fffffff};
     v3 inv{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     int stack[24];
@@ -339,8 +382,15 @@ __device__ __forceinline__ Hit traverse(const float* __restrict__ nodes, const i
         if (node >= P - 1) {  // leaf
             int obj = leaf_obj[node - (P - 1)];
             if (obj >= 0) {
-                const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)obj * L * kTriFloats);
-                for (int s = 0; s < L; ++s) tri_test(tp + 3 * s, obj * L + s, o, d, max_t, best);
+                bool test = true;
+                if (obb) {
+                    const float* b = obb + (size_t)obj * kObbFloats;
+                    if (b[15] != 0.0f) test = obb_may_hit(b, o, d, best.t);
+                }
+                if (test) {
+                    const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)obj * L * kTriFloats);
+                    for (int s = 0; s < L; ++s) tri_test(tp + 3 * s, obj * L + s, o, d, max_t, best);
+                }
             }
             if (sp == 0) break;
             node = stack[--sp];
@@ -480,6 +530,8 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
     float* s_nodes = reinterpret_cast<float*>(smem_raw);
     int32_t* s_leaf = reinterpret_cast<int32_t*>(smem_raw + ((node_bytes + 15u) & ~15u));
     float* s_tris = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_leaf) + ((leaf_bytes + 15u) & ~15u));
+    const uint32_t obb_bytes = sc.obb ? (uint32_t)((size_t)K * kObbFloats * 4) : 0u;
+    float* s_obb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_tris) + tri_bytes);
     if (SMEM && threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -497,19 +549,22 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         const float* g_nodes = sc.nodes + (size_t)e * (2 * P - 1) * kNodeFloats;
         const int32_t* g_leaf = sc.leaf_object + (size_t)e * leaf_stride;
         const float* g_tris = sc.tris + (size_t)e * K * L * kTriFloats;
+        const float* g_obb = sc.obb ? sc.obb + (size_t)e * K * kObbFloats : nullptr;
         const float* nodes = g_nodes;
         const int32_t* leaf = g_leaf;
         const float* tris = g_tris;
+        const float* obb = g_obb;
         if (SMEM) {
             if (e != staged_env) {
                 __syncthreads();  // everyone is done with the previous scene
                 if (threadIdx.x == 0) {
                     // order prior generic-proxy smem reads before the async-proxy writes
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_expect_tx(&s_bar, node_bytes + leaf_bytes + tri_bytes);
+                    mbar_expect_tx(&s_bar, node_bytes + leaf_bytes + tri_bytes + obb_bytes);
                     tma_bulk_g2s(s_nodes, g_nodes, node_bytes, &s_bar);
                     tma_bulk_g2s(s_leaf, g_leaf, leaf_bytes, &s_bar);
                     tma_bulk_g2s(s_tris, g_tris, tri_bytes, &s_bar);
+                    if (obb_bytes) tma_bulk_g2s(s_obb, g_obb, obb_bytes, &s_bar);
                 }
                 mbar_wait(&s_bar, parity);
                 parity ^= 1u;
@@ -518,6 +573,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
             nodes = s_nodes;
             leaf = s_leaf;
             tris = s_tris;
+            if (obb_bytes) obb = s_obb;
         }
         // ---- sensor pose: warp_sensor.py:180-187 ------------------------------------------------
         const float* rp = sn.robot_pose + (size_t)e * sn.robot_pose_stride;
@@ -542,9 +598,12 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         }
         const int y0 = rb * rows_per_item;
         const int y1 = min(H, y0 + rows_per_item);
-        const int n_pix = (y1 - y0) * W;
-        for (int i = threadIdx.x; i < n_pix; i += kCastThreads) {
-            const int y = y0 + i / W, x = i % W;
+        // warp <-> 8x4 pixel tile: neighbouring rays stay in one warp (coherent traversal, SIMT efficiency)
+        const int tiles_x = (W + 7) >> 3, tiles_y = (y1 - y0 + 3) >> 2;
+        const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
+        for (int tix = threadIdx.x >> 5; tix < tiles_x * tiles_y; tix += kCastThreads / 32) {
+            const int x = (tix % tiles_x) * 8 + lx, y = y0 + (tix / tiles_x) * 4 + ly;
+            if (x >= W || y >= y1) continue;
             v3 uv, rd;
             float mult = 1.0f, max_t = sn.far_plane;
             if (is_cam) {  // warp_camera_kernels.py:186-221
@@ -560,7 +619,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
                 uv = normalize3(v3{rt[0], rt[1], rt[2]});
                 rd = normalize3(quat_rotate(sq, uv));
             }
-            Hit h = traverse<SMEM>(nodes, leaf, tris, P, L, sp, rd, max_t);
+            Hit h = traverse<SMEM>(nodes, leaf, tris, obb, P, L, sp, rd, max_t);
             float dist = AGX_NO_HIT_RAY_VAL;
             int segv = AGX_NO_HIT_SEG_VAL;
             const bool hit = h.tri != 0x7fffffff;
@@ -591,7 +650,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
                 else ep = v3{sp.x + (rd.x * sn.far_plane) / mult, sp.y + (rd.y * sn.far_plane) / mult, sp.z + (rd.z * sn.far_plane) / mult};
                 v3 dv = sub3(stereo_pos, ep);
                 float dl = sqrtf(dot3(dv, dv));
-                Hit h2 = traverse<SMEM>(nodes, leaf, tris, P, L, ep, normalize3(dv), dl);
+                Hit h2 = traverse<SMEM>(nodes, leaf, tris, obb, P, L, ep, normalize3(dv), dl);
                 const bool visible = h2.tri == 0x7fffffff;
                 if (hit && visible) {
                     dist = h.t * mult;
@@ -632,10 +691,10 @@ inline int next_pow2(int v) {
     while (p < v) p <<= 1;
     return p;
 }
-inline size_t scene_smem_bytes(int K, int P, int L) {
+inline size_t scene_smem_bytes(int K, int P, int L, bool with_obb) {
     size_t nb = ((size_t)(2 * P - 1) * kNodeFloats * 4 + 15) & ~(size_t)15;
     size_t lb = (size_t)(P < 4 ? 4 : P) * 4;
-    return nb + lb + (size_t)K * L * kTriFloats * 4;
+    return nb + lb + (size_t)K * L * kTriFloats * 4 + (with_obb ? (size_t)K * kObbFloats * 4 : 0);
 }
 
 int validate_scene(const AgxHp2Scene* sc) {
@@ -645,6 +704,8 @@ int validate_scene(const AgxHp2Scene* sc) {
     if (sc->leaves_pow2 != next_pow2(sc->num_objects)) return agx_set_error(AGX_E_INVALID, "leaves_pow2 must be the next power of two >= num_objects");
     if (sc->tris_per_object < 1 || sc->tris_per_object > 64) return agx_set_error(AGX_E_INVALID, "tris_per_object must be in [1, 64]");
     if (!sc->tris || !sc->nodes || !sc->leaf_object) return agx_set_error(AGX_E_NULL, "scene storage (tris/nodes/leaf_object) is NULL");
+    if ((sc->tmpl_obb == nullptr) != (sc->obb == nullptr)) return agx_set_error(AGX_E_INVALID, "tmpl_obb and obb must be given together");
+    if ((uintptr_t)sc->obb & 15) return agx_set_error(AGX_E_INVALID, "obb storage must be 16-byte aligned");
     if (((uintptr_t)sc->tris | (uintptr_t)sc->nodes | (uintptr_t)sc->leaf_object) & 15) return agx_set_error(AGX_E_INVALID, "scene storage must be 16-byte aligned");
     return AGX_OK;
 }
@@ -660,6 +721,7 @@ uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which) {
         case 1: return (uint64_t)(2 * P - 1) * kNodeFloats * 4;
         case 2: return (uint64_t)(P < 4 ? 4 : P) * 4;
         case 3: return (uint64_t)((num_objects + 3) / 4 * 4) * 4;
+        case 4: return (uint64_t)num_objects * kObbFloats * 4;
         default: return 0;
     }
 }
@@ -710,13 +772,14 @@ int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int W = sn->width, H = sn->height;
-    // a work item = up to ~2048 rays of one (env, sensor) image
-    int rows_per_item = 2048 / W;
+    // a work item = up to ~4096 rays of one (env, sensor) image (a 64x48 image is ONE item, so the
+    // env's scene is staged once per image)
+    int rows_per_item = 4096 / W;
     if (rows_per_item < 1) rows_per_item = 1;
     if (rows_per_item > H) rows_per_item = H;
     int items_per_image = (H + rows_per_item - 1) / rows_per_item;
     long long n_items = (long long)sc->num_envs * sn->num_sensors * items_per_image;
-    size_t smem = scene_smem_bytes(sc->num_objects, sc->leaves_pow2, sc->tris_per_object);
+    size_t smem = scene_smem_bytes(sc->num_objects, sc->leaves_pow2, sc->tris_per_object, sc->obb != nullptr);
     bool use_smem = smem + 1024 <= (size_t)max_smem;
     cudaStream_t st = (cudaStream_t)stream;
     if (use_smem) {

@@ -170,17 +170,18 @@ class EnvManager:
         lo = np.zeros((N, A, 13), np.float32)
         hi = np.zeros((N, A, 13), np.float32)
         # templates: every <box> visual of every distinct URDF; an asset with b boxes = b objects
-        tmpl_index, templates, boxes_of = {}, [], {}
+        tmpl_index, templates, tmpl_obbs, boxes_of = {}, [], [], {}
         for e in range(N):
             for a, (params, path) in enumerate(per_env[e]):
                 lo[e, a], hi[e, a] = params.min_state_ratio, params.max_state_ratio
                 if path not in boxes_of:
                     model = urdf.parse_urdf(path)
                     ids = []
-                    for _, tris in urdf.box_visual_triangles(model, params.use_collision_mesh_instead_of_visual):
+                    for _, tris, obb in urdf.box_visual_triangles(model, params.use_collision_mesh_instead_of_visual):
                         tmpl_index[(path, len(ids))] = len(templates)
                         ids.append(len(templates))
                         templates.append(tris)
+                        tmpl_obbs.append(obb)
                     boxes_of[path] = ids
         gtd["asset_min_state_ratio"].copy_(torch.from_numpy(lo))
         gtd["asset_max_state_ratio"].copy_(torch.from_numpy(hi))
@@ -213,7 +214,8 @@ class EnvManager:
         self._obj_asset = torch.from_numpy(obj_asset).to(dev)
         self._obj_pose = torch.zeros(N, K, 7, device=dev)
         self.scene = RayScene(templates, seg_base, seg_mask, obj_t, obj_c, self._obj_pose, dev,
-                              bounds_min=self.engine.bounds_min, bounds_max=self.engine.bounds_max)
+                              bounds_min=self.engine.bounds_min, bounds_max=self.engine.bounds_max,
+                              tmpl_obb=np.stack(tmpl_obbs))
 
     def _build_sensors(self):
         gtd, N, dev = self.global_tensor_dict, self.num_envs, self.device

@@ -30,6 +30,13 @@ def box_triangles(size: Sequence[float]) -> np.ndarray:
     return v[f].reshape(12, 9).astype(np.float32)
 
 
+def box_obb(size: Sequence[float], R=None, p=None) -> np.ndarray:
+    """[16] oriented-box record of a box template: centre, 3 axes (columns of R), half extents, valid=1."""
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64)
+    p = np.zeros(3) if p is None else np.asarray(p, dtype=np.float64)
+    return np.concatenate([p, R[:, 0], R[:, 1], R[:, 2], np.asarray(size, dtype=np.float64) / 2.0, [1.0]]).astype(np.float32)
+
+
 def _next_pow2(v: int) -> int:
     p = 1
     while p < v:
@@ -44,7 +51,9 @@ class RayScene:
     as the last dim is contiguous and rows are uniformly strided)."""
 
     def __init__(self, templates, tmpl_seg_base, tmpl_seg_mask, obj_template, obj_seg_counter, obj_pose: torch.Tensor,
-                 device="cuda:0", tris_per_object: Optional[int] = None, bounds_min=None, bounds_max=None):
+                 device="cuda:0", tris_per_object: Optional[int] = None, bounds_min=None, bounds_max=None, tmpl_obb=None):
+        """tmpl_obb: optional [T,16] oriented-box records (box_obb) of the templates that ARE boxes (valid=1);
+        purely a culling aid -- results are identical with or without it."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -79,12 +88,19 @@ class RayScene:
         self.nodes = torch.zeros(E * nb(1) // 4, dtype=torch.float32, device=dev)
         self.leaf_object = torch.full((E * nb(2) // 4,), -1, dtype=torch.int32, device=dev)
         self.face_offset = torch.zeros(E * K, dtype=torch.int32, device=dev)
+        self.tmpl_obb = self.obb = None
+        if tmpl_obb is not None:
+            tmpl_obb = np.asarray(tmpl_obb, dtype=np.float32).reshape(len(templates), 16)
+            self.tmpl_obb = T(tmpl_obb, torch.float32)
+            self.obb = torch.zeros(E * K * 16, dtype=torch.float32, device=dev)
         s = AgxHp2Scene()
         s.num_envs, s.num_objects, s.leaves_pow2, s.tris_per_object = E, K, self.P, L
         s.num_templates, s.obj_pose_stride = len(templates), obj_pose.stride(1)
         for name in ("tmpl_tri_offset", "tmpl_tris", "tmpl_seg_base", "tmpl_seg_mask", "obj_pose", "obj_template",
                      "obj_seg_counter", "tris", "nodes", "leaf_object", "face_offset"):
             setattr(s, name, getattr(self, name).data_ptr())
+        s.tmpl_obb = self.tmpl_obb.data_ptr() if self.tmpl_obb is not None else None
+        s.obb = self.obb.data_ptr() if self.obb is not None else None
         s.bounds_min = bounds_min.data_ptr() if bounds_min is not None else None
         s.bounds_max = bounds_max.data_ptr() if bounds_max is not None else None
         self.c = s

@@ -187,8 +187,8 @@ def parse_urdf(path: str) -> UrdfModel:
 
 def box_visual_triangles(model: UrdfModel, use_collision=False):
     """Per-link list of [12,9] root-frame triangle arrays for every <box> visual (the obstacle
-    assets the reference ships are all boxes).  Returns [(link_name, triangles)]."""
-    from .hp2 import box_triangles
+    assets the reference ships are all boxes).  Returns [(link_name, triangles, obb16)]."""
+    from .hp2 import box_obb, box_triangles
 
     tf = model.link_transforms()
     out = []
@@ -200,5 +200,5 @@ def box_visual_triangles(model: UrdfModel, use_collision=False):
                 continue
             t = box_triangles(v.size).reshape(-1, 3).astype(np.float64)
             t = (R @ (v.R @ t.T + v.p[:, None]) + p[:, None]).T
-            out.append((name, t.reshape(-1, 9).astype(np.float32)))
+            out.append((name, t.reshape(-1, 9).astype(np.float32), box_obb(v.size, R @ v.R, R @ v.p + p)))
     return out

@@ -370,7 +370,7 @@ def run_hp2_depth(dev, world, rank, args):
     import torch
     import torch.distributed as dist
 
-    from aerial_gym_simulator_b200.hp2 import RayScene, RaySensor, box_triangles
+    from aerial_gym_simulator_b200.hp2 import RayScene, RaySensor, box_obb, box_triangles
 
     E, K, H, W = args.hp2_envs, 44, 48, 64
     g = torch.Generator().manual_seed(7 + rank)
@@ -382,7 +382,8 @@ def run_hp2_depth(dev, world, rank, args):
     pose[..., 3:7] = q / q.norm(dim=-1, keepdim=True)
     tm = torch.randint(0, 5, (E, K), generator=g).numpy()
     ctr = (100 + torch.arange(E * K).reshape(E, K)).numpy()
-    scene = RayScene(templates, [0] * 5, [1] * 5, tm, ctr, pose.to(dev), dev)
+    scene = RayScene(templates, [0] * 5, [1] * 5, tm, ctr, pose.to(dev), dev,
+                     tmpl_obb=np.stack([box_obb(s.tolist()) for s in sizes]))
 
     class cam:
         sensor_type, num_sensors, height, width = "camera", 1, H, W

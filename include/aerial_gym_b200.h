@@ -219,6 +219,10 @@ typedef struct AgxHp2Scene {
     int32_t* leaf_object;       /* [E][max(P,4)] object index of each Morton-sorted leaf, -1 = empty */
     int32_t* face_offset;       /* [E][K] index of each object's first triangle in the env's concatenated mesh
                                    (the face id of the normal+faceID sensors); may be NULL if those are unused */
+    /* optional culling aid: templates that are boxes carry their object-frame oriented box; leaves whose
+     * (padded) world OBB the ray misses skip their 12 triangle tests.  Culling only -- results unchanged. */
+    const float* tmpl_obb;      /* [T][16] centre.xyz, axis0.xyz, axis1.xyz, axis2.xyz, half.xyz, valid(0/1); or NULL */
+    float* obb;                 /* [E][K][16] world-frame boxes written by agx_hp2_update_scene; NULL iff tmpl_obb is NULL */
 } AgxHp2Scene;
 
 #define AGX_SENSOR_CAMERA 0              /* warp_camera_kernels.py:125-282 */
@@ -254,7 +258,7 @@ typedef struct AgxHp2Sensor {
 } AgxHp2Sensor;
 
 /* bytes the caller must allocate for scene->tris / nodes / leaf_object (per env) */
-uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which /*0 tris, 1 nodes, 2 leaf_object, 3 face_offset*/);
+uint64_t agx_hp2_scene_bytes(int num_objects, int tris_per_object, int which /*0 tris, 1 nodes, 2 leaf_object, 3 face_offset, 4 obb*/);
 
 /* Re-transform triangles + rebuild the BVH of the envs selected by `mask` ([E] bool, NULL = all).
  * Replaces WarpEnv.reset_idx (warp_env_manager.py:40-54). */

@@ -24,7 +24,9 @@ def make_scene(E, K, seed, extent=5.0, parked=0, n_templates=5):
     tm = torch.randint(0, n_templates, (E, K), generator=g).numpy().astype(np.int32)
     ctr = (100 + torch.arange(E * K).reshape(E, K)).numpy().astype(np.int32)
     offs = np.arange(0, 12 * (n_templates + 1), 12, dtype=np.int32)
-    return dict(templates=templates, tm=tm, ctr=ctr, pose=pose, offs=offs, tmpl_tris=np.concatenate(templates),
+    from aerial_gym_simulator_b200.hp2 import box_obb
+    obbs = np.stack([box_obb(s.tolist()) for s in sizes])
+    return dict(templates=templates, obbs=obbs, tm=tm, ctr=ctr, pose=pose, offs=offs, tmpl_tris=np.concatenate(templates),
                 seg_base=np.zeros(12 * n_templates, np.int32), seg_mask=np.ones(12 * n_templates, np.int32), E=E, K=K)
 
 

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def build(sc, cfg, seed=1, S=1, mount_seed=None):
+def build(sc, cfg, seed=1, S=1, mount_seed=None, use_obb=True):
     pose_d = sc["pose"].to(DEV)
-    scene = RayScene(sc["templates"], [0] * len(sc["templates"]), [1] * len(sc["templates"]), sc["tm"], sc["ctr"], pose_d, DEV)
+    scene = RayScene(sc["templates"], [0] * len(sc["templates"]), [1] * len(sc["templates"]), sc["tm"], sc["ctr"], pose_d, DEV,
+                     tmpl_obb=sc["obbs"] if use_obb else None)
     scene.update()
     E = sc["E"]
     robot = H.robot_poses(E, seed)
@@ -257,3 +258,15 @@ def test_normal_faceid_sensors_match_oracle(kind, world):
     if world or "lidar" in kind:  # the camera-frame basis (rd_p, rd_p x ez, rd_p x ey) is not orthonormal
         nrm = np.linalg.norm(ref_pix[hit], axis=-1)
         assert np.allclose(nrm, 1.0, atol=1e-5)
+
+
+def test_obb_culling_changes_nothing():
+    """The oriented-box pre-test is a culling aid only: identical pixels with and without it."""
+    cfg = H.cfg_variant(H.CamCfg, height=40, width=56)
+    sc = H.make_scene(6, 44, seed=150, extent=3.0)
+    _, s1, robot, mount, _ = build(sc, cfg, seed=16, use_obb=True)
+    _, s0, _, _, _ = build(sc, cfg, seed=16, use_obb=False)
+    s1.capture()
+    s0.capture()
+    torch.cuda.synchronize()
+    assert torch.equal(s1.pixels, s0.pixels) and torch.equal(s1.seg_pixels, s0.seg_pixels)
