@@ -278,7 +278,20 @@ def run_ours(args):
         dist.all_reduce(hot_ms, op=dist.ReduceOp.MAX)
     value_hot = world * N * K / (float(hot_ms.item()) * 1e-3)
 
-    # ---- e2e: host buffers in, host buffers out, copies inside the timed region --------------
+    # ---- e2e: the call a user makes -- task_registry.make_task(...).step(actions) -- with HOST
+    # buffers: pinned actions in, obs / reward / terminations / truncations out, every step ---------
+    import aerial_gym_simulator_b200.task  # noqa: F401  (registers tasks)
+    from aerial_gym_simulator_b200.registry.task_registry import task_registry
+
+    tcfg = task_registry.get_task_config("position_setpoint_task")
+    old_args, old_dev = tcfg.args, tcfg.device
+    tcfg.args, tcfg.device = {"env_id_offset": rank * N}, str(dev)
+    try:
+        task = task_registry.make_task("position_setpoint_task", seed=7, num_envs=N, headless=True)
+    finally:
+        tcfg.args, tcfg.device = old_args, old_dev
+    task.reset()
+    task.sim_env.engine.sim_steps.copy_((torch.arange(N, device=dev) % 500).int())
     h_act = [a.cpu().pin_memory() for a in acts]
     d_act = torch.empty(N, 4, device=dev)
     h_obs = torch.empty(N, 13).pin_memory()
@@ -288,13 +301,14 @@ def run_ours(args):
 
     def e2e_step(i):
         d_act.copy_(h_act[i % 8], non_blocking=True)
-        eng.position_task_step(d_act)
+        obs_d, rew_d, term_d, trunc_d, _ = task.step(d_act)
+        o = obs_d["observations"]
         if world > 1:
-            gather(eng.obs)
-        h_obs.copy_(eng.obs, non_blocking=True)
-        h_rew.copy_(eng.reward, non_blocking=True)
-        h_term.copy_(eng.terminations, non_blocking=True)
-        h_trunc.copy_(eng.truncations, non_blocking=True)
+            o = gather(o)[rank * N:(rank + 1) * N]
+        h_obs.copy_(o, non_blocking=True)
+        h_rew.copy_(rew_d, non_blocking=True)
+        h_term.copy_(term_d, non_blocking=True)
+        h_trunc.copy_(trunc_d, non_blocking=True)
         stream.synchronize()  # the user reads the result of every step
 
     for i in range(3):
@@ -351,7 +365,8 @@ def run_ours(args):
                          "note": "at 65,536 envs the launch is ~14 MB: FP32-issue / latency bound, not HBM bound (DESIGN.md)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "Hp1Engine.position_task_step (C ABI) with pinned host actions in, obs/reward/flags out"},
+                    "api": "task_registry.make_task('position_setpoint_task').step(actions): pinned host actions in, "
+                           "obs/reward/terminations/truncations to pinned host every step"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
             "hp2_depth": hp2,
