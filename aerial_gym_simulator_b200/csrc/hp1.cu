@@ -10,6 +10,7 @@
 // two float4 per thread.  No tensor-core path: per-env work is <= 8x6 contractions.
 //
 // Reference functions restated here are cited inline (paths relative to aerial_gym/).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -461,7 +462,11 @@ __device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3
 // main kernel
 // =========================================================================================
 // 8 CTAs/SM -> <= 128 registers: all 1024 CTAs of the 65,536-env launch are resident in one wave
-template <int M, bool TASK>
+// COOP (cooperative launch, one tile per warp, all CTAs co-resident): the stale-observation quirk is
+// resolved inside the kernel -- grid-wide sync, then every non-reset env patches its own obs[7:13]
+// from registers if ANY env reset -- instead of a second launch.  any_reset[4],[5] are the flags of
+// even / odd steps, any_reset[6] the step parity counter (device-side, so launches stay graph-safe).
+template <int M, bool TASK, bool COOP = false>
 __global__ void __launch_bounds__(kThreads, 8)
 hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
     __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
@@ -470,6 +475,14 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     const int N = cfg.num_envs;
     const int n_tiles = (N + 31) >> 5;
     const int A = cfg.num_actions;
+    int coop_ep = 0;
+    int* reset_flag = buf.any_reset;
+    if constexpr (COOP) {
+        coop_ep = *reinterpret_cast<volatile int*>(buf.any_reset + 6);
+        reset_flag = buf.any_reset + 4 + (coop_ep & 1);
+    }
+    EnvState s_keep{};
+    int env_keep = -1;
 
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < n_tiles; t += gridDim.x * kWarpsPerBlock) {
         const int env0 = t << 5;
@@ -587,6 +600,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 buf.truncations[env] = trunc ? 1 : 0;
                 if (buf.reset_mask) buf.reset_mask[env] = do_reset ? 1 : 0;
                 bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
+                (void)s_keep;
                 if (do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET)) {
                     uint32_t ep = buf.episode_count[env];
                     // temporaries: only they have their address taken by the out-of-line reset, so the
@@ -604,7 +618,9 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 buf.sim_steps[env] = steps;
                 if (fresh) d = update_states(s);
                 make_obs(s, d, tgt, o);
-                if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
+                if constexpr (COOP) {
+                    if (!fresh) { s_keep = s; env_keep = env; }  // this env's obs holds stale velocities
+                } else if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
                     V3 vb = fresh ? d.vb : quat_rotate_inverse(s.q, s.v);
                     V3 wb = fresh ? d.wb : quat_rotate_inverse(s.q, s.w);
                     const size_t Ns = (size_t)N;
@@ -613,7 +629,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 }
             }
             unsigned any = __ballot_sync(0xffffffffu, do_reset);
-            if (any && lane == 0) atomicOr(buf.any_reset, 1);
+            if (any && lane == 0) atomicOr(reset_flag, 1);
         }
         if (valid) {
             store_m<M>(buf.motor_thrust, env, p.thrust);
@@ -626,6 +642,18 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         }
         store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
         if constexpr (TASK) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+    }
+    if constexpr (COOP) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[4 + ((coop_ep + 1) & 1)] = 0;  // next step's flag
+        cooperative_groups::this_grid().sync();
+        const int any = *reinterpret_cast<volatile int*>(reset_flag);
+        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[6] = coop_ep + 1;
+        if (any && env_keep >= 0) {  // base_multirotor.py:204-205: a reset anywhere refreshes everybody
+            V3 vb = quat_rotate_inverse(s_keep.q, s_keep.v);
+            V3 wb = quat_rotate_inverse(s_keep.q, s_keep.w);
+            float* o = buf.obs + (size_t)env_keep * 13 + 7;
+            o[0] = vb.x; o[1] = vb.y; o[2] = vb.z; o[3] = wb.x; o[4] = wb.y; o[5] = wb.z;
+        }
     }
 }
 
@@ -770,6 +798,21 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
 inline int vec_ok_of(const AgxHp1Buffers* buf) {
     return (((uintptr_t)buf->root_state | (uintptr_t)buf->obs) & 15) == 0;
 }
+// how many CTAs of the cooperative task kernel can be co-resident on this device (cached)
+inline int coop_capacity(int num_motors) {
+    static int cap4 = -1, cap8 = -1;
+    int& cap = (num_motors == 4) ? cap4 : cap8;
+    if (cap < 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_motors == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp1_step_kernel<4, true, true>, kThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp1_step_kernel<8, true, true>, kThreads, 0);
+        cap = coop ? sms * per_sm : 0;
+    }
+    return cap;
+}
 inline int grid_for(int n_envs) {
     int tiles = (n_envs + 31) / 32;
     int blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -802,6 +845,15 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     if (cfg->num_envs == 0) return AGX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
+    const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
+    const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
+    if (strict_fused && !derived && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
+        // single cooperative launch: the obs patch happens after a grid-wide sync inside the kernel
+        int vv = v;
+        void* args[] = {(void*)cfg, (void*)buf, (void*)&vv};
+        const void* fn = cfg->num_motors == 4 ? (const void*)hp1_step_kernel<4, true, true> : (const void*)hp1_step_kernel<8, true, true>;
+        return agx_check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kThreads), args, 0, st), "cudaLaunchCooperativeKernel(hp1_step)");
+    }
     if (cfg->num_motors == 4) hp1_step_kernel<4, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     rc = agx_check_launch("hp1_step_kernel<task>");
@@ -812,8 +864,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     }
     // stale-derived-state quirk: if ANY env reset this step the reference refreshes
     // the derived states of ALL envs before the observation is read (base_multirotor.py:204-205).
-    if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS)) {
-        const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
+    if (strict_fused) {
         if (buf->fresh_vel && !derived) {
             hp1_obs_patch_kernel<<<(cfg->num_envs + 255) / 256, 256, 0, st>>>(cfg->num_envs, buf->fresh_vel, buf->obs, buf->any_reset);
             rc = agx_check_launch("hp1_obs_patch_kernel");

@@ -212,7 +212,7 @@ class Hp1Engine:
         self.terminations = z(N, dt=torch.bool)
         self.truncations = z(N, dt=torch.bool)
         self.reset_mask = z(N, dt=torch.bool)
-        self.any_reset = z(2, dt=torch.int32)
+        self.any_reset = z(8, dt=torch.int32)
         self.episode_count = z(N, dt=torch.int32)
         self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
         self.bounds_max = torch.tensor(spec.bounds_upper_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()

@@ -157,11 +157,13 @@ def _philox_draws(seed, gids, episodes, M):
 
 
 @pytest.mark.parametrize("case", ["quad_attitude", "octa_velocity"])
-@pytest.mark.parametrize("strict", [True, False])
-def test_fused_position_task_step(case, strict):
+@pytest.mark.parametrize("strict,materialize", [(True, True), (True, False), (False, True)],
+                         ids=["strict-two_launch", "strict-cooperative", "fresh"])
+def test_fused_position_task_step(case, strict, materialize):
     """Whole PositionSetpointTask.step in one C-ABI call, device-RNG resets, teacher-forced for
     30 steps: reward/obs to 1e-5, termination / truncation / reset masks and sim_steps bit-exact,
-    the stale-derived-state quirk reproduced (strict) or disabled."""
+    the stale-derived-state quirk reproduced (strict; via the refresh pass when derived states are
+    materialised, via the single cooperative launch otherwise) or disabled."""
     spec = H.spec_for(case)
     model = H.oracle_model_from_spec(spec)
     N, M, seed, off = 777, spec.num_motors, 99, 1000
@@ -171,7 +173,7 @@ def test_fused_position_task_step(case, strict):
     st.sim_steps = torch.randint(480, 501, (N,), generator=g, dtype=torch.int32)  # truncations within 30 steps
     st.root[:5, 0:3] = 7.9  # |x| > 8 soon -> crashes
     eng = Hp1Engine(spec, N, DEV, per_env_params="all", seed=seed, env_id_offset=off, device_rng_reset=True,
-                    strict_stale_obs=strict)
+                    strict_stale_obs=strict, materialize_derived=materialize)
     episodes = np.zeros(N, dtype=np.int64)
     target = torch.zeros(N, 3)
     n_resets = n_ill = 0
