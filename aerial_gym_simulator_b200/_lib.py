@@ -130,6 +130,8 @@ def load():
         "agx_hp2_update_scene": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_void_p],
         "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
         "agx_p2p_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
+        "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
+        "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     }.items():
         fn = getattr(lib, name)

@@ -24,6 +24,16 @@ int agx_check_launch(const char* what) { return agx_check_cuda(cudaPeekAtLastErr
 extern "C" {
 int agx_abi_version(void) { return AGX_ABI_VERSION; }
 const char* agx_last_error(void) { return g_err; }
+int agx_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return agx_set_error(AGX_E_NULL, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return AGX_OK;
+    return agx_check_cuda(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped), "cudaHostAlloc");
+}
+int agx_host_free(void* p) {
+    if (!p) return AGX_OK;
+    return agx_check_cuda(cudaFreeHost(p), "cudaFreeHost");
+}
 uint64_t agx_sizeof(int which) {
     switch (which) {
         case 0: return sizeof(AgxHp1Config);

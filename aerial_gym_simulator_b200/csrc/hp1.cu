@@ -462,10 +462,17 @@ __device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3
 // main kernel
 // =========================================================================================
 // 8 CTAs/SM -> <= 128 registers: all 1024 CTAs of the 65,536-env launch are resident in one wave
-// COOP (cooperative launch, one tile per warp, all CTAs co-resident): the stale-observation quirk is
-// resolved inside the kernel -- grid-wide sync, then every non-reset env patches its own obs[7:13]
-// from registers if ANY env reset -- instead of a second launch.  any_reset[4],[5] are the flags of
-// even / odd steps, any_reset[6] the step parity counter (device-side, so launches stay graph-safe).
+// COOP (cooperative launch: all CTAs co-resident, one tile per warp): the stale-observation quirk
+// ("a reset anywhere refreshes everybody", base_multirotor.py:204-205) is resolved inside the kernel
+// with a one-sided grid barrier instead of a second launch:
+//   * a warp that knows at its START that one of its envs truncates this step (sim_steps + 1 > episode
+//     length) raises the step's flag right away; crashes raise it in the epilogue;
+//   * every CTA counts itself in after its epilogue; an env that did not reset then needs the final
+//     value of the flag, which is known as soon as the flag is up (it is monotonic) OR all CTAs have
+//     arrived.  With staggered episodes some env truncates every step, so nobody ever waits.
+//   * the observation (and the derived arrays) are written once, after the decision.
+// any_reset[2],[3]: arrival counters of even / odd steps; [4],[5]: flags; [6]: step counter
+// (device-side, so launches stay graph-safe); the last CTA to arrive clears the other parity's slots.
 template <int M, bool TASK, bool COOP = false>
 __global__ void __launch_bounds__(kThreads, 8)
 hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
@@ -481,8 +488,13 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         coop_ep = *reinterpret_cast<volatile int*>(buf.any_reset + 6);
         reset_flag = buf.any_reset + 4 + (coop_ep & 1);
     }
-    EnvState s_keep{};
-    int env_keep = -1;
+    // state that outlives the tile loop in the COOP variant (one tile per warp there)
+    EnvState s;
+    Derived d;
+    V3 tgt{0.f, 0.f, 0.f};
+    float o[13];
+    bool need_patch = false;
+    int env0_keep = -1, n_valid_keep = 0;
 
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < n_tiles; t += gridDim.x * kWarpsPerBlock) {
         const int env0 = t << 5;
@@ -492,13 +504,11 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
 
         // every global load of the step is issued here, before the first use, so their DRAM
         // latencies overlap (the kernel is latency bound at 65,536 envs)
-        EnvState s;
         EnvParams<M> p;
-        Derived d;
         float act[AGX_MAX_MOTORS];
         float Fx = 0, Fy = 0, Fz = 0, Tx = 0, Ty = 0, Tz = 0;
         int steps_in = 0;
-        V3 tgt{0.f, 0.f, 0.f};
+        tgt = V3{0.f, 0.f, 0.f};
         if (valid) {
             load_params<M>(cfg, buf, env, p);
             if constexpr (TASK) {
@@ -520,6 +530,10 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         }
         float r[13];
         load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+        if constexpr (COOP) {  // truncations are known before the physics: publish them now
+            const bool trunc_early = valid && (steps_in + 1 > cfg.episode_len_steps);
+            if (__ballot_sync(0xffffffffu, trunc_early) && lane == 0) atomicOr(reset_flag, 1);
+        }
         if (valid) {
             s = unpack(r);
 
@@ -575,7 +589,6 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             if (cfg.physics_steps == 0) d = update_states(s);
         }
 
-        float o[13];
         bool do_reset = false;
         if constexpr (TASK) {
             if (valid) {
@@ -600,7 +613,6 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 buf.truncations[env] = trunc ? 1 : 0;
                 if (buf.reset_mask) buf.reset_mask[env] = do_reset ? 1 : 0;
                 bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
-                (void)s_keep;
                 if (do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET)) {
                     uint32_t ep = buf.episode_count[env];
                     // temporaries: only they have their address taken by the out-of-line reset, so the
@@ -619,7 +631,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 if (fresh) d = update_states(s);
                 make_obs(s, d, tgt, o);
                 if constexpr (COOP) {
-                    if (!fresh) { s_keep = s; env_keep = env; }  // this env's obs holds stale velocities
+                    need_patch = !fresh;  // this env's obs / derived arrays hold stale values
                 } else if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
                     V3 vb = fresh ? d.vb : quat_rotate_inverse(s.q, s.v);
                     V3 wb = fresh ? d.wb : quat_rotate_inverse(s.q, s.w);
@@ -633,7 +645,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         }
         if (valid) {
             store_m<M>(buf.motor_thrust, env, p.thrust);
-            store_derived(buf, env, d);
+            if (!(COOP && need_patch)) store_derived(buf, env, d);
             if (buf.body_wrench) {
                 float* bw = buf.body_wrench + (size_t)env * 6;
                 bw[0] = Fx; bw[1] = Fy; bw[2] = Fz; bw[3] = Tx; bw[4] = Ty; bw[5] = Tz;
@@ -641,18 +653,58 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             pack(s, r);
         }
         store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
-        if constexpr (TASK) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+        if constexpr (COOP) {
+            env0_keep = env0;
+            n_valid_keep = n_valid;
+        } else if constexpr (TASK) {
+            store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+        }
     }
     if constexpr (COOP) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[4 + ((coop_ep + 1) & 1)] = 0;  // next step's flag
-        cooperative_groups::this_grid().sync();
-        const int any = *reinterpret_cast<volatile int*>(reset_flag);
-        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[6] = coop_ep + 1;
-        if (any && env_keep >= 0) {  // base_multirotor.py:204-205: a reset anywhere refreshes everybody
-            V3 vb = quat_rotate_inverse(s_keep.q, s_keep.v);
-            V3 wb = quat_rotate_inverse(s_keep.q, s_keep.w);
-            float* o = buf.obs + (size_t)env_keep * 13 + 7;
-            o[0] = vb.x; o[1] = vb.y; o[2] = vb.z; o[3] = wb.x; o[4] = wb.y; o[5] = wb.z;
+        const int par = coop_ep & 1;
+        volatile int* arrived = buf.any_reset + 2 + par;
+        __syncthreads();  // this CTA's flag atomics are issued
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int prev = atomicAdd(buf.any_reset + 2 + par, 1);
+            if (prev == (int)gridDim.x - 1) {  // everybody has read the step counter: open the next step
+                buf.any_reset[2 + (par ^ 1)] = 0;
+                buf.any_reset[4 + (par ^ 1)] = 0;
+                __threadfence();
+                buf.any_reset[6] = coop_ep + 1;
+            }
+        }
+        if (env0_keep >= 0) {
+            int any = 1;
+            if (__any_sync(0xffffffffu, need_patch)) {
+                volatile int* fl = reset_flag;
+                any = *fl;
+                while (!any) {
+                    if (*arrived >= (int)gridDim.x) {
+                        __threadfence();
+                        any = *fl;  // final
+                        break;
+                    }
+                    __nanosleep(40);
+                    any = *fl;
+                }
+            }
+            const int env = env0_keep + lane;
+            if (need_patch) {
+                const bool derived = buf.euler || buf.vehicle_orientation || buf.vehicle_linvel || buf.body_linvel || buf.body_angvel;
+                if (any) {  // refresh this env
+                    if (derived) {
+                        d = update_states(s);
+                    } else {  // only the observation needs the body-frame velocities
+                        d.vb = quat_rotate_inverse(s.q, s.v);
+                        d.wb = quat_rotate_inverse(s.q, s.w);
+                    }
+                    o[7] = d.vb.x; o[8] = d.vb.y; o[9] = d.vb.z;
+                    o[10] = d.wb.x; o[11] = d.wb.y; o[12] = d.wb.z;
+                }
+                if (derived) store_derived(buf, env, d);
+            }
+            store_rows13(buf.obs, env0_keep, n_valid_keep, tile, lane, o, vec_ok);
         }
     }
 }
@@ -847,7 +899,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
     const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
     const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
-    if (strict_fused && !derived && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
+    if (strict_fused && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
         // single cooperative launch: the obs patch happens after a grid-wide sync inside the kernel
         int vv = v;
         void* args[] = {(void*)cfg, (void*)buf, (void*)&vv};

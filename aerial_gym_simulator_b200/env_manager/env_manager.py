@@ -80,7 +80,7 @@ class EnvManager:
             spec, N, dev, physics_steps=1, seed=int(self.env_args.get("seed", 0)),
             env_id_offset=int(self.env_args.get("env_id_offset", 0)), device_rng_reset=(self.reset_rng == "device"),
             strict_stale_obs=bool(self.env_args.get("strict_stale_obs", True)), materialize_derived=True,
-            per_env_params=self.env_args.get("per_env_params", "auto"))
+            per_env_params=self.env_args.get("per_env_params", "auto"), host_io=bool(self.env_args.get("host_io", False)))
         eng, gtd = self.engine, self.global_tensor_dict
         gtd["crashes"], gtd["truncations"] = eng.terminations, eng.truncations
         self.collision_tensor, self.truncation_tensor = eng.terminations, eng.truncations
@@ -114,6 +114,9 @@ class EnvManager:
         eng.bounds_max.copy_(_lerp(self._bounds_rng[2], self._bounds_rng[3], torch.rand(N, 3, device=dev)))
         self._build_obstacles()
         self._build_sensors()
+        if eng.host_io and (self.scene is not None or self.reset_rng != "device"):
+            raise NotImplementedError("args['host_io'] needs an obstacle-free env and reset_rng='device': the flags "
+                                      "live in host memory and are written only by the fused task step")
 
     # ---- obstacles: AssetLoader.select_assets_for_sim + WarpEnv (asset_loader.py:148-194, warp_env_manager.py)
     def _select_assets(self):
@@ -415,6 +418,8 @@ class EnvManager:
         return self.global_tensor_dict
 
     def delete_env(self):
+        if self.engine is not None:
+            self.engine.close()
         self.engine = None
         self.scene = None
         self.sensor = None

@@ -191,7 +191,11 @@ class Hp1Engine:
 
     def __init__(self, spec: MultirotorSpec, num_envs: int, device="cuda:0", *, physics_steps=1,
                  episode_len_steps=500, seed=0, env_id_offset=0, device_rng_reset=True, strict_stale_obs=True,
-                 materialize_derived=True, per_env_params="auto", debug_wrench=False):
+                 materialize_derived=True, per_env_params="auto", debug_wrench=False, host_io=False):
+        """host_io: obs / reward / terminations / truncations live in pinned, device-mapped HOST
+        memory (agx_host_alloc) and the fused task step stores them there directly over PCIe;
+        `actions` may then be a pinned host tensor (e.g. `self.host_actions`) that the kernel
+        reads in place.  The caller synchronises the stream before reading the results."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -207,10 +211,18 @@ class Hp1Engine:
         self.motor_thrust = z(N, M)
         self.sim_steps = z(N, dt=torch.int32)
         self.target_position = z(N, 3)
-        self.obs = z(N, 13)
-        self.reward = z(N)
-        self.terminations = z(N, dt=torch.bool)
-        self.truncations = z(N, dt=torch.bool)
+        self.host_io, self._host_allocs = bool(host_io), []
+        if self.host_io:
+            self.obs = self._host_tensor((N, 13), torch.float32)
+            self.reward = self._host_tensor((N,), torch.float32)
+            self.terminations = self._host_tensor((N,), torch.bool)
+            self.truncations = self._host_tensor((N,), torch.bool)
+            self.host_actions = self._host_tensor((N, spec.num_actions), torch.float32)
+        else:
+            self.obs = z(N, 13)
+            self.reward = z(N)
+            self.terminations = z(N, dt=torch.bool)
+            self.truncations = z(N, dt=torch.bool)
         self.reset_mask = z(N, dt=torch.bool)
         self.any_reset = z(8, dt=torch.int32)
         self.episode_count = z(N, dt=torch.int32)
@@ -241,6 +253,25 @@ class Hp1Engine:
         self._sync_buffers()
 
     # ---- plumbing ---------------------------------------------------------------------------
+    def _host_tensor(self, shape, dtype):
+        nbytes = max(1, int(np.prod(shape))) * torch.empty((), dtype=dtype).element_size()
+        p = C.c_void_p()
+        _lib.check(self.lib.agx_host_alloc(nbytes, C.byref(p)), "agx_host_alloc")
+        raw = (C.c_uint8 * nbytes).from_address(p.value)
+        C.memset(p, 0, nbytes)
+        self._host_allocs.append((p, raw))
+        n = int(np.prod(shape))
+        if n == 0:
+            return torch.empty(shape, dtype=dtype)
+        return torch.frombuffer(raw, dtype=dtype, count=n).view(shape)
+
+    def close(self):
+        """Free the mapped host buffers (host_io).  The tensors handed out must not be used afterwards."""
+        torch.cuda.synchronize(self.device)
+        for p, _ in self._host_allocs:
+            self.lib.agx_host_free(p)
+        self._host_allocs = []
+
     def _ptr(self, t: Optional[torch.Tensor]):
         return None if t is None else t.data_ptr()
 
@@ -257,8 +288,11 @@ class Hp1Engine:
     def _check_actions(self, actions):
         if actions.shape != (self.N, self.cfg.num_actions):
             raise ValueError("Action tensor does not have the correct number of environments")
-        if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
-            raise ValueError("actions must be a contiguous float32 tensor on the engine's device")
+        on_host_ok = self.host_io and actions.device.type == "cpu" and (
+            actions.data_ptr() == self.host_actions.data_ptr() or actions.is_pinned())
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or not (actions.device == self.device or on_host_ok):
+            raise ValueError("actions must be a contiguous float32 tensor on the engine's device"
+                             + (" or in pinned host memory" if self.host_io else ""))
         self._buf.actions = actions.data_ptr()
 
     # ---- C ABI calls ------------------------------------------------------------------------

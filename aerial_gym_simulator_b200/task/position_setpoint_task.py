@@ -7,7 +7,11 @@ tensors returned are the same objects every call, mutated in place, like the ref
 task_config.args:
   {"reset_rng": "device"}  (default) in-kernel Philox resets -> single launch, no host sync;
   {"reset_rng": "torch"}   reference-order torch draws; the host reads the any-reset flag each
-                           step exactly where the reference syncs (env_manager.py:364-375)."""
+                           step exactly where the reference syncs (env_manager.py:364-375).
+  {"host_io": True}        observations / rewards / terminations / truncations are pinned HOST tensors
+                           the kernel writes directly (agx_host_alloc), `actions` may be a pinned host
+                           tensor the kernel reads in place; step() returns after the stream has drained,
+                           so the results can be read at once.  For consumers that live on the host."""
 import numpy as np
 import torch
 
@@ -79,6 +83,9 @@ class PositionSetpointTask(BaseTask):
         env, eng = self.sim_env, self.sim_env.engine
         if actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.float().contiguous()
+        if eng.host_io and actions.device.type == "cpu" and not actions.is_pinned():
+            eng.host_actions.copy_(actions)  # pageable host memory: stage through the mapped buffer
+            actions = eng.host_actions
         self.prev_actions, self.actions = self.actions, actions  # the reference copies; nobody reads prev afterwards
         n = env.sample_physics_steps()  # consumes random.gauss like env_manager.py:417-425
         dist = env._draw_disturbance() if (env.spec.enable_disturbance and n == 1) else None
@@ -92,6 +99,8 @@ class PositionSetpointTask(BaseTask):
                 eng.any_reset.zero_()
                 env.reset_idx(eng.reset_mask.nonzero(as_tuple=False).squeeze(-1))  # ends with the all-env refresh + obs
         env.render(render_components="sensors")
+        if eng.host_io:
+            torch.cuda.current_stream(eng.device).synchronize()  # results are in host memory now
         self.infos = {}
         return self.get_return_tuple()
 

@@ -151,6 +151,16 @@ const char* agx_last_error(void);
  * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor */
 uint64_t agx_sizeof(int which);
 
+/* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
+ * Any of AgxHp1Buffers' `actions` (read) and `obs` / `reward` / `terminations` / `truncations`
+ * (write-only in the fused task step) may point into such a buffer: the step then loads its inputs
+ * from and stores its results to host memory over PCIe inside the one launch, without staging
+ * copies ("host I/O" mode; the caller synchronises the stream before reading).  The reference moves
+ * these tensors with .cpu() / .to("cuda") around task.step (e.g.
+ * rl_training/sample_factory/end_to_end_training/enjoy.py:70-91). */
+int agx_host_alloc(uint64_t bytes, void** out);
+int agx_host_free(void* p);
+
 /* Physics only: `physics_steps` x (update_states -> controller -> allocation -> motor -> drag ->
  * disturbance -> integrate).  Replaces the body of EnvManager.step's loop
  * (env_manager/env_manager.py:426-428 = robots/base_multirotor.py:296-307 + gym.simulate,

@@ -157,13 +157,15 @@ def _philox_draws(seed, gids, episodes, M):
 
 
 @pytest.mark.parametrize("case", ["quad_attitude", "octa_velocity"])
-@pytest.mark.parametrize("strict,materialize", [(True, True), (True, False), (False, True)],
-                         ids=["strict-two_launch", "strict-cooperative", "fresh"])
-def test_fused_position_task_step(case, strict, materialize):
+@pytest.mark.parametrize("strict,materialize,two_launch",
+                         [(True, True, True), (True, False, True), (True, True, False), (True, False, False), (False, True, False)],
+                         ids=["strict-refresh_pass", "strict-obs_patch_pass", "strict-cooperative-derived", "strict-cooperative", "fresh"])
+def test_fused_position_task_step(case, strict, materialize, two_launch):
     """Whole PositionSetpointTask.step in one C-ABI call, device-RNG resets, teacher-forced for
     30 steps: reward/obs to 1e-5, termination / truncation / reset masks and sim_steps bit-exact,
-    the stale-derived-state quirk reproduced (strict; via the refresh pass when derived states are
-    materialised, via the single cooperative launch otherwise) or disabled."""
+    the stale-derived-state quirk reproduced (strict: in the single cooperative launch, or -- the
+    path grids larger than one resident wave take, forced here by asking for the mid-step event --
+    by the refresh / obs-patch pass) or disabled."""
     spec = H.spec_for(case)
     model = H.oracle_model_from_spec(spec)
     N, M, seed, off = 777, spec.num_motors, 99, 1000
@@ -177,6 +179,10 @@ def test_fused_position_task_step(case, strict, materialize):
     episodes = np.zeros(N, dtype=np.int64)
     target = torch.zeros(N, 3)
     n_resets = n_ill = 0
+    mid = None
+    if two_launch:
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record()
     for step in range(30):
         actions = torch.rand(N, spec.num_actions, generator=g) * 2 - 1
         H.sync_engine_from_oracle(eng, st)
@@ -185,7 +191,7 @@ def test_fused_position_task_step(case, strict, materialize):
         # more than 1e-5 in ANY two fp32 implementations.  Such envs (expected ~1 per 10^4 uniformly
         # random attitudes) are checked for boundedness only.
         ok = H.well_conditioned(model, st, actions).numpy()
-        eng.position_task_step(actions.to(DEV))
+        eng.position_task_step(actions.to(DEV), mid_event=mid)
         draws = _philox_draws(seed, off + np.arange(N), episodes, M)
         st_ref = st
         obs, rew, term, trunc, rmask = O.position_task_step(model, st_ref, actions, target, 500, 1, draws=draws)
@@ -212,6 +218,9 @@ def test_fused_position_task_step(case, strict, materialize):
         H.assert_close(eng.tau_inc, st.tau_inc, f"step {step} tau_inc", scale=0.01)
         if spec.randomize_params:
             H.assert_close(eng.K_rot, st.K_rot, f"step {step} K_rot")
+        if materialize:  # derived arrays follow the same stale / refreshed rule as the observation
+            H.assert_close(eng.body_linvel.cpu()[ok], st.derived["body_linvel"][ok], f"step {step} derived body_linvel")
+            H.assert_close(eng.body_angvel.cpu()[ok], st.derived["body_angvel"][ok], f"step {step} derived body_angvel")
     assert n_resets >= N  # every env truncated at least once in the window
     assert n_ill <= 0.01 * 30 * N  # ill-conditioned samples are rare
 
@@ -238,6 +247,45 @@ def test_stale_observation_quirk():
     H.assert_close(eng.obs[:, 7:10], fresh["body_linvel"], "fresh body linvel after a reset elsewhere")
     H.assert_close(eng.obs[:, 10:13], fresh["body_angvel"], "fresh body angvel after a reset elsewhere")
     assert int(eng.any_reset[0]) == 0 and int(eng.any_reset[1]) == 0  # flag consumed
+    H.assert_close(eng.body_linvel, fresh["body_linvel"], "derived array refreshed as well")
+    ar = eng.any_reset.cpu().tolist()
+    assert ar[6] == 2 and ar[2 + 0] == 0 and ar[4 + 0] == 0  # two cooperative steps; next step's slots are clear
+
+
+def test_host_io_step_is_identical():
+    """Host I/O mode: the kernel reads actions from and writes obs / reward / flags to pinned,
+    device-mapped host memory.  Same bits as the device-buffer engine, step after step."""
+    spec = H.spec_for("quad_attitude")
+    N = 4099
+    root, actions, params = H.random_inputs(spec, N, seed=12)
+    engs = [Hp1Engine(spec, N, DEV, seed=5, materialize_derived=False, host_io=h) for h in (False, True)]
+    g = torch.Generator().manual_seed(2)
+    steps0 = torch.randint(490, 501, (N,), generator=g, dtype=torch.int32)
+    for e in engs:
+        H.load_engine_state(e, root, params)
+        e.sim_steps.copy_(steps0.to(DEV))
+    host = engs[1]
+    assert host.obs.device.type == "cpu" and host.obs.is_pinned()
+    pinned = torch.empty(N, spec.num_actions).pin_memory()
+    for step in range(25):
+        a = torch.rand(N, spec.num_actions, generator=g) * 2 - 1
+        engs[0].position_task_step(a.to(DEV))
+        if step % 2:  # the engine's own mapped buffer ...
+            host.host_actions.copy_(a)
+            host.position_task_step(host.host_actions)
+        else:         # ... or any pinned tensor
+            pinned.copy_(a)
+            host.position_task_step(pinned)
+        torch.cuda.synchronize()
+        assert torch.equal(engs[0].obs.cpu(), host.obs), f"step {step} obs"
+        assert torch.equal(engs[0].reward.cpu(), host.reward), f"step {step} reward"
+        assert torch.equal(engs[0].terminations.cpu(), host.terminations)
+        assert torch.equal(engs[0].truncations.cpu(), host.truncations)
+        assert torch.equal(engs[0].root_state, host.root_state)
+    assert host.truncations.any() or engs[0].episode_count.sum() > 0
+    with pytest.raises(ValueError):
+        host.position_task_step(torch.zeros(N, spec.num_actions))  # pageable host memory is refused
+    host.close()
 
 
 @pytest.mark.parametrize("case", ["quad_attitude", "octa_velocity"])
