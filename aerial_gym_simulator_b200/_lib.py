@@ -54,7 +54,9 @@ _HP1_BUF_FIELDS = [
 
 
 class AgxHp1Buffers(C.Structure):
-    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS]
+    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS] + [
+        ("gather_bufs", C.c_void_p), ("gather_flags", C.c_void_p), ("gather_done", C.c_void_p),
+        ("gather_world", C.c_int32), ("gather_rank", C.c_int32), ("gather_epoch", C.c_uint32), ("gather_lag", C.c_int32)]
 
 
 _HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",

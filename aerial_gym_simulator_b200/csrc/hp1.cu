@@ -44,6 +44,15 @@ struct Gains {
     V3 kp, kv, kr, kw;
 };
 
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // ---- tile IO ---------------------------------------------------------------------------
 // rows [env0, env0+n_valid) of a dense [N,13] array -> this lane's row in r[13]
 __device__ __forceinline__ void load_rows13(const float* __restrict__ base, int env0, int n_valid,
@@ -705,6 +714,52 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 if (derived) store_derived(buf, env, d);
             }
             store_rows13(buf.obs, env0_keep, n_valid_keep, tile, lane, o, vec_ok);
+            if (buf.gather_bufs) {  // the rows are still in the tile: push them into every rank's gathered buffer
+                const bool vec = vec_ok && n_valid_keep == 32 && (N & 3) == 0;
+                const size_t row0 = ((size_t)buf.gather_rank * N + env0_keep) * 13;
+                for (int pr = 0; pr < buf.gather_world; ++pr) {
+                    float* dst = reinterpret_cast<float*>(buf.gather_bufs[pr]) + row0;
+                    if (vec) {
+                        float4* d4 = reinterpret_cast<float4*>(dst);
+                        const float4* t4 = reinterpret_cast<const float4*>(tile);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            int idx = lane + 32 * i;
+                            if (idx < kTileFloats / 4) d4[idx] = t4[idx];
+                        }
+                    } else {
+                        for (int i = lane; i < n_valid_keep * 13; i += 32) dst[i] = tile[i];
+                    }
+                }
+            }
+        }
+        if (buf.gather_bufs) {
+            // all-gather handshake (same protocol as p2p_allgather_kernel): the last CTA of this rank
+            // publishes the epoch to every peer and waits for every peer's epoch
+            __syncthreads();  // the CTA's peer stores are ordered before thread 0's system-scope fence (cumulativity)
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                const unsigned done = atomicAdd(buf.gather_done, 1u);
+                if (done == gridDim.x - 1) {
+                    *buf.gather_done = 0u;
+                    __threadfence_system();
+                    const int W = buf.gather_world, R = buf.gather_rank;
+                    const uint32_t epoch = buf.gather_epoch;
+                    for (int pr = 0; pr < W; ++pr) st_release_sys_u32(buf.gather_flags[pr] + R, epoch);
+                    // gather_lag = 0: retire only when every peer's rows of THIS step have landed here.
+                    // gather_lag = 1: wait for the previous step's rows only -- this step's handshake then
+                    // overlaps the next step's compute (the consumer reads gathered obs one step late);
+                    // ranks still cannot drift more than one epoch apart, which the two buffers cover.
+                    const uint32_t want = epoch - (uint32_t)buf.gather_lag;
+                    const uint32_t* mine = buf.gather_flags[R];
+                    for (int q = 0; q < W; ++q) {
+                        unsigned long long spins = 0;
+                        while ((int32_t)(ld_acquire_sys_u32(mine + q) - want) < 0) {
+                            if (++spins > (1ull << 24)) __trap();  // a missing peer must not hang the GPU forever
+                        }
+                    }
+                }
+            }
         }
     }
 }
@@ -843,6 +898,13 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
             return agx_set_error(AGX_E_NULL, "task step needs sim_steps/obs/reward/terminations/truncations/any_reset");
         if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && !buf->episode_count)
             return agx_set_error(AGX_E_NULL, "device-RNG reset needs episode_count");
+        if (buf->gather_bufs) {
+            if (!buf->gather_flags || !buf->gather_done) return agx_set_error(AGX_E_NULL, "fused gather needs gather_flags/gather_done");
+            if (buf->gather_world < 1 || buf->gather_world > AGX_MAX_PEERS || buf->gather_rank < 0 || buf->gather_rank >= buf->gather_world)
+                return agx_set_error(AGX_E_INVALID, "fused gather: bad world/rank");
+            if (buf->gather_epoch == 0) return agx_set_error(AGX_E_INVALID, "fused gather: epoch starts at 1");
+            if (buf->gather_lag < 0 || buf->gather_lag > 1) return agx_set_error(AGX_E_INVALID, "fused gather: lag must be 0 or 1");
+        }
     }
     return AGX_OK;
 }
@@ -925,6 +987,11 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
             rc = agx_check_launch("hp1_refresh_kernel");
         }
     }
+    if (rc == AGX_OK && buf->gather_bufs && buf->gather_lag != 0)
+        return agx_set_error(AGX_E_INVALID, "gather_lag = 1 needs the cooperative path (grid within one resident wave)");
+    if (rc == AGX_OK && buf->gather_bufs)  // not fused on this path: the stand-alone all-gather kernel follows
+        rc = agx_p2p_allgather(buf->obs, buf->gather_bufs, buf->gather_flags, buf->gather_world, buf->gather_rank,
+                               (uint64_t)cfg->num_envs * 13 * sizeof(float), buf->gather_epoch, buf->gather_done, stream);
     return rc;
 }
 

@@ -50,7 +50,7 @@ p2p_allgather_kernel(const float4* __restrict__ local, void* const* __restrict__
             for (int q = 0; q < world; ++q) {
                 unsigned long long spins = 0;
                 while ((int32_t)(ld_acquire_sys(mine + q) - epoch) < 0) {
-                    if (++spins > (1ull << 31)) __trap();  // a missing peer must not hang the GPU forever
+                    if (++spins > (1ull << 24)) __trap();  // a missing peer must not hang the GPU forever
                 }
             }
         }

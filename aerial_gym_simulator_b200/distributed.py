@@ -67,7 +67,7 @@ class P2PObsAllGather:
     kernel of NVLink peer stores + a flag handshake (csrc/p2p_allgather.cu) over buffers obtained
     from a torch symmetric-memory rendezvous -- no NCCL call on the step path."""
 
-    def __init__(self, local_count: int, feat: int, device, group=None, dtype=torch.float32):
+    def __init__(self, local_count: int, feat: int, device, group=None, dtype=torch.float32, num_buffers: int = 2):
         import ctypes as C
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -87,8 +87,13 @@ class P2PObsAllGather:
         # two gathered buffers, alternated by epoch parity: a peer can run at most one epoch ahead of
         # the slowest reader (everybody waits for everybody's flag), so epoch e+1 never overwrites
         # data of epoch e that a slower rank may still be consuming
+        # (fused mode with lag 1 needs 4: a rank may push epoch e+4 once its peers finished epoch e+2,
+        # i.e. after their consumers of epoch e -- stream-ordered before their step e+2 -- are done)
+        if num_buffers not in (2, 4):
+            raise ValueError("num_buffers must be 2 or 4")
+        self.num_buffers = num_buffers
         self.outs, self.buf_ptrs = [], []
-        for _ in range(2):
+        for _ in range(num_buffers):
             o = symm_mem.empty(self.world * local_count, feat, dtype=dtype, device=self.device)
             h = symm_mem.rendezvous(o, group)
             self.outs.append(o)
@@ -103,13 +108,18 @@ class P2PObsAllGather:
         torch.cuda.synchronize(self.device)
         dist.barrier(group)  # every rank's flags are zeroed before anybody publishes epoch 1
 
+    def next_epoch(self):
+        """(epoch, buffer parity) of the next collective -- used by Hp1Engine when the all-gather is
+        fused into the step kernel (Hp1Engine.attach_obs_gather)."""
+        self.epoch += 1
+        return self.epoch, self.epoch % self.num_buffers
+
     def __call__(self, obs_local: torch.Tensor) -> torch.Tensor:
         C = self._C
         if obs_local.numel() * 4 != self.bytes or not obs_local.is_contiguous():
             raise ValueError("obs_local must be the contiguous local shard")
-        self.epoch += 1
+        _, b = self.next_epoch()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        b = self.epoch & 1
         self._check(self._lib.agx_p2p_allgather(
             C.c_void_p(obs_local.data_ptr()), C.c_void_p(self.buf_ptrs[b].data_ptr()), C.c_void_p(self.flag_ptrs.data_ptr()),
             self.world, self.rank, C.c_uint64(self.bytes), C.c_uint32(self.epoch), C.c_void_p(self.scratch.data_ptr()), stream),

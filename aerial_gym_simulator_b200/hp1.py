@@ -249,6 +249,7 @@ class Hp1Engine:
         # scratch for the light obs patch (only useful when derived states are not materialised)
         self.fresh_vel = z(6, N) if (strict_stale_obs and not materialize_derived) else None
         self._actions = None
+        self._gather, self.gathered_obs = None, None
         self._buf = AgxHp1Buffers()
         self._sync_buffers()
 
@@ -282,6 +283,33 @@ class Hp1Engine:
                 continue
             setattr(b, name, self._ptr(getattr(self, name, None)))
 
+    def attach_obs_gather(self, gather, lag=0):
+        """Fuse the multi-GPU observation all-gather into the task step (distributed.P2PObsAllGather):
+        the step kernel stores each observation row into every rank's gathered buffer over NVLink and
+        runs the flag handshake itself.  After position_task_step, `gathered_obs` is the complete
+        [world*N, 13] tensor of this step (lag=0) or of the previous step (lag=1: the handshake of
+        step t overlaps the compute of step t+1).  Several engines may share one gather object."""
+        if gather is not None and gather.bytes != self.N * 13 * 4:
+            raise ValueError("gather object was built for a different shard size")
+        self._gather, self.gathered_obs = gather, None
+        b = self._buf
+        if gather is None:
+            b.gather_bufs = b.gather_flags = b.gather_done = None
+            b.gather_world = b.gather_rank = b.gather_epoch = b.gather_lag = 0
+        else:
+            if lag not in (0, 1) or (lag == 1 and getattr(gather, "num_buffers", 2) < 4):
+                raise ValueError("lag must be 0, or 1 with a gather object built with num_buffers=4")
+            b.gather_lag = int(lag)
+            b.gather_flags, b.gather_done = gather.flag_ptrs.data_ptr(), gather.scratch.data_ptr()
+            b.gather_world, b.gather_rank = gather.world, gather.rank
+
+    def _arm_gather(self):
+        g = self._gather
+        if g is not None:
+            epoch, idx = g.next_epoch()
+            self._buf.gather_bufs, self._buf.gather_epoch = g.buf_ptrs[idx].data_ptr(), epoch
+            self.gathered_obs = g.outs[(epoch - self._buf.gather_lag) % len(g.outs)]
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -312,6 +340,7 @@ class Hp1Engine:
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
         ev = C.c_void_p(mid_event.cuda_event) if mid_event is not None else None
+        self._arm_gather()
         _lib.check(self.lib.agx_hp1_position_task_step_profiled(C.byref(self.cfg), C.byref(self._buf), self._stream(), ev),
                    "agx_hp1_position_task_step")
 

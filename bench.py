@@ -8,7 +8,8 @@
 
 One "step" = one PositionSetpointTask.step over one batch of 65,536 envs per GPU (weak scaling:
 per-GPU work fixed): fused physics + reward + termination/truncation + in-kernel reset +
-observation, then (N > 1) one NCCL all-gather of the observation tensor.
+observation and (N > 1) the all-gather of the observation tensor, by default fused into the same
+kernel (NVLink peer stores + flag handshake; --gather p2p|nccl for the stand-alone variants).
 
 Timing: W >= 3 warm-up steps, then exactly K steps bracketed by barrier + synchronize and one
 CUDA-event pair on the launching stream.  One 65,536-env working set (~12 MB) is smaller than the
@@ -212,13 +213,17 @@ def run_ours(args):
     acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
     gather = None
     if world > 1:
-        gather = P2PObsAllGather(N, 13, dev) if args.gather == "p2p" else ObsAllGather(N, 13, world * N, dev)
+        gather = ObsAllGather(N, 13, world * N, dev) if args.gather == "nccl" else \
+            P2PObsAllGather(N, 13, dev, num_buffers=4 if args.gather == "fused" else 2)
+        if args.gather == "fused":  # the step kernel pushes the rows to every peer and handshakes itself
+            for e in engines:
+                e.attach_obs_gather(gather)
     stream = torch.cuda.current_stream(dev)
 
     def step(i, mid=None, rotate=True):
         e = engines[i % R] if rotate else eng
         e.position_task_step(acts[i % 8], mid_event=mid)
-        if world > 1:
+        if world > 1 and args.gather != "fused":
             gather(e.obs)
 
     def barrier():
@@ -248,6 +253,26 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) * 1e-3
     value = world * N * K / total_s
+
+    # ---- N > 1, fused gather: same loop with the handshake of step t overlapping step t+1 (lag 1) ----
+    value_lag1 = None
+    if world > 1 and args.gather == "fused":
+        for e in engines:
+            e.attach_obs_gather(gather, lag=1)
+        for i in range(R):
+            step(i)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for i in range(K):
+            step(i)
+        l1.record(stream)
+        barrier()
+        lag_ms = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(lag_ms, op=dist.ReduceOp.MAX)
+        value_lag1 = world * N * K / (float(lag_ms.item()) * 1e-3)
+        for e in engines:
+            e.attach_obs_gather(gather, lag=0)
 
     # ---- dominant kernel alone: per-step event pairs.  At this size the fused step is ONE cooperative
     # launch (hp1_step_kernel<4,true,coop>), so the pair brackets exactly that kernel; on the
@@ -379,6 +404,7 @@ def run_ours(args):
             "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world,
                                               "obs_all_gather": (args.gather if world > 1 else None)}),
             "value_hot_l2": value_hot,
+            "value_obs_gather_lag1": value_lag1,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,coop> (whole fused step, one cooperative launch)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -487,8 +513,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1 observation all-gather: hand-written NVLink P2P kernel (default) or NCCL")
+    ap.add_argument("--gather", default="fused", choices=["fused", "p2p", "nccl"],
+                    help="N>1 observation all-gather: fused into the step kernel (NVLink peer stores + flag handshake, "
+                         "default), the stand-alone P2P kernel, or NCCL")
     ap.add_argument("--no-hp2", action="store_true", help="skip the secondary depth rays/sec measurement")
     ap.add_argument("--hp2-envs", type=int, default=8192)
     args = ap.parse_args()

@@ -128,6 +128,17 @@ typedef struct AgxHp1Buffers {
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
                                  when the stale-observation quirk is on and no derived array is materialised; the
                                  conditional pass then only patches obs[:,7:13] instead of recomputing.  May be NULL. */
+    /* multi-GPU: fused observation all-gather (NULL / 0 = off).  When set, the fused task step also
+     * stores every env's observation row into slot `gather_rank` of each rank's gathered buffer
+     * [gather_world * N, 13] over NVLink peer memory, then runs agx_p2p_allgather's flag handshake
+     * (same arguments, same meaning) before it retires -- compute and collective in one launch. */
+    void* const* gather_bufs;        /* DEVICE array of gather_world device pointers (this step's parity) */
+    uint32_t* const* gather_flags;   /* DEVICE array of gather_world device pointers to uint32[>= world] */
+    uint32_t* gather_done;           /* device uint32 (zero-initialised once): CTA completion counter */
+    int32_t gather_world, gather_rank;
+    uint32_t gather_epoch;           /* strictly increasing per step, starting at 1 */
+    int32_t gather_lag;              /* 0: the step retires when all peers' rows of this step are here;
+                                        1: when the PREVIOUS step's are (handshake overlaps the next step) */
 } AgxHp1Buffers;
 
 /* explicit uniform draws u in [0,1) for agx_hp1_reset, in the reference's call order */

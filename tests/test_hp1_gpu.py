@@ -370,3 +370,45 @@ def test_error_paths():
         eng.physics_step(torch.zeros(64, 4, device=DEV))
     with pytest.raises(_lib.AgxError):
         Hp1Engine(spec, 4, "cpu")
+
+
+class _LoopbackGather:
+    """world = 1 stand-in for distributed.P2PObsAllGather (which needs a process group): same
+    fields, plain device tensors.  Exercises the fused push + flag handshake of the step kernel."""
+
+    def __init__(self, n, dev):
+        self.world, self.rank, self.bytes, self.epoch = 1, 0, n * 13 * 4, 0
+        self.outs = [torch.zeros(n, 13, device=dev) for _ in range(2)]
+        self.buf_ptrs = [torch.tensor([o.data_ptr()], dtype=torch.int64, device=dev) for o in self.outs]
+        self.flags = torch.zeros(64, dtype=torch.int32, device=dev)
+        self.flag_ptrs = torch.tensor([self.flags.data_ptr()], dtype=torch.int64, device=dev)
+        self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch, self.epoch % 2
+
+
+@pytest.mark.parametrize("n,two_launch", [(4096, False), (777, False), (4096, True)])
+def test_fused_obs_gather_loopback(n, two_launch):
+    """The observation rows pushed into the gathered buffer by the step kernel (or, on the
+    two-launch path, by the stand-alone all-gather the library appends) equal the local obs."""
+    spec = H.spec_for("quad_attitude")
+    root, actions, params = H.random_inputs(spec, n, seed=4)
+    eng = Hp1Engine(spec, n, DEV, seed=9, materialize_derived=False)
+    H.load_engine_state(eng, root, params)
+    eng.sim_steps.copy_((torch.arange(n, device=DEV) % 500 + 480).int() % 501)
+    gth = _LoopbackGather(n, DEV)
+    eng.attach_obs_gather(gth)
+    mid = None
+    if two_launch:
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record()
+    if n % 4 and two_launch:
+        pytest.skip("stand-alone all-gather needs 16-byte shards")
+    for step in range(12):
+        eng.position_task_step(actions.to(DEV), mid_event=mid)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.gathered_obs, eng.obs), f"step {step}"
+        assert eng.gathered_obs is gth.outs[(step + 1) & 1]
+        assert int(gth.flags[0]) == step + 1 and int(gth.scratch[0]) == 0

@@ -1,5 +1,6 @@
 """N > 1 on real GPUs (needs >= 2 visible devices; the round-end single-GPU box skips it with a
-reason): the hand-written NVLink P2P observation all-gather equals NCCL's bit for bit."""
+reason): the hand-written NVLink P2P observation all-gather -- stand-alone kernel and fused into
+the HP1 step kernel -- equals NCCL's bit for bit."""
 import os
 import subprocess
 import sys
@@ -20,3 +21,4 @@ def test_p2p_allgather_equals_nccl():
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("P2P_ALLGATHER")][-1]
     assert "equal_to_nccl=True" in line, line
+    assert "fused_equal=True" in line, line  # the all-gather fused into the HP1 step kernel
