@@ -7,7 +7,7 @@ STEPS=${STEPS:-6}
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps $STEPS --warmup 3 --no-cpu-baseline --hp2-envs 2048 \
     > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:hp1_step_kernel -s 40 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:hp1_step_kernel -s ${SKIP:-20} -c 2 \
     -f -o gpurun_out/hp1_step_$TAG python bench.py --steps $STEPS --warmup 3 --no-cpu-baseline --no-hp2 \
     > gpurun_out/ncu_hp1.log 2>&1
 if [ "${HP2:-1}" = "1" ]; then
