@@ -10,7 +10,6 @@
 // two float4 per thread.  No tensor-core path: per-env work is <= 8x6 contractions.
 //
 // Reference functions restated here are cited inline (paths relative to aerial_gym/).
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -416,6 +415,42 @@ __device__ __forceinline__ void device_rng_reset(const AgxHp1Config& cfg, uint32
     apply_reset<M>(cfg, us, ubl, ubh, ug, um, s, p);
 }
 
+// Warp-cooperative form of device_rng_reset for the fused step: lane j computes Philox block j of the
+// resetting env (9 + M <= 17 blocks), the uniforms go through the warp's shared-memory tile and only
+// the owning lane applies them.  Same blocks, same uniforms, same results as the scalar form, but a
+// reset costs the warp one Philox evaluation instead of 8-17 (resets are rare and divergent: a warp
+// with ONE resetting env used to run ~850 extra instructions for it, the critical path of the launch).
+template <int M>
+__device__ __forceinline__ void coop_rng_draw(const AgxHp1Config& cfg, uint32_t env_gid, uint32_t episode, int lane, float* tile) {
+    const uint32_t k0 = (uint32_t)(cfg.seed & 0xffffffffu), k1 = (uint32_t)(cfg.seed >> 32);
+    if (lane < 9 + M) {
+        const bool bounds_hi_random = cfg.bounds_hi_min[0] != cfg.bounds_hi_max[0] || cfg.bounds_hi_min[1] != cfg.bounds_hi_max[1] ||
+                                      cfg.bounds_hi_min[2] != cfg.bounds_hi_max[2];
+        const bool needed = lane < 4 || lane >= 9 || (lane == 4 ? bounds_hi_random : (cfg.flags & AGX_F_RANDOMIZE_GAINS) != 0);
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (needed) {
+            U4 b = philox4x32_10(U4{env_gid, episode, (uint32_t)lane, 0u}, k0, k1);
+            u = make_float4(u01(b.x), u01(b.y), u01(b.z), u01(b.w));
+        }
+        reinterpret_cast<float4*>(tile)[lane] = u;
+    }
+}
+template <int M>
+__device__ __forceinline__ void apply_reset_from_tile(const AgxHp1Config& cfg, const float* tile, EnvState& s, EnvParams<M>& p) {
+    float us[13], ubl[3], ubh[3], ug[12], um[4 * M];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) us[i] = tile[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ubl[i] = tile[13 + i]; ubh[i] = tile[16 + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ug[3 * i] = tile[20 + 4 * i]; ug[3 * i + 1] = tile[21 + 4 * i]; ug[3 * i + 2] = tile[22 + 4 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * M; ++i) um[i] = tile[36 + i];
+    apply_reset<M>(cfg, us, ubl, ubh, ug, um, s, p);
+}
+
 template <int M>
 __device__ __forceinline__ void load_params(const AgxHp1Config& cfg, const AgxHp1Buffers& buf, int env, EnvParams<M>& p) {
     load_m<M>(buf.motor_thrust, env, p.thrust);
@@ -471,17 +506,32 @@ __device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3
 // main kernel
 // =========================================================================================
 // 8 CTAs/SM -> <= 128 registers: all 1024 CTAs of the 65,536-env launch are resident in one wave
-// COOP (cooperative launch: all CTAs co-resident, one tile per warp): the stale-observation quirk
-// ("a reset anywhere refreshes everybody", base_multirotor.py:204-205) is resolved inside the kernel
+// COOP (grid <= one resident wave, so all CTAs are co-resident; one tile per warp): the stale-observation
+// quirk ("a reset anywhere refreshes everybody", base_multirotor.py:204-205) is resolved inside the kernel
 // with a one-sided grid barrier instead of a second launch:
-//   * a warp that knows at its START that one of its envs truncates this step (sim_steps + 1 > episode
+//   * a warp that sees at its START that one of its envs truncates this step (sim_steps + 1 > episode
 //     length) raises the step's flag right away; crashes raise it in the epilogue;
-//   * every CTA counts itself in after its epilogue; an env that did not reset then needs the final
-//     value of the flag, which is known as soon as the flag is up (it is monotonic) OR all CTAs have
-//     arrived.  With staggered episodes some env truncates every step, so nobody ever waits.
+//   * every warp reads the flag when its physics is done (the load overlaps the epilogue).  Flag up
+//     (monotonic) -> everybody is refreshed: no waiting, no synchronisation at all.  With staggered
+//     episodes some env truncates every step, so this is the steady state;
+//   * flag still down: the warp counts itself in (fire-and-forget RED on a cumulative 64-bit counter)
+//     and waits until the flag rises OR all warps of the step have arrived (= nobody reset);
 //   * the observation (and the derived arrays) are written once, after the decision.
-// any_reset[2],[3]: arrival counters of even / odd steps; [4],[5]: flags; [6]: step counter
-// (device-side, so launches stay graph-safe); the last CTA to arrive clears the other parity's slots.
+// any_reset[2..3]: 64-bit cumulative arrival counter -- the step index is counter / n_tiles, read at
+// kernel start (device-side, so launches stay graph-safe; the buffer must always be used with the same
+// num_envs); any_reset[4],[5]: flags of even / odd steps, the next step's flag is cleared by CTA 0.
+#ifdef AGX_TIMELINE  // debug builds only (tools/dbg/timeline.py): per-warp start / end globaltimer stamps
+__device__ unsigned long long g_timeline[4][8192];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define AGX_TL(slot) do { if (lane == 0) { int w_ = blockIdx.x * kWarpsPerBlock + warp; if (w_ < 8192) g_timeline[slot][w_] = gtimer(); } } while (0)
+#else
+#define AGX_TL(slot) do { } while (0)
+#endif
+
 template <int M, bool TASK, bool COOP = false>
 __global__ void __launch_bounds__(kThreads, 8)
 hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
@@ -491,19 +541,21 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     const int N = cfg.num_envs;
     const int n_tiles = (N + 31) >> 5;
     const int A = cfg.num_actions;
-    int coop_ep = 0;
+    AGX_TL(0);
     int* reset_flag = buf.any_reset;
+    unsigned long long coop_target = 0;  // counter value once every warp of this step has arrived
     if constexpr (COOP) {
-        coop_ep = *reinterpret_cast<volatile int*>(buf.any_reset + 6);
-        reset_flag = buf.any_reset + 4 + (coop_ep & 1);
+        const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(buf.any_reset + 2);
+        const unsigned long long step_idx = cnt / (unsigned long long)n_tiles;
+        coop_target = (step_idx + 1ull) * (unsigned long long)n_tiles;
+        reset_flag = buf.any_reset + 4 + (int)(step_idx & 1ull);
+        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[4 + (int)((step_idx + 1ull) & 1ull)] = 0;  // last used two steps ago
     }
-    // state that outlives the tile loop in the COOP variant (one tile per warp there)
+    bool warp_raised = false;
     EnvState s;
     Derived d;
     V3 tgt{0.f, 0.f, 0.f};
     float o[13];
-    bool need_patch = false;
-    int env0_keep = -1, n_valid_keep = 0;
 
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < n_tiles; t += gridDim.x * kWarpsPerBlock) {
         const int env0 = t << 5;
@@ -541,7 +593,10 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         load_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
         if constexpr (COOP) {  // truncations are known before the physics: publish them now
             const bool trunc_early = valid && (steps_in + 1 > cfg.episode_len_steps);
-            if (__ballot_sync(0xffffffffu, trunc_early) && lane == 0) atomicOr(reset_flag, 1);
+            if (__ballot_sync(0xffffffffu, trunc_early)) {
+                warp_raised = true;
+                if (lane == 0) atomicOr(reset_flag, 1);
+            }
         }
         if (valid) {
             s = unpack(r);
@@ -598,11 +653,14 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             if (cfg.physics_steps == 0) d = update_states(s);
         }
 
+        AGX_TL(1);
         bool do_reset = false;
+        int flag_pre = 0;
+        if constexpr (COOP) flag_pre = *reinterpret_cast<volatile int*>(reset_flag);  // consumed after the epilogue
         if constexpr (TASK) {
+            int steps = steps_in + 1;  // env_manager.py:429
             if (valid) {
                 // ---- a16 reward + flags: position_setpoint_task.py:205-282 (stale derived) -----
-                int steps = steps_in + 1;  // env_manager.py:429
                 V3 e = quat_apply(quat_conj(d.qveh), tgt - s.x);
                 float dist = norm3(e);
                 float pos_reward = 3.0f * expf(-8.0f * dist * dist) + 2.0f * expf(-4.0f * dist * dist);
@@ -621,118 +679,132 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 buf.terminations[env] = crash ? 1 : 0;
                 buf.truncations[env] = trunc ? 1 : 0;
                 if (buf.reset_mask) buf.reset_mask[env] = do_reset ? 1 : 0;
-                bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
-                if (do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET)) {
-                    uint32_t ep = buf.episode_count[env];
-                    // temporaries: only they have their address taken by the out-of-line reset, so the
-                    // hot path keeps s / p in registers
-                    EnvState s2 = s;
-                    EnvParams<M> p2 = p;
-                    device_rng_reset<M>(cfg, (uint32_t)(cfg.env_id_offset + env), ep, s2, p2);
-                    s = s2;
-                    p = p2;
-                    buf.episode_count[env] = ep + 1u;
-                    store_reset_params<M>(buf, env, p);
-                    steps = 0;  // env_manager.py:301
-                    fresh = true;
-                }
-                buf.sim_steps[env] = steps;
-                if (fresh) d = update_states(s);
-                make_obs(s, d, tgt, o);
-                if constexpr (COOP) {
-                    need_patch = !fresh;  // this env's obs / derived arrays hold stale values
-                } else if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
-                    V3 vb = fresh ? d.vb : quat_rotate_inverse(s.q, s.v);
-                    V3 wb = fresh ? d.wb : quat_rotate_inverse(s.q, s.w);
-                    const size_t Ns = (size_t)N;
-                    buf.fresh_vel[env] = vb.x; buf.fresh_vel[Ns + env] = vb.y; buf.fresh_vel[2 * Ns + env] = vb.z;
-                    buf.fresh_vel[3 * Ns + env] = wb.x; buf.fresh_vel[4 * Ns + env] = wb.y; buf.fresh_vel[5 * Ns + env] = wb.z;
+            }
+            bool fresh = !(cfg.flags & AGX_F_STRICT_STALE_OBS);
+            // ---- a15 in-kernel reset, warp-cooperative Philox (see coop_rng_draw) -----------------
+            const bool rng_reset = do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET);
+            const unsigned rmask = __ballot_sync(0xffffffffu, rng_reset);
+            if (rmask) {
+                const uint32_t my_ep = rng_reset ? buf.episode_count[env] : 0u;
+                for (unsigned m = rmask; m; m &= m - 1) {
+                    const int owner = __ffs(m) - 1;
+                    const uint32_t ep = __shfl_sync(0xffffffffu, my_ep, owner);
+                    coop_rng_draw<M>(cfg, (uint32_t)(cfg.env_id_offset + env0 + owner), ep, lane, tile);
+                    __syncwarp();
+                    if (lane == owner) {
+                        apply_reset_from_tile<M>(cfg, tile, s, p);
+                        buf.episode_count[env] = ep + 1u;
+                        store_reset_params<M>(buf, env, p);
+                        steps = 0;  // env_manager.py:301
+                        fresh = true;
+                    }
+                    __syncwarp();
                 }
             }
-            unsigned any = __ballot_sync(0xffffffffu, do_reset);
-            if (any && lane == 0) atomicOr(reset_flag, 1);
-        }
-        if (valid) {
-            store_m<M>(buf.motor_thrust, env, p.thrust);
-            if (!(COOP && need_patch)) store_derived(buf, env, d);
-            if (buf.body_wrench) {
-                float* bw = buf.body_wrench + (size_t)env * 6;
-                bw[0] = Fx; bw[1] = Fy; bw[2] = Fz; bw[3] = Tx; bw[4] = Ty; bw[5] = Tz;
+            if constexpr (!COOP) {
+                if (valid) {
+                    buf.sim_steps[env] = steps;
+                    if (fresh) d = update_states(s);
+                    make_obs(s, d, tgt, o);
+                    if (buf.fresh_vel) {  // post-physics body velocities for the conditional obs patch
+                        V3 vb = fresh ? d.vb : quat_rotate_inverse(s.q, s.v);
+                        V3 wb = fresh ? d.wb : quat_rotate_inverse(s.q, s.w);
+                        const size_t Ns = (size_t)N;
+                        buf.fresh_vel[env] = vb.x; buf.fresh_vel[Ns + env] = vb.y; buf.fresh_vel[2 * Ns + env] = vb.z;
+                        buf.fresh_vel[3 * Ns + env] = wb.x; buf.fresh_vel[4 * Ns + env] = wb.y; buf.fresh_vel[5 * Ns + env] = wb.z;
+                    }
+                }
+                unsigned any = __ballot_sync(0xffffffffu, do_reset);
+                if (any && lane == 0) atomicOr(reset_flag, 1);
+            } else {
+                if (valid) buf.sim_steps[env] = steps;
+                if (__ballot_sync(0xffffffffu, do_reset)) {
+                    flag_pre = 1;
+                    if (!warp_raised && lane == 0) atomicOr(reset_flag, 1);
+                    warp_raised = true;
+                }
+                // ---- the decision: is anybody in the whole grid resetting this step? ----------------
+                bool counted = false;
+                int any = flag_pre;
+                if (!any && __any_sync(0xffffffffu, valid && !fresh)) {  // rare: count ourselves in, then wait
+                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(buf.any_reset + 2), 1ull);
+                    counted = true;
+                    volatile int* fl = reset_flag;
+                    volatile unsigned long long* cnt = reinterpret_cast<volatile unsigned long long*>(buf.any_reset + 2);
+                    any = *fl;
+                    while (!any) {
+                        if (*cnt >= coop_target) {  // every warp has arrived: the flag is final
+                            __threadfence();
+                            any = *fl;
+                            break;
+                        }
+                        __nanosleep(40);
+                        any = *fl;
+                    }
+                }
+                // ---- derived states for the observation: one common pass for resetting envs (new state)
+                // and, if anybody reset, for everybody else (post-physics state) ------------------------
+                const bool derived = buf.euler || buf.vehicle_orientation || buf.vehicle_linvel || buf.body_linvel || buf.body_angvel;
+                if (valid) {
+                    if (fresh || any) {
+                        if (derived) {
+                            d = update_states(s);
+                        } else {  // only the observation needs them: body-frame velocities
+                            d.vb = quat_rotate_inverse(s.q, s.v);
+                            d.wb = quat_rotate_inverse(s.q, s.w);
+                        }
+                    }
+                    make_obs(s, d, tgt, o);
+                    store_m<M>(buf.motor_thrust, env, p.thrust);
+                    if (derived) store_derived(buf, env, d);
+                    if (buf.body_wrench) {
+                        float* bw = buf.body_wrench + (size_t)env * 6;
+                        bw[0] = Fx; bw[1] = Fy; bw[2] = Fz; bw[3] = Tx; bw[4] = Ty; bw[5] = Tz;
+                    }
+                    pack(s, r);
+                }
+                store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+                store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+                if (buf.gather_bufs) {  // the rows are still in the tile: push them into every rank's gathered buffer
+                    const bool vec = vec_ok && n_valid == 32 && (N & 3) == 0;
+                    const size_t row0 = ((size_t)buf.gather_rank * N + env0) * 13;
+                    for (int pr = 0; pr < buf.gather_world; ++pr) {
+                        float* dst = reinterpret_cast<float*>(buf.gather_bufs[pr]) + row0;
+                        if (vec) {
+                            float4* d4 = reinterpret_cast<float4*>(dst);
+                            const float4* t4 = reinterpret_cast<const float4*>(tile);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                int idx = lane + 32 * i;
+                                if (idx < kTileFloats / 4) d4[idx] = t4[idx];
+                            }
+                        } else {
+                            for (int i = lane; i < n_valid * 13; i += 32) dst[i] = tile[i];
+                        }
+                    }
+                }
+                if (!counted && lane == 0) {
+                    if (warp_raised) __threadfence();  // the flag must be visible before this arrival is
+                    atomicAdd(reinterpret_cast<unsigned long long*>(buf.any_reset + 2), 1ull);
+                }
             }
-            pack(s, r);
         }
-        store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
-        if constexpr (COOP) {
-            env0_keep = env0;
-            n_valid_keep = n_valid;
-        } else if constexpr (TASK) {
-            store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+        if constexpr (!(TASK && COOP)) {
+            if (valid) {
+                store_m<M>(buf.motor_thrust, env, p.thrust);
+                store_derived(buf, env, d);
+                if (buf.body_wrench) {
+                    float* bw = buf.body_wrench + (size_t)env * 6;
+                    bw[0] = Fx; bw[1] = Fy; bw[2] = Fz; bw[3] = Tx; bw[4] = Ty; bw[5] = Tz;
+                }
+                pack(s, r);
+            }
+            store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
+            if constexpr (TASK) store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
         }
     }
+    AGX_TL(2);
     if constexpr (COOP) {
-        const int par = coop_ep & 1;
-        volatile int* arrived = buf.any_reset + 2 + par;
-        __syncthreads();  // this CTA's flag atomics are issued
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const int prev = atomicAdd(buf.any_reset + 2 + par, 1);
-            if (prev == (int)gridDim.x - 1) {  // everybody has read the step counter: open the next step
-                buf.any_reset[2 + (par ^ 1)] = 0;
-                buf.any_reset[4 + (par ^ 1)] = 0;
-                __threadfence();
-                buf.any_reset[6] = coop_ep + 1;
-            }
-        }
-        if (env0_keep >= 0) {
-            int any = 1;
-            if (__any_sync(0xffffffffu, need_patch)) {
-                volatile int* fl = reset_flag;
-                any = *fl;
-                while (!any) {
-                    if (*arrived >= (int)gridDim.x) {
-                        __threadfence();
-                        any = *fl;  // final
-                        break;
-                    }
-                    __nanosleep(40);
-                    any = *fl;
-                }
-            }
-            const int env = env0_keep + lane;
-            if (need_patch) {
-                const bool derived = buf.euler || buf.vehicle_orientation || buf.vehicle_linvel || buf.body_linvel || buf.body_angvel;
-                if (any) {  // refresh this env
-                    if (derived) {
-                        d = update_states(s);
-                    } else {  // only the observation needs the body-frame velocities
-                        d.vb = quat_rotate_inverse(s.q, s.v);
-                        d.wb = quat_rotate_inverse(s.q, s.w);
-                    }
-                    o[7] = d.vb.x; o[8] = d.vb.y; o[9] = d.vb.z;
-                    o[10] = d.wb.x; o[11] = d.wb.y; o[12] = d.wb.z;
-                }
-                if (derived) store_derived(buf, env, d);
-            }
-            store_rows13(buf.obs, env0_keep, n_valid_keep, tile, lane, o, vec_ok);
-            if (buf.gather_bufs) {  // the rows are still in the tile: push them into every rank's gathered buffer
-                const bool vec = vec_ok && n_valid_keep == 32 && (N & 3) == 0;
-                const size_t row0 = ((size_t)buf.gather_rank * N + env0_keep) * 13;
-                for (int pr = 0; pr < buf.gather_world; ++pr) {
-                    float* dst = reinterpret_cast<float*>(buf.gather_bufs[pr]) + row0;
-                    if (vec) {
-                        float4* d4 = reinterpret_cast<float4*>(dst);
-                        const float4* t4 = reinterpret_cast<const float4*>(tile);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            int idx = lane + 32 * i;
-                            if (idx < kTileFloats / 4) d4[idx] = t4[idx];
-                        }
-                    } else {
-                        for (int i = lane; i < n_valid_keep * 13; i += 32) dst[i] = tile[i];
-                    }
-                }
-            }
-        }
         if (buf.gather_bufs) {
             // all-gather handshake (same protocol as p2p_allgather_kernel): the last CTA of this rank
             // publishes the epoch to every peer and waits for every peer's epoch
@@ -749,7 +821,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                     // gather_lag = 0: retire only when every peer's rows of THIS step have landed here.
                     // gather_lag = 1: wait for the previous step's rows only -- this step's handshake then
                     // overlaps the next step's compute (the consumer reads gathered obs one step late);
-                    // ranks still cannot drift more than one epoch apart, which the two buffers cover.
+                    // ranks still cannot drift more than one epoch apart (four buffers cover that).
                     const uint32_t want = epoch - (uint32_t)buf.gather_lag;
                     const uint32_t* mine = buf.gather_flags[R];
                     for (int q = 0; q < W; ++q) {
@@ -762,6 +834,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             }
         }
     }
+    AGX_TL(3);
 }
 
 // refresh pass: update_states for all envs (+ obs).  only_if_flag: gated on any_reset[0] and the
@@ -937,6 +1010,12 @@ inline int grid_for(int n_envs) {
 
 extern "C" {
 
+#ifdef AGX_TIMELINE
+int agx_dbg_timeline(unsigned long long* host_out) {
+    return agx_check_cuda(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(g_timeline)), "timeline");
+}
+#endif
+
 int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream) {
     int rc = validate(cfg, buf, false);
     if (rc) return rc;
@@ -962,11 +1041,11 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
     const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
     if (strict_fused && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
-        // single cooperative launch: the obs patch happens after a grid-wide sync inside the kernel
-        int vv = v;
-        void* args[] = {(void*)cfg, (void*)buf, (void*)&vv};
-        const void* fn = cfg->num_motors == 4 ? (const void*)hp1_step_kernel<4, true, true> : (const void*)hp1_step_kernel<8, true, true>;
-        return agx_check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kThreads), args, 0, st), "cudaLaunchCooperativeKernel(hp1_step)");
+        // single launch: the whole grid is resident at once (g <= occupancy x SMs), so the in-kernel
+        // one-sided barrier cannot starve -- no cooperative-launch API needed for that
+        if (cfg->num_motors == 4) hp1_step_kernel<4, true, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+        else hp1_step_kernel<8, true, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+        return agx_check_launch("hp1_step_kernel<task, single-launch>");
     }
     if (cfg->num_motors == 4) hp1_step_kernel<4, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);

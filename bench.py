@@ -246,6 +246,7 @@ def run_ours(args):
     for i in range(K):
         step(i)
     ev1.record(stream)
+    t_enqueue = time.perf_counter() - t_wall0  # host time to enqueue the K steps (launches are asynchronous)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     total_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
@@ -406,6 +407,7 @@ def run_ours(args):
             "value_hot_l2": value_hot,
             "value_obs_gather_lag1": value_lag1,
             "wall_s_timed_region": t_wall,
+            "host_enqueue_us_per_step": 1e6 * t_enqueue / K,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,coop> (whole fused step, one cooperative launch)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,

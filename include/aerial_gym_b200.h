@@ -122,8 +122,9 @@ typedef struct AgxHp1Buffers {
     uint8_t* terminations;    /* [N] bool ("crashes") */
     uint8_t* truncations;     /* [N] bool */
     uint8_t* reset_mask;      /* [N] bool, envs reset (or to be reset) this step; may be NULL */
-    int32_t* any_reset;       /* [8] device scratch, zero-initialised by the caller once: [0] flag + [1] block-arrival
-                                 counter (two-launch path); [4],[5] even/odd-step flags + [6] step parity (cooperative path) */
+    int32_t* any_reset;       /* [8] device scratch, 16-byte aligned, zero-initialised by the caller once and then always used
+                                 with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path); [2..3] 64-bit
+                                 cumulative warp-arrival counter, [4],[5] even/odd-step flags (single-launch path) */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
                                  when the stale-observation quirk is on and no derived array is materialised; the
