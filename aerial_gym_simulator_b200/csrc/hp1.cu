@@ -542,6 +542,13 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     const int n_tiles = (N + 31) >> 5;
     const int A = cfg.num_actions;
     AGX_TL(0);
+    if constexpr (COOP) {
+        // programmatic dependent launch: the NEXT step's CTAs may be scheduled as soon as all of this grid's
+        // CTAs have started (they are all resident), and park at their own griddepcontrol.wait until this
+        // grid has completed and flushed -- the launch latency of step t+1 hides under the tail of step t
+        asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     int* reset_flag = buf.any_reset;
     unsigned long long coop_target = 0;  // counter value once every warp of this step has arrived
     if constexpr (COOP) {
@@ -1043,9 +1050,18 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     if (strict_fused && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
         // single launch: the whole grid is resident at once (g <= occupancy x SMs), so the in-kernel
         // one-sided barrier cannot starve -- no cooperative-launch API needed for that
-        if (cfg->num_motors == 4) hp1_step_kernel<4, true, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
-        else hp1_step_kernel<8, true, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
-        return agx_check_launch("hp1_step_kernel<task, single-launch>");
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(g);
+        lc.blockDim = dim3(kThreads);
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        cudaError_t e = (cfg->num_motors == 4) ? cudaLaunchKernelEx(&lc, hp1_step_kernel<4, true, true>, *cfg, *buf, v)
+                                               : cudaLaunchKernelEx(&lc, hp1_step_kernel<8, true, true>, *cfg, *buf, v);
+        return agx_check_cuda(e, "hp1_step_kernel<task, single-launch>");
     }
     if (cfg->num_motors == 4) hp1_step_kernel<4, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
