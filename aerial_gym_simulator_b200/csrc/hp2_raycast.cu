@@ -159,9 +159,7 @@ hp2_update_scene_kernel(const __grid_constant__ AgxHp2Scene sc, const uint8_t* _
             v3 a2 = quat_apply(q, v3{to[9], to[10], to[11]});
             o[0] = c.x + t.x; o[1] = c.y + t.y; o[2] = c.z + t.z;
             o[3] = a0.x; o[4] = a0.y; o[5] = a0.z; o[6] = a1.x; o[7] = a1.y; o[8] = a1.z; o[9] = a2.x; o[10] = a2.y; o[11] = a2.z;
-            const float scale = fabsf(o[0]) + fabsf(o[1]) + fabsf(o[2]) + to[12] + to[13] + to[14];
-            const float pad = 2e-4f + 4e-6f * scale;  // conservative: never cull a true hit
-            o[12] = to[12] + pad; o[13] = to[13] + pad; o[14] = to[14] + pad;
+            o[12] = to[12]; o[13] = to[13]; o[14] = to[14];  // true half extents; users pad them (obb_pad)
             o[15] = to[15];
         }
     }
@@ -342,16 +340,22 @@ __device__ __forceinline__ float aabb_entry(const float* nd, v3 o, v3 inv, float
     return hit ? tmin : -1.0f;
 }
 
+// padding of an oriented box for culling decisions: conservative, never culls a true hit
+__device__ __forceinline__ float obb_pad(const float* __restrict__ b) {
+    return 2e-4f + 4e-6f * (fabsf(b[0]) + fabsf(b[1]) + fabsf(b[2]) + b[12] + b[13] + b[14]);
+}
+
 // ray vs padded oriented box (object frame slabs); culling only
 __device__ __forceinline__ bool obb_may_hit(const float* __restrict__ b, v3 o, v3 d, float t_limit) {
     v3 r{o.x - b[0], o.y - b[1], o.z - b[2]};
+    const float pad = obb_pad(b);
     float tmin = 0.0f, tmax = t_limit + 1e-5f * (1.0f + t_limit);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float ax = b[3 + 3 * a], ay = b[4 + 3 * a], az = b[5 + 3 * a];
         const float oa = r.x * ax + r.y * ay + r.z * az;
         const float da = d.x * ax + d.y * ay + d.z * az;
-        const float h = b[12 + a];
+        const float h = b[12 + a] + pad;
         if (fabsf(da) < 1e-12f) {
             if (fabsf(oa) > h) return false;
         } else {
@@ -409,6 +413,194 @@ __device__ __forceinline__ Hit traverse(const float* __restrict__ nodes, const i
         } else {
             if (sp == 0) break;
             node = stack[--sp];
+        }
+    }
+    return best;
+}
+
+// =========================================================================================
+// Tile path (scenes of <= 128 leaf slots staged in shared memory): one warp = one 8x4 pixel tile.
+//  1. the warp culls the scene's objects against the tile's ray bundle ONCE (lane j tests leaf slots
+//     j, j+32, ...): four planes through the common ray origin spanned by the tile's corner rays, each
+//     pushed out to the minimum of n.d over the 32 actual ray directions, so the test is conservative
+//     for any ray set (camera pixels, LiDAR table entries, clamped border lanes);
+//  2. every lane then tests its own ray against the few surviving candidates in the same order --
+//     uniform control flow, no stack.  A canonical box (box_triangles order, obb[15] == 2) whose face
+//     the ray enters well inside needs only that face's two triangles; everything else runs all L.
+// The closest hit is the minimum over exact Moller-Trumbore tests with the oracle's tie-break, so the
+// result is independent of candidate order and bit-identical to the brute-force oracle.
+// =========================================================================================
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ v3 shfl3(v3 a, int src) {
+    return v3{__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src)};
+}
+
+constexpr int kTileMaxLeaves = 128;
+// per-image object record (shared memory, built once per work item by build_records):
+//   [0..8] box axes A0 A1 A2 | [9..11] (o - c).A_k for the sensor origin o | [12..14] true half extents |
+//   [15] pad | [16] kind (0 generic mesh in its AABB, 1 box-shaped bound only, 2 canonical box) | [17] object index |
+//   [18] face-shortcut margin | [19] nearest possible hit distance | [20] farthest point distance
+// 28-float stride: 8 lanes x 16 B of a float4 load hit 8 distinct bank groups (28 j mod 32 = 0,28,24,...,4)
+constexpr int kRecFloats = 28;
+
+__device__ __forceinline__ void build_records(const float* __restrict__ nodes, const int32_t* __restrict__ leaf,
+                                              const float* __restrict__ obb, int P, v3 o, float* __restrict__ rec, int* n_rec) {
+    for (int slot = threadIdx.x; slot < P; slot += blockDim.x) {
+        const int obj = leaf[slot];
+        if (obj < 0) continue;
+        v3 c, h, a0{1.f, 0.f, 0.f}, a1{0.f, 1.f, 0.f}, a2{0.f, 0.f, 1.f};
+        float kind = 0.0f, pad;
+        const float* b = obb ? obb + (size_t)obj * kObbFloats : nullptr;
+        if (b && b[15] != 0.0f) {
+            c = v3{b[0], b[1], b[2]};
+            a0 = v3{b[3], b[4], b[5]}; a1 = v3{b[6], b[7], b[8]}; a2 = v3{b[9], b[10], b[11]};
+            h = v3{b[12], b[13], b[14]};
+            kind = b[15];
+            pad = obb_pad(b);
+        } else {  // generic template: the leaf's world AABB
+            const float* nd = nodes + (size_t)(P - 1 + slot) * kNodeFloats;
+            c = v3{0.5f * (nd[0] + nd[4]), 0.5f * (nd[1] + nd[5]), 0.5f * (nd[2] + nd[6])};
+            h = v3{0.5f * (nd[4] - nd[0]), 0.5f * (nd[5] - nd[1]), 0.5f * (nd[6] - nd[2])};
+            pad = 2e-4f + 4e-6f * (fabsf(nd[0]) + fabsf(nd[1]) + fabsf(nd[2]) + fabsf(nd[4]) + fabsf(nd[5]) + fabsf(nd[6]));
+        }
+        const v3 r = sub3(o, c);
+        const float dist_c = sqrtf(dot3(r, r));
+        const v3 hp{h.x + pad, h.y + pad, h.z + pad};
+        const float rad_s = sqrtf(dot3(hp, hp));
+        float* q = rec + (size_t)atomicAdd(n_rec, 1) * kRecFloats;
+        q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = a1.x; q[4] = a1.y; q[5] = a1.z; q[6] = a2.x; q[7] = a2.y; q[8] = a2.z;
+        q[9] = dot3(r, a0); q[10] = dot3(r, a1); q[11] = dot3(r, a2);
+        q[12] = h.x; q[13] = h.y; q[14] = h.z;
+        q[15] = pad;
+        q[16] = kind;
+        q[17] = __int_as_float(obj);
+        q[18] = 1e-3f * (1.0f + 0.05f * (fabsf(r.x) + fabsf(r.y) + fabsf(r.z)));
+        q[19] = dist_c - rad_s;
+        q[20] = dist_c + rad_s;
+    }
+}
+
+struct TilePlanes {
+    v3 n[4];
+    float m[4];
+    float t_far;
+};
+// four planes through the common ray origin spanned by the tile's corner rays (lanes 0, 7, 31, 24), each
+// pushed out to the minimum of n.d over the 32 actual ray directions: conservative for any ray set
+__device__ __forceinline__ TilePlanes tile_planes(v3 d, float max_t) {
+    TilePlanes tp;
+    const v3 c0 = shfl3(d, 0), c1 = shfl3(d, 7), c2 = shfl3(d, 31), c3 = shfl3(d, 24);
+    const v3 dc{c0.x + c1.x + c2.x + c3.x, c0.y + c1.y + c2.y + c3.y, c0.z + c1.z + c2.z + c3.z};
+    tp.n[0] = cross3(c0, c1); tp.n[1] = cross3(c1, c2); tp.n[2] = cross3(c2, c3); tp.n[3] = cross3(c3, c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (dot3(tp.n[i], dc) < 0.0f) tp.n[i] = v3{-tp.n[i].x, -tp.n[i].y, -tp.n[i].z};
+        tp.m[i] = warp_min_f(dot3(tp.n[i], d));  // every ray of the tile satisfies n_i . d >= m_i
+    }
+    tp.t_far = warp_max_f(max_t);
+    return tp;
+}
+// can any ray of the tile hit this object's (padded) box?
+__device__ __forceinline__ bool tile_may_hit(const TilePlanes& tp, const float* __restrict__ q) {
+    const float4 q0 = reinterpret_cast<const float4*>(q)[0], q1 = reinterpret_cast<const float4*>(q)[1];
+    const float4 q2 = reinterpret_cast<const float4*>(q)[2], q3 = reinterpret_cast<const float4*>(q)[3];
+    const float4 q4 = reinterpret_cast<const float4*>(q)[4], q5 = reinterpret_cast<const float4*>(q)[5];
+    const v3 a0{q0.x, q0.y, q0.z}, a1{q0.w, q1.x, q1.y}, a2{q1.z, q1.w, q2.x};
+    const float oa0 = q2.y, oa1 = q2.z, oa2 = q2.w;
+    const float pad = q3.w;
+    const float h0 = q3.x + pad, h1 = q3.y + pad, h2 = q3.z + pad;
+    bool cand = q4.w <= tp.t_far * (1.0f + 1e-5f) + 1e-5f;  // nearest possible hit within range
+    const float reach = q5.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float n0 = dot3(tp.n[i], a0), n1 = dot3(tp.n[i], a1), n2 = dot3(tp.n[i], a2);
+        const float sN = -fmaf(oa2, n2, fmaf(oa1, n1, oa0 * n0));  // n . (c - o)
+        const float rad = fmaf(fabsf(n2), h2, fmaf(fabsf(n1), h1, fabsf(n0) * h0));
+        const float bound = tp.m[i] < 0.0f ? tp.m[i] * reach : 0.0f;
+        if (sN + rad < bound - 1e-4f * (fabsf(sN) + rad + fabsf(bound))) cand = false;  // whole box outside plane i
+    }
+    return cand;
+}
+
+__constant__ unsigned char kBoxFaceTris[6][2] = {{0, 2}, {10, 11}, {1, 5}, {7, 9}, {3, 8}, {4, 6}};  // hp2.py box_triangles
+
+// one ray (origin o, unit direction d) vs the object of record q
+__device__ __forceinline__ void record_object_test(const float* __restrict__ q, const float* __restrict__ tris, int L, v3 o, v3 d,
+                                                   float max_t, Hit& best) {
+    const float4 q0 = reinterpret_cast<const float4*>(q)[0], q1 = reinterpret_cast<const float4*>(q)[1];
+    const float4 q2 = reinterpret_cast<const float4*>(q)[2], q3 = reinterpret_cast<const float4*>(q)[3];
+    const float4 q4 = reinterpret_cast<const float4*>(q)[4];
+    const float oa[3] = {q2.y, q2.z, q2.w};
+    const float hh[3] = {q3.x, q3.y, q3.z};
+    const float pad = q3.w;
+    const float da[3] = {fmaf(d.z, q0.z, fmaf(d.y, q0.y, d.x * q0.x)), fmaf(d.z, q1.y, fmaf(d.y, q1.x, d.x * q0.w)),
+                         fmaf(d.z, q2.x, fmaf(d.y, q1.w, d.x * q1.z))};
+    float te[3];
+    float tmin = 0.0f, tmax = best.t + 1e-5f * (1.0f + best.t);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        te[a] = -FLT_MAX;
+        if (fabsf(da[a]) < 1e-12f) {
+            if (fabsf(oa[a]) > hh[a] + pad) return;
+        } else {
+            const float inv = __frcp_rn(da[a]);
+            const float hp = hh[a] + pad;
+            const float t1 = (-hp - oa[a]) * inv, t2 = (hp - oa[a]) * inv;
+            tmin = fmaxf(tmin, fminf(t1, t2));
+            tmax = fminf(tmax, fmaxf(t1, t2));
+            te[a] = ((da[a] > 0.0f ? -hh[a] : hh[a]) - oa[a]) * inv;  // entry through the TRUE face plane of this axis
+        }
+    }
+    if (!(tmin <= tmax + 1e-5f * (1.0f + fabsf(tmax)))) return;  // misses the padded box, or it lies beyond the best hit
+    const int obj = __float_as_int(q4.y);
+    const float4* tp = reinterpret_cast<const float4*>(tris + (size_t)obj * L * kTriFloats);
+    const int tri0 = obj * L;
+    if (q4.x == 2.0f && L >= 12) {
+        // entry face = the axis entered last; valid shortcut only if the ray crosses that face well inside it
+        const float t = fmaxf(te[0], fmaxf(te[1], te[2]));
+        const bool a0 = te[0] >= te[1] && te[0] >= te[2], a1 = !a0 && te[1] >= te[2];  // selected axis (no dynamic indexing)
+        const float da_sel = a0 ? da[0] : (a1 ? da[1] : da[2]);
+        const float margin = q4.z;
+        const bool lat0 = fabsf(fmaf(t, da[0], oa[0])) <= hh[0] - margin;
+        const bool lat1 = fabsf(fmaf(t, da[1], oa[1])) <= hh[1] - margin;
+        const bool lat2 = fabsf(fmaf(t, da[2], oa[2])) <= hh[2] - margin;
+        const bool inside = t > 1e-4f && fabsf(da_sel) >= 0.05f && (a0 || lat0) && (a1 || lat1) && (a0 || a1 || lat2);
+        if (inside) {
+            const int face = (a0 ? 0 : (a1 ? 2 : 4)) + (da_sel > 0.0f ? 0 : 1);
+            Hit fh{max_t, 0x7fffffff};
+            const int s0 = kBoxFaceTris[face][0], s1 = kBoxFaceTris[face][1];
+            tri_test(tp + 3 * s0, tri0 + s0, o, d, max_t, fh);
+            tri_test(tp + 3 * s1, tri0 + s1, o, d, max_t, fh);
+            if (fh.tri != 0x7fffffff) {
+                if (fh.t < best.t || (fh.t == best.t && fh.tri < best.tri)) best = fh;
+                return;
+            }
+        }
+    }
+    for (int s = 0; s < L; ++s) tri_test(tp + 3 * s, tri0 + s, o, d, max_t, best);
+}
+
+// closest hit of this lane's ray; all 32 lanes of the warp (one 8x4 tile, common origin o) must call it together
+__device__ __forceinline__ Hit tile_closest_hit(const float* __restrict__ rec, int n_rec, const float* __restrict__ tris, int L, v3 o,
+                                                v3 d, float max_t, int lane) {
+    Hit best{max_t, 0x7fffffff};
+    const TilePlanes tp = tile_planes(d, max_t);
+    for (int base = 0; base < n_rec; base += 32) {
+        const bool cand = (base + lane < n_rec) && tile_may_hit(tp, rec + (size_t)(base + lane) * kRecFloats);
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int j = base + __ffs(m) - 1;
+            m &= m - 1;
+            record_object_test(rec + (size_t)j * kRecFloats, tris, L, o, d, max_t, best);
         }
     }
     return best;
@@ -515,12 +707,13 @@ __device__ __forceinline__ float range_epilogue(const AgxHp2Sensor& s, float px)
 
 constexpr int kCastThreads = 256;
 
-template <bool SMEM>
+template <bool SMEM, bool TILE = false>
 __global__ void __launch_bounds__(kCastThreads)
 hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ AgxHp2Sensor sn, int rows_per_item,
                 int items_per_image, long long n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_nrec;
     const int K = sc.num_objects, P = sc.leaves_pow2, L = sc.tris_per_object;
     const int W = sn.width, H = sn.height, S = sn.num_sensors;
     const uint32_t node_bytes = (uint32_t)((2 * P - 1) * kNodeFloats * 4);
@@ -532,6 +725,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
     float* s_tris = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_leaf) + ((leaf_bytes + 15u) & ~15u));
     const uint32_t obb_bytes = sc.obb ? (uint32_t)((size_t)K * kObbFloats * 4) : 0u;
     float* s_obb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_tris) + tri_bytes);
+    float* s_rec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_obb) + ((obb_bytes + 15u) & ~15u));  // TILE only
     if (SMEM && threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -601,9 +795,21 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         // warp <-> 8x4 pixel tile: neighbouring rays stay in one warp (coherent traversal, SIMT efficiency)
         const int tiles_x = (W + 7) >> 3, tiles_y = (y1 - y0 + 3) >> 2;
         const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
+        constexpr bool tile_path = SMEM && TILE;
+        if constexpr (tile_path) {  // per-image object records (depend on the sensor origin)
+            __syncthreads();        // previous item's records are no longer read
+            if (threadIdx.x == 0) s_nrec = 0;
+            __syncthreads();
+            build_records(nodes, leaf, obb, P, sp, s_rec, &s_nrec);
+            __syncthreads();
+        }
+        const int n_rec = tile_path ? s_nrec : 0;
         for (int tix = threadIdx.x >> 5; tix < tiles_x * tiles_y; tix += kCastThreads / 32) {
-            const int x = (tix % tiles_x) * 8 + lx, y = y0 + (tix / tiles_x) * 4 + ly;
-            if (x >= W || y >= y1) continue;
+            int x = (tix % tiles_x) * 8 + lx, y = y0 + (tix / tiles_x) * 4 + ly;
+            const bool in_image = x < W && y < y1;
+            if (!tile_path && !in_image) continue;
+            x = min(x, W - 1);  // tile path: border lanes shadow the nearest pixel (they take part in the
+            y = min(y, y1 - 1); // warp-wide culling) and skip the stores
             v3 uv, rd;
             float mult = 1.0f, max_t = sn.far_plane;
             if (is_cam) {  // warp_camera_kernels.py:186-221
@@ -619,7 +825,13 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
                 uv = normalize3(v3{rt[0], rt[1], rt[2]});
                 rd = normalize3(quat_rotate(sq, uv));
             }
-            Hit h = traverse<SMEM>(nodes, leaf, tris, obb, P, L, sp, rd, max_t);
+            Hit h;
+            if constexpr (tile_path) {
+                h = tile_closest_hit(s_rec, n_rec, tris, L, sp, rd, max_t, lane);
+                if (!in_image) continue;
+            } else {
+                h = traverse<SMEM>(nodes, leaf, tris, obb, P, L, sp, rd, max_t);
+            }
             float dist = AGX_NO_HIT_RAY_VAL;
             int segv = AGX_NO_HIT_SEG_VAL;
             const bool hit = h.tri != 0x7fffffff;
@@ -691,6 +903,7 @@ inline int next_pow2(int v) {
     while (p < v) p <<= 1;
     return p;
 }
+inline size_t record_smem_bytes(int K) { return (size_t)K * kRecFloats * 4 + 16; }
 inline size_t scene_smem_bytes(int K, int P, int L, bool with_obb) {
     size_t nb = ((size_t)(2 * P - 1) * kNodeFloats * 4 + 15) & ~(size_t)15;
     size_t lb = (size_t)(P < 4 ? 4 : P) * 4;
@@ -782,7 +995,20 @@ int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
     size_t smem = scene_smem_bytes(sc->num_objects, sc->leaves_pow2, sc->tris_per_object, sc->obb != nullptr);
     bool use_smem = smem + 1024 <= (size_t)max_smem;
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_smem) {
+    const bool use_tile = use_smem && sc->leaves_pow2 <= kTileMaxLeaves &&
+                          smem + record_smem_bytes(sc->num_objects) + 1024 <= (size_t)max_smem;
+    if (use_tile) {  // small staged scenes: warp-per-tile candidate culling, no per-ray BVH walk
+        smem += record_smem_bytes(sc->num_objects);
+        rc = agx_check_cuda(cudaFuncSetAttribute(hp2_cast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(cast)");
+        if (rc) return rc;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp2_cast_kernel<true, true>, kCastThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sms * per_sm;
+        if (grid > n_items) grid = n_items;
+        hp2_cast_kernel<true, true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+    } else if (use_smem) {
         rc = agx_check_cuda(cudaFuncSetAttribute(hp2_cast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(cast)");
         if (rc) return rc;

@@ -31,10 +31,13 @@ def box_triangles(size: Sequence[float]) -> np.ndarray:
 
 
 def box_obb(size: Sequence[float], R=None, p=None) -> np.ndarray:
-    """[16] oriented-box record of a box template: centre, 3 axes (columns of R), half extents, valid=1."""
+    """[16] oriented-box record of a box template: centre, 3 axes (columns of R), half extents, kind.
+    kind = 2: the template's triangles are box_triangles(size) in that order, transformed by (R, p) --
+    the ray-caster may then test only the two triangles of the face a ray enters through; kind = 1: some
+    other mesh with this bounding box (culling only); kind = 0: no box."""
     R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64)
     p = np.zeros(3) if p is None else np.asarray(p, dtype=np.float64)
-    return np.concatenate([p, R[:, 0], R[:, 1], R[:, 2], np.asarray(size, dtype=np.float64) / 2.0, [1.0]]).astype(np.float32)
+    return np.concatenate([p, R[:, 0], R[:, 1], R[:, 2], np.asarray(size, dtype=np.float64) / 2.0, [2.0]]).astype(np.float32)
 
 
 def _next_pow2(v: int) -> int:
