@@ -452,8 +452,12 @@ constexpr int kTileMaxLeaves = 128;
 // 28-float stride: 8 lanes x 16 B of a float4 load hit 8 distinct bank groups (28 j mod 32 = 0,28,24,...,4)
 constexpr int kRecFloats = 28;
 
+// frustum: optional 4 inward plane normals through o that bound every ray of the work item (camera pixel
+// blocks: ray directions are affine in the pixel coordinates before normalisation, so the block's corner
+// rays span all of them); objects entirely outside one plane get no record.
 __device__ __forceinline__ void build_records(const float* __restrict__ nodes, const int32_t* __restrict__ leaf,
-                                              const float* __restrict__ obb, int P, v3 o, float* __restrict__ rec, int* n_rec) {
+                                              const float* __restrict__ obb, int P, v3 o, const v3* frustum, float t_far,
+                                              float* __restrict__ rec, int* n_rec) {
     for (int slot = threadIdx.x; slot < P; slot += blockDim.x) {
         const int obj = leaf[slot];
         if (obj < 0) continue;
@@ -476,6 +480,21 @@ __device__ __forceinline__ void build_records(const float* __restrict__ nodes, c
         const float dist_c = sqrtf(dot3(r, r));
         const v3 hp{h.x + pad, h.y + pad, h.z + pad};
         const float rad_s = sqrtf(dot3(hp, hp));
+        if (dist_c - rad_s > t_far * (1.0f + 1e-5f) + 1e-5f) continue;  // out of range for every ray of the item
+        if (frustum) {
+            bool outside = false;
+            const v3 rc{-r.x, -r.y, -r.z};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const v3 n = frustum[i];
+                const float sN = dot3(n, rc);
+                const float rad = fmaf(fabsf(dot3(n, a2)), hp.z, fmaf(fabsf(dot3(n, a1)), hp.y, fabsf(dot3(n, a0)) * hp.x));
+                // rays satisfy n.d >= -1e-5 |n| (rounding of the corner rays): points on them n.x >= -1e-5 |n| |x|
+                const float bound = -1e-5f * sqrtf(dot3(n, n)) * (dist_c + rad_s);
+                if (sN + rad < bound - 1e-4f * (fabsf(sN) + rad + fabsf(bound))) outside = true;
+            }
+            if (outside) continue;
+        }
         float* q = rec + (size_t)atomicAdd(n_rec, 1) * kRecFloats;
         q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = a1.x; q[4] = a1.y; q[5] = a1.z; q[6] = a2.x; q[7] = a2.y; q[8] = a2.z;
         q[9] = dot3(r, a0); q[10] = dot3(r, a1); q[11] = dot3(r, a2);
@@ -707,8 +726,13 @@ __device__ __forceinline__ float range_epilogue(const AgxHp2Sensor& s, float px)
 
 constexpr int kCastThreads = 256;
 
+// 4 CTAs of 256 threads per SM (<= 64 registers): the kernel is latency bound, 32 resident warps per SM
+// measured 2.0x faster than 16 (tools/dbg/build_variant.sh) despite ~200 B of spills
+#ifndef AGX_CAST_MIN_BLOCKS
+#define AGX_CAST_MIN_BLOCKS 4
+#endif
 template <bool SMEM, bool TILE = false>
-__global__ void __launch_bounds__(kCastThreads)
+__global__ void __launch_bounds__(kCastThreads, AGX_CAST_MIN_BLOCKS)
 hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ AgxHp2Sensor sn, int rows_per_item,
                 int items_per_image, long long n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -800,7 +824,37 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
             __syncthreads();        // previous item's records are no longer read
             if (threadIdx.x == 0) s_nrec = 0;
             __syncthreads();
-            build_records(nodes, leaf, obb, P, sp, s_rec, &s_nrec);
+            v3 fr[4];
+            bool have_frustum = false;
+            float item_far = sn.far_plane;
+            if (is_cam) {  // corner rays of this item's pixel block, same arithmetic as the per-pixel rays below
+                const float xs[2] = {0.0f, (float)(W - 1)}, ys[2] = {(float)(rb * rows_per_item), (float)(min(H, rb * rows_per_item + rows_per_item) - 1)};
+                v3 cd[4];
+                float min_mult = 1.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v3 cuv = kinv_mul(sn.kinv, v3{xs[(k == 1 || k == 2) ? 1 : 0], ys[k >> 1], 1.0f});
+                    if (norm_uv) cuv = normalize3(cuv);
+                    cd[k] = normalize3(quat_rotate(sq, cuv));
+                    min_mult = fminf(min_mult, dot3(cd[k], rd_p));
+                }
+                // the planes are only meaningful for a pyramid narrower than a half space
+                const v3 dcs{cd[0].x + cd[1].x + cd[2].x + cd[3].x, cd[0].y + cd[1].y + cd[2].y + cd[3].y, cd[0].z + cd[1].z + cd[2].z + cd[3].z};
+                have_frustum = min_mult > 0.2f;
+                fr[0] = cross3(cd[0], cd[1]); fr[1] = cross3(cd[1], cd[2]); fr[2] = cross3(cd[2], cd[3]); fr[3] = cross3(cd[3], cd[0]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (dot3(fr[k], dcs) < 0.0f) fr[k] = v3{-fr[k].x, -fr[k].y, -fr[k].z};
+                    // every corner ray must be on the inner side of every plane, else do not trust the pyramid
+                    for (int j = 0; j < 4; ++j)
+                        if (dot3(fr[k], cd[j]) < -1e-5f * sqrtf(dot3(fr[k], fr[k]))) have_frustum = false;
+                }
+                if (sn.kind != AGX_SENSOR_NORMAL_FACEID_CAMERA && !sn.return_pointcloud && sn.calculate_depth && min_mult > 0.2f)
+                    item_far = sn.far_plane / min_mult;  // largest per-pixel max_t of the block is at a corner
+                else if (sn.kind != AGX_SENSOR_NORMAL_FACEID_CAMERA && !sn.return_pointcloud && sn.calculate_depth)
+                    item_far = FLT_MAX;
+            }
+            build_records(nodes, leaf, obb, P, sp, have_frustum ? fr : nullptr, item_far, s_rec, &s_nrec);
             __syncthreads();
         }
         const int n_rec = tile_path ? s_nrec : 0;
