@@ -16,6 +16,7 @@ UNITS = [
     # hp1: 2-ulp division / sqrt (no slow-path branches): the step is instruction-fetch bound at
     # 65,536 envs (profiles/hp1_step_r1.md: stall_no_instruction dominates), every instruction counts
     ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
+    ("hp1_aux.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

@@ -67,6 +67,15 @@ class AgxHp1ResetDraws(C.Structure):
     _fields_ = [(n, fp) for n in _HP1_DRAW_FIELDS]
 
 
+class AgxNavRewardParams(C.Structure):
+    _fields_ = [("v", C.c_float * 18)]
+
+
+class AgxImuConfig(C.Structure):
+    _fields_ = [("world_frame", C.c_int32), ("enable_noise", C.c_int32), ("enable_bias", C.c_int32), ("sqrt_dt", C.c_float),
+                ("g_world", C.c_float * 3), ("bias_std", C.c_float * 6), ("noise_std", C.c_float * 6), ("max_meas", C.c_float * 6)]
+
+
 class AgxHp2Scene(C.Structure):
     _fields_ = [
         ("num_envs", C.c_int32), ("num_objects", C.c_int32), ("leaves_pow2", C.c_int32),
@@ -132,6 +141,10 @@ def load():
         "agx_hp2_update_scene": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_void_p],
         "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
         "agx_p2p_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
+        "agx_nav_reward": [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                           C.POINTER(AgxNavRewardParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "agx_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p],
+        "agx_imu_update": [C.c_int, C.POINTER(AgxImuConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7,
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
         "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -143,6 +156,8 @@ def load():
     lib.agx_hp2_scene_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     if lib.agx_sizeof(3) != C.sizeof(AgxHp2Scene) or lib.agx_sizeof(4) != C.sizeof(AgxHp2Sensor):
         raise AgxError("HP2 ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
+    if lib.agx_sizeof(5) != C.sizeof(AgxNavRewardParams) or lib.agx_sizeof(6) != C.sizeof(AgxImuConfig):
+        raise AgxError("aux ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
             or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):
         raise AgxError("ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")

@@ -28,3 +28,80 @@ class position_setpoint_task_config:
         "absolute_action_reward_gain": [2.0, 2.0, 2.0],
         "crash_penalty": -100,
     }
+
+
+class navigation_task_config:
+    """config/task_config/navigation_task_config.py"""
+    seed = -1
+    sim_name = "base_sim"
+    env_name = "env_with_obstacles"
+    robot_name = "lmf2"
+    controller_name = "lmf2_velocity_control"
+    args = {}
+    num_envs = 1024
+    use_warp = True
+    headless = True
+    device = "cuda:0"
+    observation_space_dim = 13 + 4 + 64  # root_state + action_dim + latent_dims
+    privileged_observation_space_dim = 0
+    action_space_dim = 4
+    episode_len_steps = 100
+    return_state_before_reset = False
+    target_min_ratio = [0.90, 0.1, 0.1]
+    target_max_ratio = [0.94, 0.90, 0.90]
+    reward_parameters = {
+        "pos_reward_magnitude": 5.0,
+        "pos_reward_exponent": 1.0 / 3.5,
+        "very_close_to_goal_reward_magnitude": 5.0,
+        "very_close_to_goal_reward_exponent": 2.0,
+        "getting_closer_reward_multiplier": 10.0,
+        "x_action_diff_penalty_magnitude": 0.8,
+        "x_action_diff_penalty_exponent": 3.333,
+        "z_action_diff_penalty_magnitude": 0.8,
+        "z_action_diff_penalty_exponent": 5.0,
+        "yawrate_action_diff_penalty_magnitude": 0.8,
+        "yawrate_action_diff_penalty_exponent": 3.33,
+        "x_absolute_action_penalty_magnitude": 0.1,
+        "x_absolute_action_penalty_exponent": 0.3,
+        "z_absolute_action_penalty_magnitude": 1.5,
+        "z_absolute_action_penalty_exponent": 1.0,
+        "yawrate_absolute_action_penalty_magnitude": 1.5,
+        "yawrate_absolute_action_penalty_exponent": 2.0,
+        "collision_penalty": -100.0,
+    }
+
+    class vae_config:
+        use_vae = True
+        latent_dims = 64
+        # the reference ships its weights inside its own tree (utils/vae/weights/, 44 MB, not redistributed here):
+        # point model_file at that checkpoint; without it the encoder runs with its initial weights
+        model_file = "ICRA_test_set_more_sim_data_kld_beta_3_LD_64_epoch_49.pth"
+        model_folder = ""
+        image_res = (270, 480)
+        interpolation_mode = "nearest"
+        return_sampled_latent = True
+
+    class curriculum:
+        min_level = 15
+        max_level = 50
+        check_after_log_instances = 2048
+        increase_step = 2
+        decrease_step = 1
+        success_rate_for_increase = 0.7
+        success_rate_for_decrease = 0.6
+
+    @staticmethod
+    def action_transformation_function(action):
+        """3-D policy action -> [vx, 0, vz, yaw_rate] (navigation_task_config.py:87-117)."""
+        import math
+
+        import torch
+
+        clamped = torch.clamp(action, -1.0, 1.0)
+        max_speed, max_yawrate, max_incl = 2.0, math.pi / 3, math.pi / 4
+        clamped[:, 0] += 1.0
+        out = torch.zeros((clamped.shape[0], 4), device=action.device)
+        out[:, 0] = clamped[:, 0] * torch.cos(max_incl * clamped[:, 1]) * max_speed / 2.0
+        out[:, 2] = clamped[:, 0] * torch.sin(max_incl * clamped[:, 1]) * max_speed / 2.0
+        out[:, 3] = clamped[:, 2] * max_yawrate
+        return out

@@ -39,6 +39,8 @@ uint64_t agx_sizeof(int which) {
         case 0: return sizeof(AgxHp1Config);
         case 1: return sizeof(AgxHp1Buffers);
         case 2: return sizeof(AgxHp1ResetDraws);
+        case 5: return sizeof(AgxNavRewardParams);
+        case 6: return sizeof(AgxImuConfig);
 #ifdef AGX_HAVE_HP2
         case 3: return sizeof(AgxHp2Scene);
         case 4: return sizeof(AgxHp2Sensor);

@@ -80,7 +80,8 @@ class EnvManager:
             spec, N, dev, physics_steps=1, seed=int(self.env_args.get("seed", 0)),
             env_id_offset=int(self.env_args.get("env_id_offset", 0)), device_rng_reset=(self.reset_rng == "device"),
             strict_stale_obs=bool(self.env_args.get("strict_stale_obs", True)), materialize_derived=True,
-            per_env_params=self.env_args.get("per_env_params", "auto"), host_io=bool(self.env_args.get("host_io", False)))
+            per_env_params=self.env_args.get("per_env_params", "auto"), host_io=bool(self.env_args.get("host_io", False)),
+            debug_wrench=bool(getattr(self.robot_cfg.sensor_config, "enable_imu", False)))  # the IMU reads the net body force
         eng, gtd = self.engine, self.global_tensor_dict
         gtd["crashes"], gtd["truncations"] = eng.terminations, eng.truncations
         self.collision_tensor, self.truncation_tensor = eng.terminations, eng.truncations
@@ -224,6 +225,12 @@ class EnvManager:
         gtd, N, dev = self.global_tensor_dict, self.num_envs, self.device
         sc = self.robot_cfg.sensor_config
         self.sensor, self.sensor_cfg = None, None
+        self.imu = None
+        if getattr(sc, "enable_imu", False):  # robot_manager.py:91-96, 246-262
+            from ..sensors import IMUSensor
+            gtd["force_sensor_tensor"] = self.engine.body_wrench  # [N,6] net base-frame wrench of the last physics step
+            self.imu = IMUSensor(sc.imu_config, N, dev)
+            self.imu.init_tensors(gtd)
         if not self.use_warp:
             return
         if sc.enable_camera and sc.enable_lidar:
@@ -308,6 +315,8 @@ class EnvManager:
             t0, t1, e0, e1 = self._mount_rng
             self.sensor_mount[env_ids, :, 0:3] = _lerp(t0, t1, torch.rand(k, S, 3, device=dev))
             self.sensor_mount[env_ids, :, 3:7] = _quat_from_euler(_lerp(e0, e1, torch.rand(k, S, 3, device=dev)))
+        if self.imu is not None:
+            self.imu.reset_idx(env_ids)
         eng.refresh()  # update_states of ALL envs (base_multirotor.py:204-205); sim_steps zeroed by the kernel
 
     def _sample_assets_and_update_scene(self, env_ids, mask, A):
@@ -391,6 +400,8 @@ class EnvManager:
             self.render_sensors()
 
     def render_sensors(self):
+        if self.imu is not None:
+            self.imu.update()
         if self.sensor is None:
             return
         self.sensor.capture()

@@ -160,7 +160,8 @@ typedef struct AgxHp1ResetDraws {
 int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
- * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor */
+ * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor,
+ * 5 AgxNavRewardParams, 6 AgxImuConfig */
 uint64_t agx_sizeof(int which);
 
 /* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
@@ -203,6 +204,52 @@ int agx_hp1_reset(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, const uint8
  * plus the position-task observation when buf->obs != NULL.  only_if_flag != 0: the pass is a
  * no-op unless buf->any_reset[0] != 0 (and it clears the flag). */
 int agx_hp1_refresh(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, int only_if_flag, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * NavigationTask epilogue and IMU (small per-env kernels; the
+ * random draws are inputs, drawn by the host with torch in the reference's call order)
+ * -------------------------------------------------------------------------------------- */
+/* reward_parameters of config/task_config/navigation_task_config.py:30-49, in that order:
+ * pos_reward_{magnitude,exponent}, very_close_to_goal_reward_{magnitude,exponent},
+ * getting_closer_reward_multiplier, {x,z,yawrate}_action_diff_penalty_{magnitude,exponent},
+ * {x,z,yawrate}_absolute_action_penalty_{magnitude,exponent}, collision_penalty */
+typedef struct AgxNavRewardParams {
+    float v[18];
+} AgxNavRewardParams;
+
+/* NavigationTask.compute_rewards_and_crashes + compute_reward
+ * (task/navigation_task/navigation_task.py:397-418, 436-521).
+ *   robot_state [N,stride] (position in columns 0..2), vehicle_orientation [N,4], target_position [N,3],
+ *   crashes [N] bool, actions / prev_actions [N,4] (obs_dict robot_actions / robot_prev_actions);
+ *   pos_error [N,3]: in = last step's vehicle-frame position error, out = this step's;
+ *   pos_error_prev [N,3] out = the value pos_error held on entry; rewards [N] out. */
+int agx_nav_reward(int num_envs, const float* robot_state, int robot_state_stride, const float* vehicle_orientation,
+                   const float* target_position, const uint8_t* crashes, const float* actions, const float* prev_actions,
+                   float curriculum_progress_fraction, const AgxNavRewardParams* params, float* pos_error, float* pos_error_prev,
+                   float* rewards, void* stream);
+
+/* NavigationTask.process_obs_for_task (navigation_task.py:369-395), observation columns 0..16 of obs
+ * [N,obs_stride]; columns 17.. (the VAE latents) are not touched.  u_vec, u_euler [N,3]: the two
+ * torch.rand_like draws of :374 and :382, in that order. */
+int agx_nav_obs(int num_envs, const float* robot_state, int robot_state_stride, const float* vehicle_orientation, const float* euler,
+                const float* body_linvel, const float* body_angvel, const float* robot_actions, const float* target_position,
+                const float* u_vec, const float* u_euler, float* obs, int obs_stride, void* stream);
+
+typedef struct AgxImuConfig {
+    int32_t world_frame;     /* BaseImuConfig.world_frame */
+    int32_t enable_noise, enable_bias;
+    float sqrt_dt;           /* sqrt(sim dt), base_sensor.py:23 */
+    float g_world[3];        /* gravity * (1 - gravity_compensation), imu_sensor.py:61-63 */
+    float bias_std[6], noise_std[6], max_meas[6]; /* base_imu_config.py:16-43 */
+} AgxImuConfig;
+
+/* IMUSensor.update (sensors/imu_sensor.py:85-131).  force [N,force_stride]: the IMU link's force-sensor
+ * reading (columns 0..2), robot_state [N,stride] (orientation in columns 3..6), body_angvel [N,3],
+ * sensor_quats [N,4]; n_noise, n_bias [N,6]: torch.randn draws of sample_noise (:74-77) and update_bias
+ * (:79-83), in that order; bias [N,6] in/out (random walk); imu_meas [N,6] out (accel, gyro). */
+int agx_imu_update(int num_envs, const AgxImuConfig* cfg, const float* force, int force_stride, const float* mass,
+                   const float* robot_state, int robot_state_stride, const float* body_angvel, const float* sensor_quats,
+                   const float* n_noise, const float* n_bias, float* bias, float* imu_meas, void* stream);
 
 
 /* ======================================================================================
