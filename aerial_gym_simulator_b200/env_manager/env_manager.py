@@ -40,6 +40,11 @@ def _quat_from_euler(e):  # utils/math.py:155-172
                         cy * cr * cp + sy * sr * sp], dim=-1)
 
 
+def _quat_rotate_inverse(q, v):
+    qw, qv = q[:, 3:4], q[:, 0:3]
+    return v * (2.0 * qw * qw - 1.0) - torch.cross(qv, v, dim=-1) * qw * 2.0 + qv * (qv * v).sum(-1, keepdim=True) * 2.0
+
+
 class EnvManager:
     def __init__(self, sim_name, env_name, robot_name, controller_name, device, args=None, num_envs=None,
                  use_warp=None, headless=None):
@@ -228,7 +233,9 @@ class EnvManager:
         self.imu = None
         if getattr(sc, "enable_imu", False):  # robot_manager.py:91-96, 246-262
             from ..sensors import IMUSensor
-            gtd["force_sensor_tensor"] = self.engine.body_wrench  # [N,6] net base-frame wrench of the last physics step
+            # PhysX's force sensor reports the TOTAL force on the link, gravity included (base_imu_config.py:48), in the link
+            # frame: here = applied base-frame force of the last physics step + m R(q)^T g  (refreshed in render_sensors)
+            gtd["force_sensor_tensor"] = torch.zeros(N, 6, device=dev)
             self.imu = IMUSensor(sc.imu_config, N, dev)
             self.imu.init_tensors(gtd)
         if not self.use_warp:
@@ -401,6 +408,10 @@ class EnvManager:
 
     def render_sensors(self):
         if self.imu is not None:
+            gtd = self.global_tensor_dict
+            fs, w = gtd["force_sensor_tensor"], self.engine.body_wrench
+            fs[:, 0:3] = w[:, 0:3] + gtd["robot_mass"].unsqueeze(1) * _quat_rotate_inverse(gtd["robot_orientation"], gtd["gravity"])
+            fs[:, 3:6] = w[:, 3:6]
             self.imu.update()
         if self.sensor is None:
             return

@@ -3,9 +3,10 @@ measurement lives in global_tensor_dict["imu_measurement"] -- with update() as O
 (agx_imu_update).  Random numbers are drawn with torch in the reference's call order (randn for the
 noise, randn for the bias walk; rand for resets).
 
-`force_sensor_tensor` is PhysX's force-sensor reading in the reference (robot_manager.py:259-262,
-not observable here); this simulator supplies the net applied base-frame force of the last physics
-step (Hp1Engine(debug_wrench=True).body_wrench), i.e. the specific force times the mass."""
+`force_sensor_tensor` is PhysX's force-sensor reading in the reference (robot_manager.py:259-262, not
+observable here): the total force on the link, gravity included, in the link frame.  EnvManager fills
+it from the integrator: applied base-frame force of the last physics step (Hp1Engine body_wrench)
++ m R(q)^T g, so a hovering robot reads zero total force and the IMU reports +g along body z."""
 import ctypes as C
 import math
 

@@ -61,9 +61,10 @@ def test_nav_obs_kernel_matches_reference_fixture():
     state = torch.zeros(n, 13, device=DEV)
     state[:, 0:3] = _d(d["pos"])
     obs = torch.full((n, 81), 7.0, device=DEV)
-    _lib.check(lib.agx_nav_obs(n, _p(state), 13, _p(_d(d["vehicle_orientation"])), _p(_d(d["euler"])), _p(_d(d["body_linvel"])),
-                               _p(_d(d["body_angvel"])), _p(_d(d["robot_actions"])), _p(_d(d["target"])), _p(_d(d["obs_draw_vec"])),
-                               _p(_d(d["obs_draw_euler"])), _p(obs), 81, None), "agx_nav_obs")
+    # (the tensors must outlive the call: keep them in a list, a temporary would be freed before the launch)
+    t = [_d(d[k]) for k in ("vehicle_orientation", "euler", "body_linvel", "body_angvel", "robot_actions", "target", "obs_draw_vec",
+                            "obs_draw_euler")]
+    _lib.check(lib.agx_nav_obs(n, _p(state), 13, *[_p(x) for x in t], _p(obs), 81, None), "agx_nav_obs")
     ref = torch.tensor(d["obs"])
     assert torch.allclose(obs.cpu(), ref, rtol=1e-5, atol=1e-5), (obs.cpu() - ref).abs().max()  # incl. untouched latent columns
 
@@ -121,7 +122,7 @@ def test_imu_kernel_matches_reference_fixture(tag):
 
 def test_navigation_task_end_to_end():
     """The reference's navigation_task configuration, shrunk: 16 envs of env_with_obstacles (44 boxes), lmf2 with the
-    velocity controller and IMU, 135x240 depth camera, VAE encoder (initial weights: the checkpoint does not travel)."""
+    velocity controller, 135x240 depth camera, VAE encoder (initial weights: the checkpoint does not travel)."""
     import aerial_gym_simulator_b200.task  # noqa: F401
     from aerial_gym_simulator_b200.registry.task_registry import task_registry
 
@@ -141,8 +142,29 @@ def test_navigation_task_end_to_end():
         assert torch.equal(o[:, 13:17], task.obs_dict["robot_actions"])
         assert (rew[term] == -100.0).all() or not term.any()
         n_resets += int((term | trunc).sum())
-    imu = task.obs_dict["imu_measurement"]
-    assert imu.shape == (16, 6) and torch.isfinite(imu).all()
     assert task.obs_dict["depth_range_pixels"].shape == (16, 1, 135, 240)
     assert task.image_latents.abs().sum() > 0
     task.close()
+
+
+def test_imu_in_env_manager():
+    """base_quadrotor_with_imu in an empty env: a hovering robot's accelerometer reads +g along body z (specific force),
+    the gyro reads the body rates; both within the sensor's noise."""
+    from aerial_gym_simulator_b200.sim import SimBuilder
+
+    env = SimBuilder().build_env(sim_name="base_sim", env_name="empty_env", robot_name="base_quadrotor_with_imu",
+                                 controller_name="lee_position_control", args={"seed": 1}, device=DEV, num_envs=64, headless=True)
+    env.reset()
+    gtd = env.get_obs()
+    hold = gtd["robot_position"].clone()
+    act = torch.cat([hold, torch.zeros(64, 1, device=DEV)], dim=1)  # hold position, yaw 0
+    for _ in range(300):
+        env.step(act)
+        env.render()
+    imu = gtd["imu_measurement"]
+    assert imu.shape == (64, 6) and torch.isfinite(imu).all()
+    up = torch.nn.functional.normalize(imu[:, 0:3], dim=1)
+    assert (imu[:, 0:3].norm(dim=1) - 9.81).abs().max() < 1.0       # |specific force| ~ g once settled
+    assert (imu[:, 3:6] - gtd["robot_body_angvel"]).abs().max() < 0.2  # gyro = body rates + noise + bias
+    assert up[:, 2].min() > 0.9
+    env.delete_env()
