@@ -22,7 +22,10 @@ def _module(name, **attrs):
 def install():
     if getattr(sys.modules.get("aerial_gym"), "_b200_compat", False):
         return
-    from . import config, control, env_manager, registry, robots, sim, task, utils
+    from . import config, control, env_manager, registry, robots, sensors, sim, task, utils
+    from .sensors import imu_sensor
+    from .task import navigation_task, position_setpoint_task
+    from .utils import vae_encoder
     from .config import (PACKAGE_DIRECTORY, asset_config, controller_config, env_config, robot_config, sensor_config,
                          sim_config, task_config)
     import importlib
@@ -48,6 +51,14 @@ def install():
         "utils.logging": logging, "utils.math": math, "config": config, "config.sim_config": sim_config,
         "config.env_config": env_config, "config.robot_config": robot_config, "config.controller_config": controller_config,
         "config.sensor_config": sensor_config, "config.asset_config": asset_config, "config.task_config": task_config,
+        "sensors": sensors, "sensors.imu_sensor": imu_sensor,
+        "task.navigation_task": _module("aerial_gym.task.navigation_task", navigation_task=navigation_task, __path__=[]),
+        "task.navigation_task.navigation_task": navigation_task,
+        "task.position_setpoint_task": _module("aerial_gym.task.position_setpoint_task", position_setpoint_task=position_setpoint_task,
+                                               __path__=[]),
+        "task.position_setpoint_task.position_setpoint_task": position_setpoint_task,
+        "utils.vae": _module("aerial_gym.utils.vae", vae_image_encoder=vae_encoder, __path__=[]),
+        "utils.vae.vae_image_encoder": vae_encoder,
     }
     for name, mod in table.items():
         sys.modules["aerial_gym." + name] = mod
@@ -55,6 +66,8 @@ def install():
             setattr(pkg, name, mod)
     # reference-style deep config paths
     deep = {
+        "config.task_config.navigation_task_config": _module(
+            "aerial_gym.config.task_config.navigation_task_config", task_config=task_config.navigation_task_config),
         "config.task_config.position_setpoint_task_config": _module(
             "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
         "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),

@@ -101,3 +101,30 @@ def test_compat_import_paths_of_the_reference():
     assert gymutil.parse_device_str("cuda:3") == ("cuda", 3)
     assert task_config.controller_name == "lee_attitude_control" and task_config.episode_len_steps == 500
     CustomLogger("t").setLoggerLevel("INFO")
+    # SURVEY 8(f) rows built in round 1: navigation task, IMU, VAE encoder wrapper
+    from aerial_gym.config.task_config.navigation_task_config import task_config as nav_cfg
+    from aerial_gym.sensors.imu_sensor import IMUSensor  # noqa: F401
+    from aerial_gym.task.navigation_task.navigation_task import NavigationTask  # noqa: F401
+    from aerial_gym.utils.vae.vae_image_encoder import VAEImageEncoder  # noqa: F401
+
+    assert tr.get_task_config("navigation_task") is nav_cfg and nav_cfg.robot_name == "lmf2"
+
+
+def test_navigation_task_config_matches_reference_values():
+    """Reward parameters / curriculum / action transform of config/task_config/navigation_task_config.py."""
+    import math
+
+    import torch
+
+    from aerial_gym_simulator_b200.config.task_config import navigation_task_config as C
+
+    assert C.observation_space_dim == 81 and C.episode_len_steps == 100 and C.env_name == "env_with_obstacles"
+    assert C.reward_parameters["collision_penalty"] == -100.0 and C.reward_parameters["pos_reward_exponent"] == 1.0 / 3.5
+    assert (C.curriculum.min_level, C.curriculum.max_level, C.curriculum.check_after_log_instances) == (15, 50, 2048)
+    a = torch.tensor([[1.0, 0.5, -1.0, 0.3], [-1.0, 0.0, 0.5, 0.0], [3.0, -2.0, 2.0, 0.0]])
+    out = C.action_transformation_function(a.clone())
+    c = torch.clamp(a, -1, 1)
+    want_x = (c[:, 0] + 1) * torch.cos(math.pi / 4 * c[:, 1]) * 2.0 / 2.0
+    want_z = (c[:, 0] + 1) * torch.sin(math.pi / 4 * c[:, 1]) * 2.0 / 2.0
+    assert torch.allclose(out[:, 0], want_x) and torch.allclose(out[:, 2], want_z)
+    assert torch.allclose(out[:, 3], c[:, 2] * math.pi / 3) and (out[:, 1] == 0).all()
