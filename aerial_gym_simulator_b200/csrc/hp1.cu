@@ -43,6 +43,14 @@ struct Gains {
     V3 kp, kv, kr, kw;
 };
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -63,11 +71,11 @@ __device__ __forceinline__ void load_rows13(const float* __restrict__ base, int 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int idx = lane + 32 * i;
-            if (idx < kTileFloats / 4) t4[idx] = s4[idx];
+            if (idx < kTileFloats / 4) t4[idx] = __ldcg(s4 + idx);  // L2 (see "chained steps": never a stale L1 line)
         }
     } else {
         int n = n_valid * 13;
-        for (int i = lane; i < n; i += 32) tile[i] = src[i];
+        for (int i = lane; i < n; i += 32) tile[i] = __ldcg(src + i);
     }
     __syncwarp();
     if (lane < n_valid) {
@@ -104,12 +112,12 @@ __device__ __forceinline__ void load_m(const float* __restrict__ p, int env, flo
         const float4* p4 = reinterpret_cast<const float4*>(p + (size_t)env * M);
 #pragma unroll
         for (int i = 0; i < M / 4; ++i) {
-            float4 v = p4[i];
+            float4 v = __ldcg(p4 + i);
             out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < M; ++i) out[i] = p[(size_t)env * M + i];
+        for (int i = 0; i < M; ++i) out[i] = __ldcg(p + (size_t)env * M + i);
     }
 }
 template <int M>
@@ -127,6 +135,7 @@ __device__ __forceinline__ void st3(float* p, int env, V3 v) {
     p[(size_t)env * 3 + 0] = v.x; p[(size_t)env * 3 + 1] = v.y; p[(size_t)env * 3 + 2] = v.z;
 }
 __device__ __forceinline__ V3 ld3c(const float* c) { return V3{c[0], c[1], c[2]}; }
+__device__ __forceinline__ V3 ld3cg(const float* p) { return V3{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)}; }
 
 __device__ __forceinline__ EnvState unpack(const float r[13]) {
     EnvState s;
@@ -469,10 +478,10 @@ __device__ __forceinline__ void load_params(const AgxHp1Config& cfg, const AgxHp
 #pragma unroll
         for (int i = 0; i < M; ++i) p.k[i] = cfg.k_thrust;
     }
-    p.g.kp = buf.K_pos ? ld3(buf.K_pos + (size_t)env * 3) : ld3c(cfg.K_pos);
-    p.g.kv = buf.K_vel ? ld3(buf.K_vel + (size_t)env * 3) : ld3c(cfg.K_vel);
-    p.g.kr = buf.K_rot ? ld3(buf.K_rot + (size_t)env * 3) : ld3c(cfg.K_rot);
-    p.g.kw = buf.K_angvel ? ld3(buf.K_angvel + (size_t)env * 3) : ld3c(cfg.K_angvel);
+    p.g.kp = buf.K_pos ? ld3cg(buf.K_pos + (size_t)env * 3) : ld3c(cfg.K_pos);
+    p.g.kv = buf.K_vel ? ld3cg(buf.K_vel + (size_t)env * 3) : ld3c(cfg.K_vel);
+    p.g.kr = buf.K_rot ? ld3cg(buf.K_rot + (size_t)env * 3) : ld3c(cfg.K_rot);
+    p.g.kw = buf.K_angvel ? ld3cg(buf.K_angvel + (size_t)env * 3) : ld3c(cfg.K_angvel);
 }
 template <int M>
 __device__ __forceinline__ void store_reset_params(const AgxHp1Buffers& buf, int env, const EnvParams<M>& p) {
@@ -506,20 +515,32 @@ __device__ __forceinline__ void make_obs(const EnvState& s, const Derived& d, V3
 // main kernel
 // =========================================================================================
 // 8 CTAs/SM -> <= 128 registers: all 1024 CTAs of the 65,536-env launch are resident in one wave
-// COOP (grid <= one resident wave, so all CTAs are co-resident; one tile per warp): the stale-observation
-// quirk ("a reset anywhere refreshes everybody", base_multirotor.py:204-205) is resolved inside the kernel
-// with a one-sided grid barrier instead of a second launch:
+// COOP (grid <= one resident wave, so all CTAs are co-resident; one tile per warp).
+//
+// (1) The stale-observation quirk ("a reset anywhere refreshes everybody", base_multirotor.py:204-205) is
+// resolved inside the kernel with a one-sided grid barrier instead of a second launch:
 //   * a warp that sees at its START that one of its envs truncates this step (sim_steps + 1 > episode
 //     length) raises the step's flag right away; crashes raise it in the epilogue;
 //   * every warp reads the flag when its physics is done (the load overlaps the epilogue).  Flag up
 //     (monotonic) -> everybody is refreshed: no waiting, no synchronisation at all.  With staggered
 //     episodes some env truncates every step, so this is the steady state;
-//   * flag still down: the warp counts itself in (fire-and-forget RED on a cumulative 64-bit counter)
-//     and waits until the flag rises OR all warps of the step have arrived (= nobody reset);
+//   * flag still down: the warp counts itself in and waits until the flag rises OR all warps of the step
+//     have arrived (= nobody reset);
 //   * the observation (and the derived arrays) are written once, after the decision.
-// any_reset[2..3]: 64-bit cumulative arrival counter -- the step index is counter / n_tiles, read at
-// kernel start (device-side, so launches stay graph-safe; the buffer must always be used with the same
-// num_envs); any_reset[4],[5]: flags of even / odd steps, the next step's flag is cleared by CTA 0.
+//
+// (2) Chained steps.  Env i's step T+1 depends on env i's step T only, so consecutive step launches are
+// chained per TILE, not per grid: launched with programmatic stream serialization, a step's CTAs are
+// scheduled while the previous step's slower warps are still running, each warp takes its step number T
+// from a per-tile claim counter (atomicAdd, before the CTA triggers its dependents, so claims are in launch
+// order), spins until its tile's done-counter says step T-1 has been published (st.release after the last
+// store / ld.acquire before the first L2-only load), and runs.  The launch's tail (slow SMs, the ~6 % of
+// warps with a resetting env) no longer gates the next step.  A warp also waits until step T-2 is complete
+// everywhere, so at most two consecutive steps are in flight and four parity slots suffice:
+//   any_reset[4 + (T & 3)]        u32 flag of step T: raised = holds T + 1 (monotonic, never cleared)
+//   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared)
+//   tile_sync[tile], tile_sync[n_tiles + tile]   claim / done counters of the tile
+// With the fused all-gather attached the grid-wide order is kept (griddepcontrol.wait): its handshake
+// assumes one step at a time.
 #ifdef AGX_TIMELINE  // debug builds only (tools/dbg/timeline.py): per-warp start / end globaltimer stamps
 __device__ unsigned long long g_timeline[4][8192];
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -542,22 +563,42 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     const int n_tiles = (N + 31) >> 5;
     const int A = cfg.num_actions;
     AGX_TL(0);
+    uint32_t* reset_flag = reinterpret_cast<uint32_t*>(buf.any_reset);
+    unsigned long long* arrive_ctr = nullptr;
+    unsigned long long arrive_target = 0;  // arrivals once every warp of this step has counted itself in
+    uint32_t step_T = 0;
     if constexpr (COOP) {
-        // programmatic dependent launch: the NEXT step's CTAs may be scheduled as soon as all of this grid's
-        // CTAs have started (they are all resident), and park at their own griddepcontrol.wait until this
-        // grid has completed and flushed -- the launch latency of step t+1 hides under the tail of step t
-        asm volatile("griddepcontrol.launch_dependents;");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int my_tile = blockIdx.x * kWarpsPerBlock + warp;
+        const bool has_tile = my_tile < n_tiles;
+        if (has_tile && lane == 0) step_T = atomicAdd(buf.tile_sync + my_tile, 1u);  // claim: which step of this tile am I?
+        step_T = __shfl_sync(0xffffffffu, step_T, 0);
+        __syncthreads();  // both warps hold their claim before the CTA lets the next launch in
+        // programmatic dependent launch: once every CTA of this grid is here, the NEXT step's CTAs may be scheduled
+        asm volatile("griddepcontrol.launch_dependents;" ::"r"(step_T) : "memory");
+        if (buf.gather_bufs) asm volatile("griddepcontrol.wait;" ::: "memory");  // fused gather: one step at a time
+        if (has_tile) {
+            if (lane == 0) {
+                const uint32_t* done = buf.tile_sync + n_tiles + my_tile;
+                unsigned long long spins = 0;
+                while (ld_acquire_gpu_u32(done) != step_T)  // this tile's previous step has published its state
+                    if (++spins > (1ull << 22)) __trap();
+                if (step_T >= 2u) {  // step T-2 complete everywhere: bounds the skew to two steps in flight
+                    const uint32_t P = step_T - 2u;
+                    const volatile unsigned long long* a2 = reinterpret_cast<const volatile unsigned long long*>(buf.any_reset + 8) + (P & 3u);
+                    const unsigned long long want = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
+                    spins = 0;
+                    while (*a2 < want)
+                        if (++spins > (1ull << 22)) __trap();
+                    __threadfence();
+                }
+            }
+            __syncwarp();
+        }
+        reset_flag = reinterpret_cast<uint32_t*>(buf.any_reset) + 4 + (step_T & 3u);
+        arrive_ctr = reinterpret_cast<unsigned long long*>(buf.any_reset + 8) + (step_T & 3u);
+        arrive_target = (unsigned long long)(step_T / 4u + 1u) * (unsigned long long)n_tiles;
     }
-    int* reset_flag = buf.any_reset;
-    unsigned long long coop_target = 0;  // counter value once every warp of this step has arrived
-    if constexpr (COOP) {
-        const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(buf.any_reset + 2);
-        const unsigned long long step_idx = cnt / (unsigned long long)n_tiles;
-        coop_target = (step_idx + 1ull) * (unsigned long long)n_tiles;
-        reset_flag = buf.any_reset + 4 + (int)(step_idx & 1ull);
-        if (blockIdx.x == 0 && threadIdx.x == 0) buf.any_reset[4 + (int)((step_idx + 1ull) & 1ull)] = 0;  // last used two steps ago
-    }
+    const uint32_t flag_tag = step_T + 1u;
     bool warp_raised = false;
     EnvState s;
     Derived d;
@@ -580,17 +621,17 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         if (valid) {
             load_params<M>(cfg, buf, env, p);
             if constexpr (TASK) {
-                steps_in = buf.sim_steps[env];
-                if (buf.target_position) tgt = ld3(buf.target_position + (size_t)env * 3);
+                steps_in = __ldcg(buf.sim_steps + env);
+                if (buf.target_position) tgt = ld3cg(buf.target_position + (size_t)env * 3);
             }
             if (A == 4) {
-                float4 a4 = reinterpret_cast<const float4*>(buf.actions)[env];
+                float4 a4 = __ldcg(reinterpret_cast<const float4*>(buf.actions) + env);
                 act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
 #pragma unroll
                 for (int i = 4; i < AGX_MAX_MOTORS; ++i) act[i] = 0.0f;
             } else {
 #pragma unroll
-                for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = (i < A) ? buf.actions[(size_t)env * A + i] : 0.0f;
+                for (int i = 0; i < AGX_MAX_MOTORS; ++i) act[i] = (i < A) ? __ldcg(buf.actions + (size_t)env * A + i) : 0.0f;
             }
             // clip_actions, robots/base_multirotor.py:207-211
 #pragma unroll
@@ -602,7 +643,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             const bool trunc_early = valid && (steps_in + 1 > cfg.episode_len_steps);
             if (__ballot_sync(0xffffffffu, trunc_early)) {
                 warp_raised = true;
-                if (lane == 0) atomicOr(reset_flag, 1);
+                if (lane == 0) atomicMax(reset_flag, flag_tag);
             }
         }
         if (valid) {
@@ -648,8 +689,8 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 V3 dtq = neg(ld3c(cfg.drag_ang1) * d.wb) + neg(ld3c(cfg.drag_ang2) * wabs * d.wb);
                 if (buf.disturbance) {  // apply_disturbance :213-234 (draws stay in torch)
                     const float* dp = buf.disturbance + (size_t)env * 6;
-                    df = df + V3{dp[0], dp[1], dp[2]};
-                    dtq = dtq + V3{dp[3], dp[4], dp[5]};
+                    df = df + ld3cg(dp);
+                    dtq = dtq + ld3cg(dp + 3);
                 }
                 V3 com = ld3c(cfg.com);
                 V3 F{w6[0] + df.x, w6[1] + df.y, w6[2] + df.z};
@@ -663,7 +704,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         AGX_TL(1);
         bool do_reset = false;
         int flag_pre = 0;
-        if constexpr (COOP) flag_pre = *reinterpret_cast<volatile int*>(reset_flag);  // consumed after the epilogue
+        if constexpr (COOP) flag_pre = (*reinterpret_cast<volatile uint32_t*>(reset_flag) == flag_tag);  // consumed after the epilogue
         if constexpr (TASK) {
             int steps = steps_in + 1;  // env_manager.py:429
             if (valid) {
@@ -692,7 +733,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
             const bool rng_reset = do_reset && (cfg.flags & AGX_F_DEVICE_RNG_RESET);
             const unsigned rmask = __ballot_sync(0xffffffffu, rng_reset);
             if (rmask) {
-                const uint32_t my_ep = rng_reset ? buf.episode_count[env] : 0u;
+                const uint32_t my_ep = rng_reset ? __ldcg(buf.episode_count + env) : 0u;
                 for (unsigned m = rmask; m; m &= m - 1) {
                     const int owner = __ffs(m) - 1;
                     const uint32_t ep = __shfl_sync(0xffffffffu, my_ep, owner);
@@ -722,31 +763,33 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                     }
                 }
                 unsigned any = __ballot_sync(0xffffffffu, do_reset);
-                if (any && lane == 0) atomicOr(reset_flag, 1);
+                if (any && lane == 0) atomicOr(buf.any_reset, 1);
             } else {
                 if (valid) buf.sim_steps[env] = steps;
                 if (__ballot_sync(0xffffffffu, do_reset)) {
                     flag_pre = 1;
-                    if (!warp_raised && lane == 0) atomicOr(reset_flag, 1);
+                    if (!warp_raised && lane == 0) atomicMax(reset_flag, flag_tag);
                     warp_raised = true;
                 }
                 // ---- the decision: is anybody in the whole grid resetting this step? ----------------
                 bool counted = false;
                 int any = flag_pre;
                 if (!any && __any_sync(0xffffffffu, valid && !fresh)) {  // rare: count ourselves in, then wait
-                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(buf.any_reset + 2), 1ull);
+                    if (lane == 0) atomicAdd(arrive_ctr, 1ull);
                     counted = true;
-                    volatile int* fl = reset_flag;
-                    volatile unsigned long long* cnt = reinterpret_cast<volatile unsigned long long*>(buf.any_reset + 2);
-                    any = *fl;
+                    volatile uint32_t* fl = reset_flag;
+                    volatile unsigned long long* cnt = arrive_ctr;
+                    any = (*fl == flag_tag);
+                    unsigned long long spins = 0;
                     while (!any) {
-                        if (*cnt >= coop_target) {  // every warp has arrived: the flag is final
+                        if (*cnt >= arrive_target) {  // every warp of this step has arrived: the flag is final
                             __threadfence();
-                            any = *fl;
+                            any = (*fl == flag_tag);
                             break;
                         }
+                        if (++spins > (1ull << 22)) __trap();
                         __nanosleep(40);
-                        any = *fl;
+                        any = (*fl == flag_tag);
                     }
                 }
                 // ---- derived states for the observation: one common pass for resetting envs (new state)
@@ -790,9 +833,11 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                         }
                     }
                 }
-                if (!counted && lane == 0) {
-                    if (warp_raised) __threadfence();  // the flag must be visible before this arrival is
-                    atomicAdd(reinterpret_cast<unsigned long long*>(buf.any_reset + 2), 1ull);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
+                    if (!counted) atomicAdd(arrive_ctr, 1ull);
+                    st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
                 }
             }
         }
@@ -1047,7 +1092,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
     const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
     const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
-    if (strict_fused && !ev_after_main && coop_capacity(cfg->num_motors) >= g) {
+    if (strict_fused && !ev_after_main && buf->tile_sync && coop_capacity(cfg->num_motors) >= g) {
         // single launch: the whole grid is resident at once (g <= occupancy x SMs), so the in-kernel
         // one-sided barrier cannot starve -- no cooperative-launch API needed for that
         cudaLaunchConfig_t lc = {};

@@ -227,7 +227,8 @@ class Hp1Engine:
             self.terminations = z(N, dt=torch.bool)
             self.truncations = z(N, dt=torch.bool)
         self.reset_mask = z(N, dt=torch.bool)
-        self.any_reset = z(8, dt=torch.int32)
+        self.any_reset = z(16, dt=torch.int32)
+        self.tile_sync = z(2 * ((N + 31) // 32), dt=torch.int32)  # per-tile claim / done counters (chained steps)
         self.episode_count = z(N, dt=torch.int32)
         self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
         self.bounds_max = torch.tensor(spec.bounds_upper_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()

@@ -16,7 +16,10 @@ CUDA-event pair on the launching stream.  One 65,536-env working set (~12 MB) is
 126 MB L2, so the timed loop rotates over R = 16 independent replicas of the environment batch
 (~190 MB of state in total, larger than L2): every step finds its state cold in L2, nothing is
 flushed and no step is skipped.  value = N_gpus * envs * K / elapsed, max over ranks.
-`value_hot_l2` is the same loop on a single replica (state resident in L2, what an RL loop sees).
+`value_hot_l2` is the same loop on a single replica (state resident in L2; every tile's step waits for
+that tile's previous step -- the dependent-chain figure, what a policy-free rollout of ONE batch sees).
+Step launches are chained per 32-env tile, not per grid (hp1.cu "chained steps"), so in the rotating
+loop the tail of one replica's step overlaps the next replica's step.
 
 Reference arm (`--impl reference`): the reference's Isaac Gym sim_device=cpu pipeline cannot run
 here or on the GPU box (isaacgym is a closed binary, not installed; /root/reference does not
@@ -50,7 +53,9 @@ def workload_config(n_gpus, extra=None):
         "episode_len_steps": 500,
         "actions": "U(-1,1) resampled from 8 pre-generated batches",
         "parallelism": f"env-sharded x{n_gpus}" + (" + all-gather(obs) every step" if n_gpus > 1 else ""),
-        "l2": "inputs larger than L2: timed loop rotates over 16 replicas of the env batch (~190 MB)",
+        "l2": "inputs larger than L2: timed loop rotates over 16 replicas of the env batch (~190 MB); consecutive step "
+              "launches are chained per 32-env tile (programmatic dependent launch), so steps of different replicas overlap "
+              "in flight; value_hot_l2 = one replica stepped back to back (every step waits for its own previous step)",
     }
     if extra:
         cfg.update(extra)

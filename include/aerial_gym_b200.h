@@ -122,13 +122,16 @@ typedef struct AgxHp1Buffers {
     uint8_t* terminations;    /* [N] bool ("crashes") */
     uint8_t* truncations;     /* [N] bool */
     uint8_t* reset_mask;      /* [N] bool, envs reset (or to be reset) this step; may be NULL */
-    int32_t* any_reset;       /* [8] device scratch, 16-byte aligned, zero-initialised by the caller once and then always used
-                                 with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path); [2..3] 64-bit
-                                 cumulative warp-arrival counter, [4],[5] even/odd-step flags (single-launch path) */
+    int32_t* any_reset;       /* [16] device scratch, 16-byte aligned, zero-initialised by the caller once and then always
+                                 used with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path);
+                                 [4..7] per-step flags, [8..15] four 64-bit arrival counters (single-launch path, hp1.cu) */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
                                  when the stale-observation quirk is on and no derived array is materialised; the
                                  conditional pass then only patches obs[:,7:13] instead of recomputing.  May be NULL. */
+    uint32_t* tile_sync;      /* [2][ceil(N/32)] device scratch, zero-initialised once: per-tile claim / done counters that
+                                 chain consecutive single-launch steps tile by tile (hp1.cu "chained steps").
+                                 NULL = the step always takes the two-launch path. */
     /* multi-GPU: fused observation all-gather (NULL / 0 = off).  When set, the fused task step also
      * stores every env's observation row into slot `gather_rank` of each rank's gathered buffer
      * [gather_world * N, 13] over NVLink peer memory, then runs agx_p2p_allgather's flag handshake

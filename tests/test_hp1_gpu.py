@@ -249,8 +249,11 @@ def test_stale_observation_quirk():
     assert int(eng.any_reset[0]) == 0 and int(eng.any_reset[1]) == 0  # flag consumed
     H.assert_close(eng.body_linvel, fresh["body_linvel"], "derived array refreshed as well")
     ar = eng.any_reset.cpu().tolist()
-    # single-launch path: 2 steps x 8 warps counted in; step 0's flag slot was cleared again, step 1's is up
-    assert ar[2] == 2 * (N // 32) and ar[3] == 0 and ar[4] == 0 and ar[5] == 1
+    # single-launch path: 8 warps counted in per step (64-bit counters of steps 0 and 1 at [8], [10]); step 0's flag
+    # never rose, step 1's holds its tag (T + 1 = 2); every tile claimed and published two steps
+    assert ar[8] == N // 32 and ar[10] == N // 32 and ar[4] == 0 and ar[5] == 2
+    ts = eng.tile_sync.cpu().tolist()
+    assert ts == [2] * (2 * (N // 32))
 
 
 def test_host_io_step_is_identical():
