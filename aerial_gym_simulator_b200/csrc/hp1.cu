@@ -815,6 +815,12 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 }
                 store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
                 store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
+                __syncwarp();  // (before the peer pushes below: this fence must not wait for NVLink stores)
+                if (lane == 0) {
+                    __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
+                    if (!counted) atomicAdd(arrive_ctr, 1ull);
+                    st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
+                }
                 if (buf.gather_bufs) {  // the rows are still in the tile: push them into every rank's gathered buffer
                     const bool vec = vec_ok && n_valid == 32 && (N & 3) == 0;
                     const size_t row0 = ((size_t)buf.gather_rank * N + env0) * 13;
@@ -832,12 +838,6 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                             for (int i = lane; i < n_valid * 13; i += 32) dst[i] = tile[i];
                         }
                     }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
-                    if (!counted) atomicAdd(arrive_ctr, 1ull);
-                    st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
                 }
             }
         }
