@@ -422,7 +422,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,
                          "kernel_ms_avg": main_avg_s * 1e3,
                          "kernel_ms_isolated_event_pair": main_iso_s * 1e3,
-                         "note": "at 65,536 envs the launch is ~14 MB: FP32-issue / latency bound, not HBM bound (DESIGN.md)"},
+                         "note": "at 65,536 envs the launch is ~14 MB: FP32 dependent-chain latency bound, not HBM bound (DESIGN.md). "
+                                 "kernel_ms_avg = timed region / K launches; launches are chained per tile and overlap in flight, one "
+                                 "launch alone spans ~11.5 us (tools/dbg/timeline.py) and 17-19 us when serialised by its own event pair / ncu"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "value_memcpy_variant": e2e_memcpy,
