@@ -280,7 +280,7 @@ def run_ours(args):
         for e in engines:
             e.attach_obs_gather(gather, lag=0)
 
-    # ---- dominant kernel alone: per-step event pairs.  At this size the fused step is ONE cooperative
+    # ---- dominant kernel alone: per-step event pairs.  At this size the fused step is ONE
     # launch (hp1_step_kernel<4,true,coop>), so the pair brackets exactly that kernel; on the
     # two-launch path the library would record the second event between main kernel and obs pass.
     Kk = min(K, 200)
