@@ -17,6 +17,7 @@ UNITS = [
     # 65,536 envs (profiles/hp1_step_r1.md: stall_no_instruction dominates), every instruction counts
     ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
     ("hp1_aux.cu", []),
+    ("lidar_nav.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

@@ -71,6 +71,10 @@ class AgxNavRewardParams(C.Structure):
     _fields_ = [("v", C.c_float * 18)]
 
 
+class AgxLidarNavRewardParams(C.Structure):
+    _fields_ = [("v", C.c_float * 22)]
+
+
 class AgxImuConfig(C.Structure):
     _fields_ = [("world_frame", C.c_int32), ("enable_noise", C.c_int32), ("enable_bias", C.c_int32), ("sqrt_dt", C.c_float),
                 ("g_world", C.c_float * 3), ("bias_std", C.c_float * 6), ("noise_std", C.c_float * 6), ("max_meas", C.c_float * 6)]
@@ -145,6 +149,10 @@ def load():
                            C.POINTER(AgxNavRewardParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "agx_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p],
         "agx_imu_update": [C.c_int, C.POINTER(AgxImuConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7,
+        "agx_lidar_nav_pool": [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 3,
+        "agx_lidar_nav_reward": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_float, C.POINTER(AgxLidarNavRewardParams)]
+                                + [C.c_void_p] * 4,
+        "agx_lidar_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p],
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
         "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -156,7 +164,8 @@ def load():
     lib.agx_hp2_scene_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     if lib.agx_sizeof(3) != C.sizeof(AgxHp2Scene) or lib.agx_sizeof(4) != C.sizeof(AgxHp2Sensor):
         raise AgxError("HP2 ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
-    if lib.agx_sizeof(5) != C.sizeof(AgxNavRewardParams) or lib.agx_sizeof(6) != C.sizeof(AgxImuConfig):
+    if lib.agx_sizeof(5) != C.sizeof(AgxNavRewardParams) or lib.agx_sizeof(6) != C.sizeof(AgxImuConfig) \
+            or lib.agx_sizeof(7) != C.sizeof(AgxLidarNavRewardParams):
         raise AgxError("aux ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
             or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):

@@ -24,7 +24,7 @@ def install():
         return
     from . import config, control, env_manager, registry, robots, sensors, sim, task, utils
     from .sensors import imu_sensor
-    from .task import navigation_task, position_setpoint_task
+    from .task import lidar_navigation_task, navigation_task, position_setpoint_task
     from .utils import vae_encoder
     from .config import (PACKAGE_DIRECTORY, asset_config, controller_config, env_config, robot_config, sensor_config,
                          sim_config, task_config)
@@ -54,6 +54,9 @@ def install():
         "sensors": sensors, "sensors.imu_sensor": imu_sensor,
         "task.navigation_task": _module("aerial_gym.task.navigation_task", navigation_task=navigation_task, __path__=[]),
         "task.navigation_task.navigation_task": navigation_task,
+        "task.lidar_navigation_task": _module("aerial_gym.task.lidar_navigation_task", lidar_navigation_task=lidar_navigation_task,
+                                              __path__=[]),
+        "task.lidar_navigation_task.lidar_navigation_task": lidar_navigation_task,
         "task.position_setpoint_task": _module("aerial_gym.task.position_setpoint_task", position_setpoint_task=position_setpoint_task,
                                                __path__=[]),
         "task.position_setpoint_task.position_setpoint_task": position_setpoint_task,
@@ -68,6 +71,15 @@ def install():
     deep = {
         "config.task_config.navigation_task_config": _module(
             "aerial_gym.config.task_config.navigation_task_config", task_config=task_config.navigation_task_config),
+        "config.task_config.lidar_navigation_task_config": _module(
+            "aerial_gym.config.task_config.lidar_navigation_task_config", task_config=task_config.lidar_navigation_task_config),
+        "config.env_config.env_with_lidar_nav_obstacles": _module(
+            "aerial_gym.config.env_config.env_with_lidar_nav_obstacles", EnvWithLidarNavObstaclesCfg=env_config.EnvWithLidarNavObstaclesCfg),
+        "config.sensor_config.lidar_config": _module("aerial_gym.config.sensor_config.lidar_config", __path__=[]),
+        "config.sensor_config.lidar_config.rslidar_airy_config": _module(
+            "aerial_gym.config.sensor_config.lidar_config.rslidar_airy_config", RSLidar_Airy_Config=sensor_config.RSLidar_Airy_Config),
+        "config.sensor_config.lidar_config.osdome_64_config": _module(
+            "aerial_gym.config.sensor_config.lidar_config.osdome_64_config", OSDome_64_Config=sensor_config.OSDome_64_Config),
         "config.task_config.position_setpoint_task_config": _module(
             "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
         "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),

@@ -65,11 +65,11 @@ class object_asset_params(asset_state_params):
     color = [80, 255, 100]
 
 
-def _wall(fname, ratio, sem):
+def _wall(fname, ratio, sem, keep_in_env=True):
     lo, hi = _ratio(ratio, ratio)
     return type(fname.replace(".urdf", ""), (asset_state_params,), dict(
         num_assets=1, asset_folder=f"{_ENV_ASSETS}/walls", file=fname, min_position_ratio=list(ratio),
-        max_position_ratio=list(ratio), min_state_ratio=lo, max_state_ratio=hi, keep_in_env=True,
+        max_position_ratio=list(ratio), min_state_ratio=lo, max_state_ratio=hi, keep_in_env=keep_in_env,
         semantic_id=sem, color=[100, 200, 210]))
 
 
@@ -79,3 +79,27 @@ top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_ID)
 bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID)
 front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID)
 back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID)
+
+
+# ---- config/asset_config/lidar_nav_env_config.py: the denser scene of env_with_lidar_nav_obstacles.  Same asset families;
+# 15 panels + 70 objects + 6 walls = 91 boxes, wider placement ratios, and NOTHING is kept in the env when the curriculum
+# level is below the asset's slot (keep_in_env = False everywhere, walls included: lidar_nav_env_config.py:115,355-592).
+class lidar_nav_panel_asset_params(panel_asset_params):
+    num_assets = 15
+    min_position_ratio, max_position_ratio = [0.1, 0.0, 0.0], [1.0, 1.0, 1.0]
+    min_state_ratio, max_state_ratio = _ratio((0.35, 0.0, 0.0), (1.0, 1.0, 1.0), (0, 0, -PI / 3.0), (0, 0, PI / 3.0))
+    keep_in_env = False
+
+
+class lidar_nav_object_asset_params(object_asset_params):
+    num_assets = 70
+    min_state_ratio, max_state_ratio = _ratio((0.30, 0.0, 0.0), (1.0, 1.0, 1.0), (-PI, -PI, -PI), (PI, PI, PI))
+    keep_in_env = False
+
+
+lidar_nav_left_wall = _wall("left_wall.urdf", (0.5, 1.0, 0.5), LEFT_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_right_wall = _wall("right_wall.urdf", (0.5, 0.0, 0.5), RIGHT_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID, keep_in_env=False)

@@ -1,4 +1,5 @@
-"""config/env_config/{empty_env,env_with_obstacles}.py"""
+"""config/env_config/{empty_env,env_with_obstacles,env_with_lidar_nav_obstacles}.py"""
+from . import asset_config as _ac
 from .asset_config import (back_wall, bottom_wall, front_wall, left_wall, object_asset_params, panel_asset_params,
                            right_wall, top_wall)
 
@@ -62,4 +63,21 @@ class EnvWithObstaclesCfg:
             "panels": panel_asset_params, "objects": object_asset_params,
             "left_wall": left_wall, "right_wall": right_wall, "back_wall": back_wall,
             "front_wall": front_wall, "bottom_wall": bottom_wall, "top_wall": top_wall,
+        }
+
+
+class EnvWithLidarNavObstaclesCfg(EnvWithObstaclesCfg):
+    """config/env_config/env_with_lidar_nav_obstacles.py: bigger bounds, the lidar_nav asset set."""
+    class env(EnvWithObstaclesCfg.env):
+        lower_bound_min = [-7.50, -7.50, -5.0]
+        lower_bound_max = [-5.0, -5.0, -3.0]
+        upper_bound_min = [5.0, 5.0, 3.0]
+        upper_bound_max = [7.5, 7.5, 5.0]
+
+    class env_config:
+        include_asset_type = dict(EnvWithObstaclesCfg.env_config.include_asset_type)
+        asset_type_to_dict_map = {
+            "panels": _ac.lidar_nav_panel_asset_params, "objects": _ac.lidar_nav_object_asset_params,
+            "left_wall": _ac.lidar_nav_left_wall, "right_wall": _ac.lidar_nav_right_wall, "back_wall": _ac.lidar_nav_back_wall,
+            "front_wall": _ac.lidar_nav_front_wall, "bottom_wall": _ac.lidar_nav_bottom_wall, "top_wall": _ac.lidar_nav_top_wall,
         }

@@ -4,7 +4,7 @@ Articulated robots (ROV, reconfigurable, Morphy) are out of the hot-path scope (
 import numpy as np
 
 from . import RESOURCES_DIRECTORY
-from .sensor_config import BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, OSDome_64_Config
+from .sensor_config import BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, OSDome_64_Config, RSLidar_Airy_Config
 
 PI = np.pi
 QUAD_ALLOCATION = [
@@ -228,6 +228,7 @@ class MagpieCfg(LMF2Cfg):
 
     class sensor_config(BaseQuadCfg.sensor_config):
         enable_lidar = True
+        lidar_config = RSLidar_Airy_Config  # magpie_config.py:52-53
 
     class robot_asset(BaseQuadCfg.robot_asset):
         asset_folder = f"{RESOURCES_DIRECTORY}/robots/magpie"

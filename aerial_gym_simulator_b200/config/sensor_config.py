@@ -84,6 +84,31 @@ class OSDome_64_Config(BaseLidarConfig):
         pixel_dropout_prob = 0.0
 
 
+class RSLidar_Airy_Config(BaseLidarConfig):
+    """config/sensor_config/lidar_config/rslidar_airy_config.py: 48 x 120 hemispherical LiDAR that returns a WORLD-frame
+    point cloud (what LiDARNavigationTask.process_image_observation consumes)."""
+    height, width = 48, 120
+    vertical_fov_deg_min, vertical_fov_deg_max = 0, 90
+    max_range, min_range = 10.0, 0.2
+    return_pointcloud = True
+    segmentation_camera = False
+    normalize_range = False
+    pointcloud_in_world_frame = True
+    randomize_placement = True  # a degenerate range: the mount is fixed, but the draws are still made
+    min_translation = [-0.05, 0.0, 0.0]
+    max_translation = [-0.05, 0.0, 0.0]
+    min_euler_rotation_deg = [0.0, -90.0, 0.0]
+    max_euler_rotation_deg = [0.0, -90.0, 0.0]
+
+    class sensor_noise:
+        enable_sensor_noise = False
+        std_a = 0.00038089
+        std_b = -0.00343351
+        std_c = 0.01553284
+        mean_offset = -0.025
+        pixel_dropout_prob = 0.0
+
+
 class DepthCamera64x48Config(BaseDepthCameraConfig):
     """BASELINE.json north-star sensor: 64x48 depth + segmentation."""
     height, width = 48, 64

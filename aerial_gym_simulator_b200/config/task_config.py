@@ -105,3 +105,82 @@ class navigation_task_config:
         out[:, 2] = clamped[:, 0] * torch.sin(max_incl * clamped[:, 1]) * max_speed / 2.0
         out[:, 3] = clamped[:, 2] * max_yawrate
         return out
+
+
+class lidar_navigation_task_config:
+    """config/task_config/lidar_navigation_task_config.py"""
+    seed = -1
+    sim_name = "base_sim"
+    env_name = "env_with_lidar_nav_obstacles"
+    robot_name = "magpie"
+    controller_name = "magpie_acceleration_control"
+    args = {}
+    num_envs = 512
+    use_warp = True
+    headless = False
+    device = "cuda:0"
+    observation_space_dim = 13 + 4 + 16 * 20  # root_state + action_dim + min-pooled 48x120 LiDAR image
+    privileged_observation_space_dim = 0
+    action_space_dim = 4
+    episode_len_steps = 110
+    return_state_before_reset = False
+    target_min_ratio = [0.90, 0.15, 0.15]
+    target_max_ratio = [0.92, 0.80, 0.80]
+    # the reference task hard-codes these in process_image_observation (lidar_navigation_task.py:320-347)
+    lidar_pool_window = (3, 6)
+    lidar_max_range, lidar_min_range, lidar_invalid_value, time_to_collision_max = 10.0, 0.2, 10.0, 10.0
+    reward_parameters = {
+        "pos_reward_magnitude": 3.0,
+        "pos_reward_exponent": 1.0,
+        "very_close_to_goal_reward_magnitude": 5.0,
+        "very_close_to_goal_reward_exponent": 8.0,
+        "vel_direction_component_reward_magnitude": 1.0,
+        "x_action_diff_penalty_magnitude": 0.3,
+        "x_action_diff_penalty_exponent": 5.0,
+        "y_action_diff_penalty_magnitude": 0.3,
+        "y_action_diff_penalty_exponent": 5.0,
+        "z_action_diff_penalty_magnitude": 0.3,
+        "z_action_diff_penalty_exponent": 5.0,
+        "yawrate_action_diff_penalty_magnitude": 0.3,
+        "yawrate_action_diff_penalty_exponent": 5.0,
+        "x_absolute_action_penalty_magnitude": 0.1,
+        "x_absolute_action_penalty_exponent": 0.3,
+        "y_absolute_action_penalty_magnitude": 0.1,
+        "y_absolute_action_penalty_exponent": 0.3,
+        "z_absolute_action_penalty_magnitude": 0.15,
+        "z_absolute_action_penalty_exponent": 1.0,
+        "yawrate_absolute_action_penalty_magnitude": 0.15,
+        "yawrate_absolute_action_penalty_exponent": 2.0,
+        "collision_penalty": -10.0,
+    }
+
+    class vae_config:
+        use_vae = False
+        latent_dims = 64
+        model_file = "ICRA_test_set_more_sim_data_kld_beta_3_LD_64_epoch_49.pth"
+        model_folder = ""
+        image_res = (270, 480)
+        interpolation_mode = "nearest"
+        return_sampled_latent = True
+
+    class curriculum:
+        min_level = 25
+        max_level = 70
+        check_after_log_instances = 2048
+        increase_step = 2
+        decrease_step = 1
+        success_rate_for_increase = 0.7
+        success_rate_for_decrease = 0.6
+
+    @staticmethod
+    def action_transformation_function(action):
+        """4-D policy action -> [2 ax, 2 ay, 2 az, yaw_rate] (lidar_navigation_task_config.py:105-115)."""
+        import math
+
+        import torch
+
+        clamped = torch.clamp(action, -1.0, 1.0)
+        out = torch.zeros((clamped.shape[0], 4), device=action.device)
+        out[:, 0:3] = 2 * clamped[:, 0:3]
+        out[:, 3] = clamped[:, 3] * (math.pi / 3)
+        return out

@@ -5,14 +5,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// AGX_DEV: device-only in the product build.  tests/csrc/host_shadow.cu defines AGX_HOST_SHADOW to get the very same
+// functions as host code, so per-env arithmetic can be checked against the oracle on a machine without a GPU.
+#ifdef AGX_HOST_SHADOW
+#include <math.h>
+#define AGX_DEV __host__ __device__ __forceinline__
+#else
+#define AGX_DEV __device__ __forceinline__
+#endif
+
 namespace agx {
 
 // sin/cos of an angle in [-2pi, 2pi].  AGX_FAST_TRIG: MUFU.SIN/COS (__sincosf, abs error <= 2^-21.4
 // on [-pi, pi], CUDA C Programming Guide table 9) instead of the ~40-instruction libdevice path.
 #ifdef AGX_FAST_TRIG
-__device__ __forceinline__ void sincos_(float x, float* s, float* c) { __sincosf(x, s, c); }
+AGX_DEV void sincos_(float x, float* s, float* c) { __sincosf(x, s, c); }
 #else
-__device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+AGX_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
 #endif
 
 #define AGX_PI_F 3.14159265358979323846f
@@ -25,21 +34,21 @@ struct Q4 {
     float x, y, z, w;
 };
 
-__device__ __forceinline__ V3 mk3(float x, float y, float z) { return V3{x, y, z}; }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
-__device__ __forceinline__ V3 neg(V3 a) { return V3{-a.x, -a.y, -a.z}; }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+AGX_DEV V3 mk3(float x, float y, float z) { return V3{x, y, z}; }
+AGX_DEV V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+AGX_DEV V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+AGX_DEV V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+AGX_DEV V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+AGX_DEV V3 neg(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+AGX_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+AGX_DEV V3 cross(V3 a, V3 b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-__device__ __forceinline__ float norm3(V3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+AGX_DEV float norm3(V3 a) { return sqrtf(dot(a, a)); }
+AGX_DEV V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
 
 // utils/math.py:58-65  quat_rotate
-__device__ __forceinline__ V3 quat_rotate(Q4 q, V3 v) {
+AGX_DEV V3 quat_rotate(Q4 q, V3 v) {
     V3 qv{q.x, q.y, q.z};
     float s = 2.0f * q.w * q.w - 1.0f;
     V3 a = v * s;
@@ -48,7 +57,7 @@ __device__ __forceinline__ V3 quat_rotate(Q4 q, V3 v) {
     return a + b + c;
 }
 // utils/math.py:339-347  quat_rotate_inverse
-__device__ __forceinline__ V3 quat_rotate_inverse(Q4 q, V3 v) {
+AGX_DEV V3 quat_rotate_inverse(Q4 q, V3 v) {
     V3 qv{q.x, q.y, q.z};
     float s = 2.0f * q.w * q.w - 1.0f;
     V3 a = v * s;
@@ -57,15 +66,15 @@ __device__ __forceinline__ V3 quat_rotate_inverse(Q4 q, V3 v) {
     return a - b + c;
 }
 // utils/math.py:313-320  quat_apply
-__device__ __forceinline__ V3 quat_apply(Q4 q, V3 v) {
+AGX_DEV V3 quat_apply(Q4 q, V3 v) {
     V3 qv{q.x, q.y, q.z};
     V3 t = cross(qv, v) * 2.0f;
     return v + t * q.w + cross(qv, t);
 }
-__device__ __forceinline__ Q4 quat_conj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
+AGX_DEV Q4 quat_conj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
 
 // utils/math.py:242-263  quat_mul (9-multiply form)
-__device__ __forceinline__ Q4 quat_mul(Q4 a, Q4 b) {
+AGX_DEV Q4 quat_mul(Q4 a, Q4 b) {
     float ww = (a.z + a.x) * (b.x + b.y);
     float yy = (a.w - a.y) * (b.w + b.z);
     float zz = (a.w + a.y) * (b.w - b.z);
@@ -83,7 +92,7 @@ struct M33 {
     float m[9];  // row-major
 };
 // utils/math.py:266-293  quat_to_rotation_matrix
-__device__ __forceinline__ M33 quat_to_matrix(Q4 q) {
+AGX_DEV M33 quat_to_matrix(Q4 q) {
     float xx = q.x * q.x, xy = q.x * q.y, xz = q.x * q.z, xw = q.x * q.w;
     float yy = q.y * q.y, yz = q.y * q.z, yw = q.y * q.w;
     float zz = q.z * q.z, zw = q.z * q.w;
@@ -101,16 +110,16 @@ __device__ __forceinline__ M33 quat_to_matrix(Q4 q) {
 }
 
 // python-style x % 2pi for x in (-2pi, 2pi): fmod is the identity there, then the sign fix.
-__device__ __forceinline__ float wrap_0_2pi(float x) { return (x < 0.0f) ? x + AGX_TWO_PI_F : x; }
+AGX_DEV float wrap_0_2pi(float x) { return (x < 0.0f) ? x + AGX_TWO_PI_F : x; }
 // utils/math.py:149-152 ssa for a in [0, 2pi): remainder(a + pi, 2pi) - pi
-__device__ __forceinline__ float ssa_0_2pi(float a) {
+AGX_DEV float ssa_0_2pi(float a) {
     float t = a + AGX_PI_F;
     t = (t >= AGX_TWO_PI_F) ? t - AGX_TWO_PI_F : t;
     return t - AGX_PI_F;
 }
 
 // utils/math.py:123-146 get_euler_xyz_tensor: roll/pitch/yaw each wrapped to [0, 2pi)
-__device__ __forceinline__ V3 euler_xyz_0_2pi(Q4 q) {
+AGX_DEV V3 euler_xyz_0_2pi(Q4 q) {
     float sinr_cosp = 2.0f * (q.w * q.x + q.y * q.z);
     float cosr_cosp = q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
     float roll = atan2f(sinr_cosp, cosr_cosp);
@@ -123,7 +132,7 @@ __device__ __forceinline__ V3 euler_xyz_0_2pi(Q4 q) {
 }
 
 // utils/math.py:155-172 quat_from_euler_xyz
-__device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw) {
+AGX_DEV Q4 quat_from_euler(float roll, float pitch, float yaw) {
     float sy, cy, sr, cr, sp, cp;
     sincos_(yaw * 0.5f, &sy, &cy);
     sincos_(roll * 0.5f, &sr, &cr);
@@ -137,7 +146,7 @@ __device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw
 }
 // same with roll = pitch = 0 (vehicle_frame_quat_from_quat, utils/math.py:175-180):
 // cos(0)=1, sin(0)=0 make the products exact, so only the yaw half-angle survives.
-__device__ __forceinline__ Q4 quat_from_yaw(float yaw) {
+AGX_DEV Q4 quat_from_yaw(float yaw) {
     float sy, cy;
     sincos_(yaw * 0.5f, &sy, &cy);
     return Q4{0.0f, 0.0f, sy, cy};
@@ -145,7 +154,7 @@ __device__ __forceinline__ Q4 quat_from_yaw(float yaw) {
 
 // pytorch3d.transforms.matrix_to_quaternion (published algorithm) -> xyzw.
 // R given by columns b1,b2,b3 (base_lee_controller.py:184-189).
-__device__ __forceinline__ Q4 matrix_cols_to_quat(V3 b1, V3 b2, V3 b3) {
+AGX_DEV Q4 matrix_cols_to_quat(V3 b1, V3 b2, V3 b3) {
     float m00 = b1.x, m10 = b1.y, m20 = b1.z;
     float m01 = b2.x, m11 = b2.y, m21 = b2.z;
     float m02 = b3.x, m12 = b3.y, m22 = b3.z;
@@ -177,12 +186,19 @@ __device__ __forceinline__ Q4 matrix_cols_to_quat(V3 b1, V3 b2, V3 b3) {
 struct U4 {
     uint32_t x, y, z, w;
 };
-__device__ __forceinline__ U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+AGX_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+AGX_DEV U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
         U4 n;
         n.x = hi1 ^ ctr.y ^ k0;
         n.y = lo1;
@@ -194,6 +210,6 @@ __device__ __forceinline__ U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
     }
     return ctr;
 }
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+AGX_DEV float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
 }  // namespace agx

@@ -164,7 +164,7 @@ int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
  * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor,
- * 5 AgxNavRewardParams, 6 AgxImuConfig */
+ * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams */
 uint64_t agx_sizeof(int which);
 
 /* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
@@ -253,6 +253,51 @@ typedef struct AgxImuConfig {
 int agx_imu_update(int num_envs, const AgxImuConfig* cfg, const float* force, int force_stride, const float* mass,
                    const float* robot_state, int robot_state_stride, const float* body_angvel, const float* sensor_quats,
                    const float* n_noise, const float* n_bias, float* bias, float* imu_meas, void* stream);
+
+/* ---- LiDARNavigationTask epilogue (task/lidar_navigation_task/lidar_navigation_task.py) ---------------- */
+
+/* LiDARNavigationTask.process_image_observation up to the min-pooling (:313-347): for every return of the
+ * world-frame point cloud  range = |p - robot_position|  (> max_range or < min_range -> invalid_value, :320-321),
+ * the per-pixel time to collision along the robot's world velocity (:327-335), then
+ *   image_ds [N, height/pool_h, width/pool_w] = min-pool (pool_h x pool_w, stride = window; -max_pool2d(-x), :346-347)
+ *   time_to_collision [N] = clamp(min over ALL pixels, 0, ttc_max)  (:339; ttc_max is also the value of a pixel
+ *   the robot is not moving towards).
+ * pointcloud [N,height,width,3] (depth_range_pixels with the sensor dimension squeezed); robot_state [N,stride] with
+ * the position in columns 0..2 and the world linear velocity in columns 7..9.  The task's own noise model (:286-310,
+ * torch RNG) and the final 1/x (:351) stay with the caller.  The reference hard-codes max_range = invalid_value =
+ * ttc_max = 10, min_range = 0.2, pool 3 x 6 on a 48 x 120 image. */
+int agx_lidar_nav_pool(int num_envs, int height, int width, int pool_h, int pool_w, const float* pointcloud,
+                       const float* robot_state, int robot_state_stride, float max_range, float min_range,
+                       float invalid_value, float ttc_max, float* image_ds, float* time_to_collision, void* stream);
+
+/* reward_parameters of LiDARNavigationTask in the order of config/task_config/lidar_navigation_task_config.py:28-51:
+ * pos_reward_{magnitude,exponent}, very_close_to_goal_reward_{magnitude,exponent},
+ * vel_direction_component_reward_magnitude, {x,y,z,yawrate}_action_diff_penalty_{magnitude,exponent},
+ * {x,y,z,yawrate}_absolute_action_penalty_{magnitude,exponent}, collision_penalty */
+typedef struct AgxLidarNavRewardParams {
+    float v[22];
+} AgxLidarNavRewardParams;
+
+/* LiDARNavigationTask.compute_rewards_and_crashes + compute_reward (:471-499, :554-720).
+ *   robot_state [N,stride] (position in columns 0..2), vehicle_orientation [N,4], target_position [N,3],
+ *   euler [N,3] (robot_euler_angles), target_yaw [N], vehicle_linvel / body_angvel [N,3], crashes [N] bool,
+ *   actions / prev_actions [N,4] (the task's current_action / prev_action), time_to_collision [N] (last value
+ *   written by agx_lidar_nav_pool);
+ *   pos_error [N,3] in = last step's vehicle-frame position error, out = this step's; pos_error_prev [N,3] out =
+ *   the value pos_error held on entry; rewards [N] out. */
+int agx_lidar_nav_reward(int num_envs, const float* robot_state, int robot_state_stride, const float* vehicle_orientation,
+                         const float* target_position, const float* euler, const float* target_yaw, const float* vehicle_linvel,
+                         const float* body_angvel, const uint8_t* crashes, const float* actions, const float* prev_actions,
+                         const float* time_to_collision, float curriculum_progress_fraction, const AgxLidarNavRewardParams* params,
+                         float* pos_error, float* pos_error_prev, float* rewards, void* stream);
+
+/* LiDARNavigationTask.process_obs_for_task (:440-469): observation columns 0..16 of obs [N,obs_stride], then columns
+ * 17..17+num_lidar-1 = lidar_obs [N,num_lidar] (downsampled_lidar_data; NULL or num_lidar = 0: untouched).
+ * u_vec, u_euler [N,3]: the two torch.rand_like draws of :446 and :456, in that order. */
+int agx_lidar_nav_obs(int num_envs, const float* robot_state, int robot_state_stride, const float* vehicle_orientation,
+                      const float* euler, const float* body_linvel, const float* body_angvel, const float* robot_actions,
+                      const float* target_position, const float* target_yaw, const float* u_vec, const float* u_euler,
+                      const float* lidar_obs, int num_lidar, float* obs, int obs_stride, void* stream);
 
 
 /* ======================================================================================

@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE ONLY -- CPU "shadow" of the per-env device code.
+//
+// The build container has no GPU.  The headers under aerial_gym_simulator_b200/csrc that hold per-env / per-lane arithmetic
+// (AGX_DEV functions) are compiled here a second time as HOST code (-DAGX_HOST_SHADOW) and driven by plain loops that stand in
+// for the kernels' thread mapping: envs one after the other, and for the pooling kernel warps and lanes one after the other with
+// the kernel's phase order.  tests/test_lidar_nav_shadow.py checks the result against the reference-generated fixtures and the
+// oracle, so arithmetic and indexing of a new kernel are verified before it ever reaches a GPU; the -m gpu tests then run the
+// real kernels through the C ABI.  Nothing in the product loads this library.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
+
+using namespace agx;
+
+extern "C" {
+
+// stands in for lidar_nav_pool_kernel<VEC4> (same locals, same order of the three phases per band)
+int shadow_lidar_nav_pool(int num_envs, int H, int W, int ph, int pw, const float* pc, const float* state, int stride, float max_range,
+                          float min_range, float invalid_value, float ttc_max, float* image_ds, float* ttc_out, int force_scalar) {
+    const long long band_floats = (long long)ph * W * 3;
+    const bool vec4 = !force_scalar && (((uintptr_t)pc & 15) == 0) && (band_floats % 4 == 0) && (((long long)H * W * 3) % 4 == 0);
+    const int band_slot = (int)((band_floats + 3) & ~3LL);
+    float* smem = nullptr;
+    if (posix_memalign((void**)&smem, 16, sizeof(float) * (size_t)kLnavPoolWarps * band_slot)) return -1;
+    for (int env = 0; env < num_envs; ++env) {
+        float warp_min[kLnavPoolWarps];
+        const float* st = state + (size_t)env * stride;
+        const V3 pos{st[0], st[1], st[2]}, vel{st[7], st[8], st[9]};
+        const int OH = H / ph, OW = W / pw;
+        const int nbands = (H + ph - 1) / ph;
+        const float* env_pc = pc + (size_t)env * H * W * 3;
+        for (int warp = 0; warp < kLnavPoolWarps; ++warp) {
+            float* buf = smem + (size_t)warp * band_slot;
+            float tmin_lane[32];
+            for (int lane = 0; lane < 32; ++lane) tmin_lane[lane] = ttc_max;
+            for (int b = warp; b < nbands; b += kLnavPoolWarps) {
+                const int rows = (ph < H - b * ph) ? ph : (H - b * ph);
+                const int nfl = rows * W * 3, npx = rows * W;
+                const float* src = env_pc + (size_t)b * band_floats;
+                for (int lane = 0; lane < 32; ++lane) lnav_band_stage(lane, vec4, src, buf, nfl);
+                for (int lane = 0; lane < 32; ++lane)
+                    tmin_lane[lane] = lnav_band_pixels(lane, buf, npx, pos, vel, max_range, min_range, invalid_value, ttc_max, tmin_lane[lane]);
+                if (b < OH)
+                    for (int lane = 0; lane < 32; ++lane) lnav_band_pool(lane, buf, W, ph, pw, OW, image_ds + ((size_t)env * OH + b) * OW);
+            }
+            float tmin = tmin_lane[0];
+            for (int lane = 1; lane < 32; ++lane) tmin = fminf(tmin, tmin_lane[lane]);
+            warp_min[warp] = tmin;
+        }
+        float m = warp_min[0];
+        for (int w = 1; w < kLnavPoolWarps; ++w) m = fminf(m, warp_min[w]);
+        ttc_out[env] = fminf(fmaxf(m, 0.0f), ttc_max);
+    }
+    free(smem);
+    return vec4 ? 1 : 0;
+}
+
+void shadow_lidar_nav_reward(int num_envs, const float* state, int stride, const float* veh_q, const float* target, const float* euler,
+                             const float* target_yaw, const float* veh_linvel, const float* body_angvel, const uint8_t* crashes,
+                             const float* act, const float* prev_act, const float* ttc, float frac, const AgxLidarNavRewardParams* p,
+                             float* pos_err, float* pos_err_prev, float* rewards) {
+    for (int e = 0; e < num_envs; ++e)
+        lnav_reward_env(e, state, stride, veh_q, target, euler, target_yaw, veh_linvel, body_angvel, crashes, act, prev_act, ttc, frac, *p,
+                        pos_err, pos_err_prev, rewards);
+}
+
+void shadow_lidar_nav_obs(int num_envs, const float* state, int stride, const float* veh_q, const float* euler, const float* blv,
+                          const float* bav, const float* actions, const float* target, const float* target_yaw, const float* u_vec,
+                          const float* u_euler, const float* lidar_obs, int num_lidar, float* obs, int obs_stride) {
+    for (int e = 0; e < num_envs; ++e)
+        lnav_obs_env(e, state, stride, veh_q, euler, blv, bav, actions, target, target_yaw, u_vec, u_euler, obs, obs_stride);
+    // lidar_nav_obs_copy_kernel: one "thread" per element
+    if (lidar_obs && num_lidar > 0) {
+        const long long total = (long long)num_envs * num_lidar;
+        for (long long i = 0; i < total; ++i) {
+            const long long e = i / num_lidar;
+            const int k = (int)(i - e * num_lidar);
+            obs[(size_t)e * obs_stride + 17 + k] = lidar_obs[i];
+        }
+    }
+}
+
+}  // extern "C"

@@ -59,3 +59,37 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
     assert os.path.isdir(os.path.join(root, "oracle"))
+
+
+def _header_prototypes():
+    import re
+    hdr = os.path.join(os.path.dirname(_build.PKG), "include", "aerial_gym_b200.h")
+    txt = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|uint64_t|const char\*)\s+(agx_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        params = [p.strip() for p in m.group(2).split(",")]
+        protos[m.group(1)] = [] if params == ["void"] else params
+    return protos
+
+
+def test_ctypes_argtypes_match_the_header(lib):
+    """Every prototype in include/aerial_gym_b200.h against the argtypes _lib.load() declared: same arity, and
+    pointer / float / integer in the same positions (a miscounted c_void_p run would shift every later argument)."""
+    protos = _header_prototypes()
+    assert len(protos) >= 18
+    for name, params in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            assert not params or name in ("agx_last_error", "agx_abi_version"), f"{name}: no argtypes declared in _lib.py"
+            continue
+        assert len(fn.argtypes) == len(params), f"{name}: header has {len(params)} parameters, _lib.py declares {len(fn.argtypes)}"
+        for i, (p, t) in enumerate(zip(params, fn.argtypes)):
+            if "*" in p:
+                ok = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_") and isinstance(t._type_, type)
+            elif p.startswith("float"):
+                ok = t is ctypes.c_float
+            else:
+                ok = t in (ctypes.c_int, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64)
+                if "uint64_t" in p:
+                    ok = t is ctypes.c_uint64
+            assert ok, f"{name}: parameter {i} `{p}` declared as {t}"

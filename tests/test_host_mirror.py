@@ -128,3 +128,53 @@ def test_navigation_task_config_matches_reference_values():
     want_z = (c[:, 0] + 1) * torch.sin(math.pi / 4 * c[:, 1]) * 2.0 / 2.0
     assert torch.allclose(out[:, 0], want_x) and torch.allclose(out[:, 2], want_z)
     assert torch.allclose(out[:, 3], c[:, 2] * math.pi / 3) and (out[:, 1] == 0).all()
+
+
+def test_lidar_navigation_task_surface_and_config():
+    """LiDARNavigationTask is registered with the reference's names and values (config/task_config/
+    lidar_navigation_task_config.py, env_with_lidar_nav_obstacles.py, rslidar_airy_config.py, magpie_config.py:52-53)."""
+    import math
+
+    import torch
+
+    import aerial_gym_simulator_b200.compat as compat
+    from aerial_gym_simulator_b200.config import asset_config as ac
+    from aerial_gym_simulator_b200.config.robot_config import MagpieCfg
+    from aerial_gym_simulator_b200.config.sensor_config import RSLidar_Airy_Config
+    from aerial_gym_simulator_b200.config.task_config import lidar_navigation_task_config as C
+
+    compat.install()
+    from aerial_gym.config.task_config.lidar_navigation_task_config import task_config
+    from aerial_gym.task.lidar_navigation_task.lidar_navigation_task import LiDARNavigationTask
+
+    assert task_registry.get_task_config("lidar_navigation_task") is task_config is C
+    assert task_registry.get_task_class("lidar_navigation_task") is LiDARNavigationTask
+    assert (C.robot_name, C.controller_name, C.env_name) == ("magpie", "magpie_acceleration_control", "env_with_lidar_nav_obstacles")
+    assert C.observation_space_dim == 337 and C.episode_len_steps == 110 and C.reward_parameters["collision_penalty"] == -10.0
+    assert (C.curriculum.min_level, C.curriculum.max_level) == (25, 70)
+    assert "magpie_acceleration_control" in controller_registry.get_controller_names()
+    assert MagpieCfg.sensor_config.enable_lidar and MagpieCfg.sensor_config.lidar_config is RSLidar_Airy_Config
+    L = RSLidar_Airy_Config
+    assert (L.height, L.width, L.return_pointcloud, L.pointcloud_in_world_frame, L.normalize_range) == (48, 120, True, True, False)
+    env = env_config_registry.make_env("env_with_lidar_nav_obstacles")
+    m = env.env_config.asset_type_to_dict_map
+    assert sum(p.num_assets for p in m.values()) == 15 + 70 + 6 and not any(p.keep_in_env for p in m.values())
+    assert m["panels"].min_state_ratio[0] == 0.35 and m["objects"].max_state_ratio[0:3] == [1.0, 1.0, 1.0]
+    assert env.env.lower_bound_min == [-7.5, -7.5, -5.0] and env.env.upper_bound_max == [7.5, 7.5, 5.0]
+    assert ac.panel_asset_params.num_assets == 3 and ac.left_wall.keep_in_env  # the navigation-task scene is untouched
+    a = torch.tensor([[0.5, -2.0, 0.25, 1.0], [3.0, 0.1, -0.3, -0.5]])
+    out = C.action_transformation_function(a)
+    assert torch.allclose(out[:, 0:3], 2 * torch.clamp(a[:, 0:3], -1, 1)) and torch.allclose(out[:, 3], torch.clamp(a[:, 3], -1, 1) * math.pi / 3)
+
+
+def test_lidar_task_noise_reproduces_the_reference_draws():
+    """The host-side noise of LiDARNavigationTask (torch RNG, CPU here) against the fixture recorded from the reference's own
+    add_noise_to_downsampled_lidar_data under the same seed."""
+    import torch
+
+    from aerial_gym_simulator_b200.task.lidar_navigation_task import add_noise_to_downsampled_lidar_data
+
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "lidar_nav_task_epilogue.npz"))
+    torch.manual_seed(int(d["pool_noise_seed"]))
+    noisy = add_noise_to_downsampled_lidar_data(torch.tensor(d["pool_image_ds"]))
+    assert torch.equal(noisy, torch.tensor(d["pool_image_noisy"]))
