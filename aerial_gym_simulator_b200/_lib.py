@@ -153,6 +153,7 @@ def load():
         "agx_lidar_nav_reward": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_float, C.POINTER(AgxLidarNavRewardParams)]
                                 + [C.c_void_p] * 4,
         "agx_lidar_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+        "agx_obstacle_step": [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p],
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
         "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -103,3 +103,9 @@ lidar_nav_top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_I
 lidar_nav_bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID, keep_in_env=False)
 lidar_nav_front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID, keep_in_env=False)
 lidar_nav_back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID, keep_in_env=False)
+
+
+# ---- config/asset_config/dynamic_env_object_config.py: free-floating objects moved by env_actions ("dynamic_env")
+class dynamic_object_asset_params(object_asset_params):
+    disable_gravity = True   # dynamic_env_object_config.py:28
+    fix_base_link = False    # :41

@@ -81,3 +81,20 @@ class EnvWithLidarNavObstaclesCfg(EnvWithObstaclesCfg):
             "left_wall": _ac.lidar_nav_left_wall, "right_wall": _ac.lidar_nav_right_wall, "back_wall": _ac.lidar_nav_back_wall,
             "front_wall": _ac.lidar_nav_front_wall, "bottom_wall": _ac.lidar_nav_bottom_wall, "top_wall": _ac.lidar_nav_top_wall,
         }
+
+
+class DynamicEnvironmentCfg(EnvWithObstaclesCfg):
+    """config/env_config/dynamic_environment.py: 35 free-floating objects (no panels, no walls) whose twist is set through
+    env.step(actions, env_actions=[N,35,6]) (examples/dynamic_env_example.py:33-45)."""
+    class env(EnvWithObstaclesCfg.env):
+        num_env_actions = 6
+        create_ground_plane = True
+        write_to_sim_at_every_timestep = True
+        lower_bound_min = [-2.0, -4.0, 0.0]
+        lower_bound_max = [-1.0, -2.5, 0.0]
+        upper_bound_min = [9.0, 2.5, 4.0]
+        upper_bound_max = [10.0, 4.0, 5.0]
+
+    class env_config:
+        include_asset_type = {k: (k == "objects") for k in EnvWithObstaclesCfg.env_config.include_asset_type}
+        asset_type_to_dict_map = {"objects": _ac.dynamic_object_asset_params}

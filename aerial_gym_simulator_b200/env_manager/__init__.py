@@ -7,6 +7,7 @@ from ..registry._core import env_config_registry, sim_config_registry
 env_config_registry.register("empty_env", _ec.EmptyEnvCfg)
 env_config_registry.register("env_with_obstacles", _ec.EnvWithObstaclesCfg)
 env_config_registry.register("env_with_lidar_nav_obstacles", _ec.EnvWithLidarNavObstaclesCfg)
+env_config_registry.register("dynamic_env", _ec.DynamicEnvironmentCfg)
 sim_config_registry.register("base_sim", _sc.BaseSimConfig)
 sim_config_registry.register("base_sim_headless", _sc.BaseSimHeadlessConfig)
 sim_config_registry.register("base_sim_2ms", _sc.SimCfg2Ms)

@@ -164,6 +164,10 @@ class EnvManager:
         A = len(per_env[0]) if per_env else 0
         if any(len(s) != A for s in per_env):
             raise ValueError("All environments should have the same number of assets")
+        # dynamic obstacles (agx_obstacle_step): one pair of damping coefficients for the whole scene -- every shipped asset
+        # class has 0.1 / 0.1 (config/asset_config/*_config.py: asset_state_params)
+        p0 = per_env[0][0][0] if A else None
+        self._asset_damping = (float(getattr(p0, "linear_damping", 0.0)), float(getattr(p0, "angular_damping", 0.0)))
         self.num_obs_in_env = A
         gtd["num_obstacles_in_env"] = A
         gtd["env_asset_state_tensor"] = torch.zeros(N, A, 13, device=dev)
@@ -386,8 +390,33 @@ class EnvManager:
                 self.compute_observations()
         elif n > 0:
             self.engine.physics_step(a, physics_steps=n)  # n sub-steps fused in one launch
+        if env_actions is not None and self.num_obs_in_env > 1 and n > 0:  # ObstacleManager.pre_physics_step, obstacle_manager.py:40-44
+            self._step_obstacles(gtd["env_actions"], n)
         self.engine.sim_steps += 1
         self.step_counter += 1
+
+    def _step_obstacles(self, twist, n):
+        """dynamic_env: the obstacles' twist is overwritten with env_actions [N,A,6] before each of the n physics steps and
+        the obstacles move (PhysX in the reference; agx_obstacle_step's kinematic advance here, one launch for the n steps).
+        The reference leaves its Warp meshes stale until the next reset ("refit() ... expensive", env_manager.py:340-342);
+        here re-posing + rebuilding the BVHs of all envs is one more launch, done by default (args['refit_dynamic_obstacles'])
+        so the ray-cast sensors and the collision test of the next env step see the obstacles where they are."""
+        import ctypes as C
+
+        from .. import _lib
+        gtd, N, A = self.global_tensor_dict, self.num_envs, self.num_obs_in_env
+        ast = gtd["env_asset_state_tensor"]
+        if tuple(twist.shape) != (N, A, 6) or twist.dtype != torch.float32 or twist.device != ast.device:
+            raise ValueError(f"env_actions must be a float32 [{N},{A},6] tensor on {ast.device} (linear + angular velocity per obstacle)")
+        twist = twist.contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.load().agx_obstacle_step(N, A, C.c_void_p(ast.data_ptr()), ast.stride(1), C.c_void_p(twist.data_ptr()),
+                                                 float(self.sim_config.sim.dt), int(n), self._asset_damping[0], self._asset_damping[1],
+                                                 stream), "agx_obstacle_step")
+        if self.scene is not None and bool(self.env_args.get("refit_dynamic_obstacles", True)):
+            idx = self._obj_asset.unsqueeze(-1).expand(-1, -1, 7)
+            self._obj_pose.copy_(torch.gather(ast[..., 0:7], 1, idx))
+            self.scene.update()
 
     def compute_observations(self):
         """crashes += contact (env_manager.py:358-362).  PhysX contact forces are replaced by a

@@ -300,6 +300,17 @@ int agx_lidar_nav_obs(int num_envs, const float* robot_state, int robot_state_st
                       const float* lidar_obs, int num_lidar, float* obs, int obs_stride, void* stream);
 
 
+/* ---- dynamic obstacles ("dynamic_env": env_manager/obstacle_manager.py:40-44 + PhysX) ------------------- */
+
+/* Kinematic advance of every obstacle by `substeps` physics steps of `dt`.  asset_state [N,A,asset_stride] rows
+ * x y z qx qy qz qw vx vy vz wx wy wz (env_asset_state_tensor, IGE_env_manager.py:315-317), in/out; twist [N,A,6] =
+ * env_actions (linear, angular velocity, world frame; written into the state before EVERY physics step like
+ * ObstacleManager.pre_physics_step does) or NULL = keep the velocities the state holds.  Per physics step (our spec -- PhysX
+ * is not observable; the robot integrator's form): v *= max(0, 1 - dt linear_damping), w likewise, x += dt v,
+ * q = normalize(dq(w dt) (x) q).  The caller re-poses the ray-cast scene afterwards (agx_hp2_update_scene). */
+int agx_obstacle_step(int num_envs, int num_assets, float* asset_state, int asset_stride, const float* twist, float dt, int substeps,
+                      float linear_damping, float angular_damping, void* stream);
+
 /* ======================================================================================
  * HP2 -- depth / segmentation / LiDAR ray-caster
  * ====================================================================================== */

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "host_shadow.cu")
 LIB = os.path.join(HERE, "_build", "libagx_host_shadow.so")
 _CSRC = os.path.join(HERE, "..", "aerial_gym_simulator_b200", "csrc")
-_DEPS = [SRC, os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
+_DEPS = [SRC, os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
          os.path.join(HERE, "..", "include", "aerial_gym_b200.h")]
 _lib = None
 
@@ -36,5 +36,7 @@ def load():
         lib.shadow_lidar_nav_reward.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_float, C.c_void_p] + [C.c_void_p] * 3
         lib.shadow_lidar_nav_obs.restype = None
         lib.shadow_lidar_nav_obs.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int]
+        lib.shadow_obstacle_step.restype = None
+        lib.shadow_obstacle_step.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]
         _lib = lib
     return _lib

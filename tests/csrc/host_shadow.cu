@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
+#include "../../aerial_gym_simulator_b200/csrc/obstacle_core.cuh"
 
 using namespace agx;
 
@@ -82,6 +83,13 @@ void shadow_lidar_nav_obs(int num_envs, const float* state, int stride, const fl
             obs[(size_t)e * obs_stride + 17 + k] = lidar_obs[i];
         }
     }
+}
+
+// stands in for obstacle_step_kernel: one "thread" per obstacle
+void shadow_obstacle_step(int num_envs, int num_assets, float* state, int stride, const float* twist, float dt, int substeps,
+                          float lin_damp, float ang_damp) {
+    const long long total = (long long)num_envs * num_assets;
+    for (long long i = 0; i < total; ++i) obstacle_step_item(i, state, stride, twist, dt, substeps, lin_damp, ang_damp);
 }
 
 }  // extern "C"

@@ -178,3 +178,12 @@ def test_lidar_task_noise_reproduces_the_reference_draws():
     torch.manual_seed(int(d["pool_noise_seed"]))
     noisy = add_noise_to_downsampled_lidar_data(torch.tensor(d["pool_image_ds"]))
     assert torch.equal(noisy, torch.tensor(d["pool_image_noisy"]))
+
+
+def test_dynamic_env_config():
+    """config/env_config/dynamic_environment.py + dynamic_env_object_config.py"""
+    env = env_config_registry.make_env("dynamic_env")
+    m = env.env_config.asset_type_to_dict_map
+    assert list(m) == ["objects"] and m["objects"].num_assets == 35 and not m["objects"].fix_base_link and m["objects"].disable_gravity
+    assert env.env.num_env_actions == 6 and env.env.write_to_sim_at_every_timestep and env.env.lower_bound_min[2] == 0.0
+    assert env.env.num_physics_steps_per_env_step_mean == 10
