@@ -18,6 +18,7 @@ UNITS = [
     ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
     ("hp1_aux.cu", []),
     ("lidar_nav.cu", []),
+    ("sensor_noise.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

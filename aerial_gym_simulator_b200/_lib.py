@@ -103,6 +103,12 @@ class AgxHp2Sensor(C.Structure):
     ]
 
 
+class AgxHp2Noise(C.Structure):
+    _fields_ = [("components", C.c_int32), ("enable_noise", C.c_int32), ("apply_limits", C.c_int32), ("normalize", C.c_int32),
+                ("std_a", f32), ("std_b", f32), ("std_c", f32), ("mean_offset", f32), ("pixel_dropout_prob", f32),
+                ("max_range", f32), ("min_range", f32), ("far_out_of_range_value", f32), ("near_out_of_range_value", f32)]
+
+
 SENSOR_CAMERA, SENSOR_LIDAR, SENSOR_STEREO_CAMERA, SENSOR_NORMAL_FACEID_CAMERA, SENSOR_NORMAL_FACEID_LIDAR = 0, 1, 2, 3, 4
 
 
@@ -154,6 +160,7 @@ def load():
                                 + [C.c_void_p] * 4,
         "agx_lidar_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p],
         "agx_obstacle_step": [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p],
+        "agx_hp2_noise_limits": [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(AgxHp2Noise), C.c_uint64, C.c_uint32, C.c_void_p],
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
         "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -166,7 +173,7 @@ def load():
     if lib.agx_sizeof(3) != C.sizeof(AgxHp2Scene) or lib.agx_sizeof(4) != C.sizeof(AgxHp2Sensor):
         raise AgxError("HP2 ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(5) != C.sizeof(AgxNavRewardParams) or lib.agx_sizeof(6) != C.sizeof(AgxImuConfig) \
-            or lib.agx_sizeof(7) != C.sizeof(AgxLidarNavRewardParams):
+            or lib.agx_sizeof(7) != C.sizeof(AgxLidarNavRewardParams) or lib.agx_sizeof(8) != C.sizeof(AgxHp2Noise):
         raise AgxError("aux ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
             or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):

@@ -45,6 +45,7 @@ uint64_t agx_sizeof(int which) {
 #ifdef AGX_HAVE_HP2
         case 3: return sizeof(AgxHp2Scene);
         case 4: return sizeof(AgxHp2Sensor);
+        case 8: return sizeof(AgxHp2Noise);
 #endif
         default: return 0;
     }

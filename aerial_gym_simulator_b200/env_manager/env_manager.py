@@ -267,6 +267,19 @@ class EnvManager:
         self.sensor = RaySensor(cfg, self.scene, self.engine.root_state, gtd["depth_range_pixels"], seg, self.sensor_mount)
         self.sensor.mount = self.sensor_mount  # keep the live tensor (RaySensor made it contiguous already)
         self.sensor.c.mount = self.sensor_mount.data_ptr()
+        # sensor noise (WarpSensor.apply_noise, warp_sensor.py:227-250): "device" = one in-place pass with a counter-based
+        # device RNG (agx_hp2_noise_limits; default next to the in-kernel Philox resets), "torch" = the reference's torch calls
+        # in the reference's order (default when reset_rng == "torch", i.e. when every random number comes from torch)
+        self.sensor_noise_rng = self.env_args.get("sensor_noise_rng", "device" if self.reset_rng == "device" else "torch")
+        if self.sensor_noise_rng not in ("device", "torch"):
+            raise ValueError("args['sensor_noise_rng'] must be 'device' or 'torch'")
+        self._device_noise = None
+        if self.sensor.noise_enabled and self.sensor_noise_rng == "device":
+            from ..sensors.noise import DeviceSensorNoise
+            px = gtd["depth_range_pixels"]
+            per_env = px[0].numel() // (3 if pc else 1)
+            self._device_noise = DeviceSensorNoise(cfg, px, seed=int(self.env_args.get("seed", 0)) ^ 0x5E4503_4E015E,
+                                                   first_pixel=int(self.env_args.get("env_id_offset", 0)) * per_env)
 
     # ------------------------------------------------------------------------------------------
     # reset (env_manager.py:273-301)
@@ -445,20 +458,12 @@ class EnvManager:
         if self.sensor is None:
             return
         self.sensor.capture()
-        if self.sensor.noise_enabled:  # WarpSensor.apply_noise + limits in torch (warp_sensor.py:202-247)
-            self._noise_and_limits()
-
-    def _noise_and_limits(self):
-        cfg, px = self.sensor_cfg, self.global_tensor_dict["depth_range_pixels"]
-        nz = cfg.sensor_noise
-        std = nz.std_a * px**2 + nz.std_b * px + nz.std_c
-        px[:] = torch.normal(mean=(px - nz.mean_offset), std=std)
-        px[torch.bernoulli(torch.ones_like(px) * nz.pixel_dropout_prob) > 0] = cfg.near_out_of_range_value
-        if not cfg.return_pointcloud:
-            px[px > cfg.max_range] = cfg.far_out_of_range_value
-            px[px < cfg.min_range] = cfg.near_out_of_range_value
-        if cfg.normalize_range and not cfg.pointcloud_in_world_frame:
-            px[:] = px / cfg.max_range
+        if self.sensor.noise_enabled:  # WarpSensor.apply_noise + apply_range_limits + normalize_observation (warp_sensor.py:197-250)
+            if self._device_noise is not None:
+                self._device_noise.apply()
+            else:
+                from ..sensors.noise import apply_noise_and_limits_torch
+                apply_noise_and_limits_torch(self.global_tensor_dict["depth_range_pixels"], self.sensor_cfg)
 
     def post_reward_calculation_step(self):
         envs_to_reset = self.reset_terminated_and_truncated_envs()

@@ -164,7 +164,7 @@ int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
  * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor,
- * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams */
+ * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams, 8 AgxHp2Noise */
 uint64_t agx_sizeof(int which);
 
 /* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
@@ -423,6 +423,28 @@ int agx_hp2_collide(const AgxHp2Scene* scene, const float* robot_pose, int robot
  *   epoch                  : strictly increasing per call, starting at 1 */
 int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const* peer_flags, int world, int rank,
                       uint64_t bytes, uint32_t epoch, uint32_t* scratch, void* stream);
+
+/* Sensor noise + range limits + normalisation, one pass, device RNG.  Replaces WarpSensor.apply_noise +
+ * apply_range_limits + normalize_observation (sensors/warp/warp_sensor.py:202-247) when the sensor's noise model is enabled
+ * (agx_hp2_cast then runs with fuse_epilogue = 0 and leaves raw ranges).  Same distributions as the reference --
+ * value ~ N(p - mean_offset, std_a p^2 + std_b p + std_c), dropout with probability pixel_dropout_prob -> near value, then
+ * > max_range -> far value, < min_range -> near value (on the norm of a sensor-frame point), / max_range -- but its own stream:
+ * Philox4x32-10, counter (pixel lo, pixel hi, frame, component), key = seed.  The torch-RNG path with the reference's draw
+ * order is the host's (aerial_gym_simulator_b200/sensors/noise.py). */
+typedef struct AgxHp2Noise {
+    int32_t components;        /* floats per pixel: 1 (depth / range image) or 3 (point cloud) */
+    int32_t enable_noise;      /* sensor_noise.enable_sensor_noise */
+    int32_t apply_limits;      /* 1 for camera / lidar / stereo images and sensor-frame point clouds (:198-215) */
+    int32_t normalize;         /* normalize_range and not pointcloud_in_world_frame (:222-225) */
+    float std_a, std_b, std_c, mean_offset, pixel_dropout_prob;   /* cfg.sensor_noise */
+    float max_range, min_range, far_out_of_range_value, near_out_of_range_value;
+} AgxHp2Noise;
+
+/* pixels: num_pixels * components floats, in place.  first_pixel: GLOBAL index of pixels[0] (env_id_offset x pixels per env on a
+ * sharded run, so the noise does not depend on how the envs are split over GPUs).  frame: a counter the caller advances once
+ * per render. */
+int agx_hp2_noise_limits(float* pixels, uint64_t num_pixels, uint64_t first_pixel, const AgxHp2Noise* cfg, uint64_t seed, uint32_t frame,
+                         void* stream);
 
 #ifdef __cplusplus
 }

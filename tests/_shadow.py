@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "host_shadow.cu")
 LIB = os.path.join(HERE, "_build", "libagx_host_shadow.so")
 _CSRC = os.path.join(HERE, "..", "aerial_gym_simulator_b200", "csrc")
-_DEPS = [SRC, os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
+_DEPS = [SRC, os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "noise_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
          os.path.join(HERE, "..", "include", "aerial_gym_b200.h")]
 _lib = None
 
@@ -38,5 +38,9 @@ def load():
         lib.shadow_lidar_nav_obs.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int]
         lib.shadow_obstacle_step.restype = None
         lib.shadow_obstacle_step.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]
+        lib.shadow_noise_limits.restype = None
+        lib.shadow_noise_limits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32]
+        lib.shadow_philox4x32_10.restype = None
+        lib.shadow_philox4x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = lib
     return _lib

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
+#include "../../aerial_gym_simulator_b200/csrc/noise_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/obstacle_core.cuh"
 
 using namespace agx;
@@ -90,6 +91,17 @@ void shadow_obstacle_step(int num_envs, int num_assets, float* state, int stride
                           float lin_damp, float ang_damp) {
     const long long total = (long long)num_envs * num_assets;
     for (long long i = 0; i < total; ++i) obstacle_step_item(i, state, stride, twist, dt, substeps, lin_damp, ang_damp);
+}
+
+// stands in for noise_limits_kernel: one "thread" per pixel
+void shadow_noise_limits(float* pixels, uint64_t num_pixels, uint64_t first_pixel, const AgxHp2Noise* cfg, uint64_t seed, uint32_t frame) {
+    for (uint64_t i = 0; i < num_pixels; ++i) noise_limits_pixel(i, first_pixel + i, pixels, *cfg, frame, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+}
+
+// the device Philox4x32-10 itself (agx_math.cuh), for the Random123 known-answer vectors
+void shadow_philox4x32_10(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {
+    const U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, k0, k1);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
 }  // extern "C"
