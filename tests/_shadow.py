@@ -7,19 +7,35 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "host_shadow.cu")
 LIB = os.path.join(HERE, "_build", "libagx_host_shadow.so")
 _CSRC = os.path.join(HERE, "..", "aerial_gym_simulator_b200", "csrc")
-_DEPS = [SRC, os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "noise_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
+_HP1_CU = os.path.join(_CSRC, "hp1.cu")
+_DEPS = [SRC, os.path.join(HERE, "csrc", "host_shadow_hp1.inc"), _HP1_CU, os.path.join(_CSRC, "hp1_core.cuh"), os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "noise_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
          os.path.join(HERE, "..", "include", "aerial_gym_b200.h")]
 _lib = None
+
+
+def _extract_kernel_blocks():
+    """The two inline blocks of hp1_step_kernel (one physics sub-step; the position-task reward) are not functions -- making them
+    functions changes the kernel's SASS -- so their TEXT is lifted out of hp1.cu, between `// AGX_SHADOW_BEGIN(name)` and
+    `// AGX_SHADOW_END(name)`, into tests/_build/hp1_<name>.inc, which the shadow includes in a scope with the same variable names."""
+    import re
+    txt = open(_HP1_CU).read()
+    for name in ("physics_substep", "position_task_reward"):
+        m = re.search(r"// AGX_SHADOW_BEGIN\(%s\)[^\n]*\n(.*?)\n[ \t]*// AGX_SHADOW_END\(%s\)" % (name, name), txt, re.S)
+        if not m:
+            raise RuntimeError(f"marker AGX_SHADOW_BEGIN({name}) not found in hp1.cu")
+        with open(os.path.join(os.path.dirname(LIB), f"hp1_{name}.inc"), "w") as f:
+            f.write(m.group(1) + "\n")
 
 
 def build(force=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in _DEPS):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    _extract_kernel_blocks()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     # host code only is used; nvcc is the compiler because the headers are CUDA headers (float4, __host__ __device__)
     cmd = [nvcc, "-x", "cu", "-DAGX_HOST_SHADOW", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
-           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", LIB, SRC]
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-I", os.path.dirname(LIB), "-shared", "-o", LIB, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("host shadow build failed:\n" + r.stdout + r.stderr)
@@ -42,5 +58,13 @@ def load():
         lib.shadow_noise_limits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32]
         lib.shadow_philox4x32_10.restype = None
         lib.shadow_philox4x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        from aerial_gym_simulator_b200 import _lib as A
+        for name, extra in (("shadow_hp1_physics_step", []), ("shadow_hp1_position_task_step", [C.c_int]),
+                            ("shadow_hp1_reset", [C.c_void_p, C.POINTER(A.AgxHp1ResetDraws)]), ("shadow_hp1_refresh", [])):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(A.AgxHp1Config), C.POINTER(A.AgxHp1Buffers)] + extra
+        lib.shadow_hp1_position_reward.restype = C.c_int
+        lib.shadow_hp1_position_reward.argtypes = [C.POINTER(A.AgxHp1Config), C.c_int] + [C.c_void_p] * 8
         _lib = lib
     return _lib

@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "../../aerial_gym_simulator_b200/csrc/hp1_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/noise_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/obstacle_core.cuh"
@@ -105,3 +106,5 @@ void shadow_philox4x32_10(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_
 }
 
 }  // extern "C"
+
+#include "host_shadow_hp1.inc"
