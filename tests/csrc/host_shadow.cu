@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "../../aerial_gym_simulator_b200/csrc/aux_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/hp1_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/noise_core.cuh"
@@ -85,6 +86,20 @@ void shadow_lidar_nav_obs(int num_envs, const float* state, int stride, const fl
             obs[(size_t)e * obs_stride + 17 + k] = lidar_obs[i];
         }
     }
+}
+
+// stand in for nav_reward_kernel / nav_obs_kernel / imu_kernel (hp1_aux.cu): one "thread" per env
+void shadow_nav_reward(int n, const float* state, int stride, const float* veh_q, const float* target, const uint8_t* crashes, const float* act,
+                       const float* prev_act, float frac, const AgxNavRewardParams* p, float* pos_err, float* pos_err_prev, float* rewards) {
+    for (int e = 0; e < n; ++e) nav_reward_env(e, state, stride, veh_q, target, crashes, act, prev_act, frac, *p, pos_err, pos_err_prev, rewards);
+}
+void shadow_nav_obs(int n, const float* state, int stride, const float* veh_q, const float* euler, const float* blv, const float* bav,
+                    const float* actions, const float* target, const float* u_vec, const float* u_euler, float* obs, int obs_stride) {
+    for (int e = 0; e < n; ++e) nav_obs_env(e, state, stride, veh_q, euler, blv, bav, actions, target, u_vec, u_euler, obs, obs_stride);
+}
+void shadow_imu_update(int n, const AgxImuConfig* c, const float* force, int force_stride, const float* mass, const float* state, int stride,
+                       const float* bav, const float* sensor_q, const float* n_noise, const float* n_bias, float* bias, float* meas) {
+    for (int e = 0; e < n; ++e) imu_env(e, *c, force, force_stride, mass, state, stride, bav, sensor_q, n_noise, n_bias, bias, meas);
 }
 
 // stands in for obstacle_step_kernel: one "thread" per obstacle
