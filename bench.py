@@ -218,8 +218,18 @@ def run_ours(args):
     acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
     gather = None
     if world > 1:
-        gather = ObsAllGather(N, 13, world * N, dev) if args.gather == "nccl" else \
-            P2PObsAllGather(N, 13, dev, num_buffers=4 if args.gather == "fused" else 2)
+        if args.gather != "nccl":
+            try:  # symmetric-memory rendezvous (NVLink peer mappings); every rank must take the same branch
+                gather = P2PObsAllGather(N, 13, dev, num_buffers=4 if args.gather == "fused" else 2)
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:  # noqa: BLE001  -- e.g. a box without P2P between some GPU pair
+                sys.stderr.write(f"[bench rank {rank}] {args.gather} gather unavailable ({exc!r})\n")
+                gather, ok = None, torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:  # somebody failed: everybody uses the library collective, and the line says so
+                args.gather, gather = "nccl", None
+        if args.gather == "nccl":
+            gather = ObsAllGather(N, 13, world * N, dev)
         if args.gather == "fused":  # the step kernel pushes the rows to every peer and handshakes itself
             for e in engines:
                 e.attach_obs_gather(gather)
