@@ -75,11 +75,8 @@ def install():
             "aerial_gym.config.task_config.lidar_navigation_task_config", task_config=task_config.lidar_navigation_task_config),
         "config.env_config.env_with_lidar_nav_obstacles": _module(
             "aerial_gym.config.env_config.env_with_lidar_nav_obstacles", EnvWithLidarNavObstaclesCfg=env_config.EnvWithLidarNavObstaclesCfg),
-        "config.sensor_config.lidar_config": _module("aerial_gym.config.sensor_config.lidar_config", __path__=[]),
-        "config.sensor_config.lidar_config.rslidar_airy_config": _module(
-            "aerial_gym.config.sensor_config.lidar_config.rslidar_airy_config", RSLidar_Airy_Config=sensor_config.RSLidar_Airy_Config),
-        "config.sensor_config.lidar_config.osdome_64_config": _module(
-            "aerial_gym.config.sensor_config.lidar_config.osdome_64_config", OSDome_64_Config=sensor_config.OSDome_64_Config),
+        "config.env_config.dynamic_environment": _module(
+            "aerial_gym.config.env_config.dynamic_environment", DynamicEnvironmentCfg=env_config.DynamicEnvironmentCfg),
         "config.task_config.position_setpoint_task_config": _module(
             "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
         "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),
@@ -90,3 +87,20 @@ def install():
                                                         **{k: v for k, v in vars(robot_config).items() if k.startswith("BaseQuad")}),
     }
     del deep
+    # the reference's one-class-per-file sensor catalogue: config/sensor_config/{lidar,camera,imu}_config/<file>.py
+    catalogue = {
+        "lidar_config": {"base_lidar_config": "BaseLidarConfig", "os0_128_config": "OS_0_128_Config", "os0_64_config": "OS_0_64_Config",
+                         "os1_64_config": "OS_1_64_Config", "os2_64_config": "OS_2_64_Config", "osdome_64_config": "OSDome_64_Config",
+                         "rslidar_airy_config": "RSLidar_Airy_Config", "pmd_flexx2_config": "pmd_flexx2_config",
+                         "st_vl53l5cx_config": "ST_VL53L5CXConfig", "fake_radar_config": "fake_radar_config"},
+        "camera_config": {"base_depth_camera_config": "BaseDepthCameraConfig", "d455_depth_config": "RsD455Config",
+                          "intel_realsense_d455_config": "IntelRealSenseD455Config", "luxonis_oak_d_config": "LuxonisOakDConfig",
+                          "luxonis_oak_d_pro_w_config": "LuxonisOakDProWConfig", "stereo_camera_config": "StereoCameraConfig",
+                          "base_normal_faceID_camera_config": "BaseNormalFaceIDCameraConfig"},
+        "imu_config": {"base_imu_config": "BaseImuConfig", "bosch_bmi088_config": "BoschBMI088Config", "vn100_config": "VN100Config"},
+    }
+    for pkg_name, files in catalogue.items():
+        _module(f"aerial_gym.config.sensor_config.{pkg_name}", __path__=[])
+        for fname, cls in files.items():
+            _module(f"aerial_gym.config.sensor_config.{pkg_name}.{fname}", **{cls: getattr(sensor_config, cls)})
+    _module("aerial_gym.config.sensor_config.base_sensor_config", BaseSensorConfig=sensor_config.BaseSensorConfig)

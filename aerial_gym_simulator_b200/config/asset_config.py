@@ -26,11 +26,17 @@ class asset_state_params:
     max_position_ratio = [0.5, 0.5, 0.5]
     collision_mask = 1
     disable_gravity = False
+    replace_cylinder_with_capsule = True   # PhysX asset options, kept for config parity (unused: no PhysX here)
+    flip_visual_attachments = True
     density = 0.001
     angular_damping = 0.1
     linear_damping = 0.1
     max_angular_velocity = 100.0
     max_linear_velocity = 100.0
+    armature = 0.001
+    place_force_sensor = False
+    force_sensor_parent_link = "base_link"
+    force_sensor_transform = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
     collapse_fixed_joints = True
     fix_base_link = True
     specific_filepath = None
@@ -49,6 +55,7 @@ class panel_asset_params(asset_state_params):
     num_assets = 3
     asset_folder = f"{_ENV_ASSETS}/panels"
     min_position_ratio, max_position_ratio = [0.3, 0.05, 0.05], [0.85, 0.95, 0.95]
+    specified_position = [-1000.0, -1000.0, -1000.0]  # unused by the reference as well
     min_euler_angles, max_euler_angles = [0.0, 0.0, -PI / 3.0], [0.0, 0.0, PI / 3.0]
     min_state_ratio, max_state_ratio = _ratio((0.3, 0.05, 0.05), (0.85, 0.95, 0.95), (0, 0, -PI / 3.0), (0, 0, PI / 3.0))
     keep_in_env = True
@@ -62,21 +69,21 @@ class object_asset_params(asset_state_params):
     min_state_ratio, max_state_ratio = _ratio((0.30, 0.05, 0.05), (0.85, 0.9, 0.9), (-PI, -PI, -PI), (PI, PI, PI))
     keep_in_env = False
     semantic_id = -1
-    color = [80, 255, 100]
+    color = None  # (the colour line is commented out in env_object_config.py:313)
 
 
-def _wall(fname, ratio, sem, keep_in_env=True):
+def _wall(fname, ratio, sem, keep_in_env=True, color=(100, 200, 210)):
     lo, hi = _ratio(ratio, ratio)
     return type(fname.replace(".urdf", ""), (asset_state_params,), dict(
-        num_assets=1, asset_folder=f"{_ENV_ASSETS}/walls", file=fname, min_position_ratio=list(ratio),
-        max_position_ratio=list(ratio), min_state_ratio=lo, max_state_ratio=hi, keep_in_env=keep_in_env,
-        semantic_id=sem, color=[100, 200, 210]))
+        num_assets=1, asset_folder=f"{_ENV_ASSETS}/walls", file=fname, min_state_ratio=lo, max_state_ratio=hi, keep_in_env=keep_in_env,
+        specific_filepath="cube.urdf",
+        semantic_id=sem, color=list(color)))
 
 
 left_wall = _wall("left_wall.urdf", (0.5, 1.0, 0.5), LEFT_WALL_SEMANTIC_ID)
 right_wall = _wall("right_wall.urdf", (0.5, 0.0, 0.5), RIGHT_WALL_SEMANTIC_ID)
 top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_ID)
-bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID)
+bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID, color=(100, 150, 150))
 front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID)
 back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID)
 
@@ -100,12 +107,13 @@ class lidar_nav_object_asset_params(object_asset_params):
 lidar_nav_left_wall = _wall("left_wall.urdf", (0.5, 1.0, 0.5), LEFT_WALL_SEMANTIC_ID, keep_in_env=False)
 lidar_nav_right_wall = _wall("right_wall.urdf", (0.5, 0.0, 0.5), RIGHT_WALL_SEMANTIC_ID, keep_in_env=False)
 lidar_nav_top_wall = _wall("top_wall.urdf", (0.5, 0.5, 1.0), TOP_WALL_SEMANTIC_ID, keep_in_env=False)
-lidar_nav_bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID, keep_in_env=False)
+lidar_nav_bottom_wall = _wall("bottom_wall.urdf", (0.5, 0.5, 0.0), BOTTOM_WALL_SEMANTIC_ID, keep_in_env=False, color=(100, 150, 150))
 lidar_nav_front_wall = _wall("front_wall.urdf", (1.0, 0.5, 0.5), FRONT_WALL_SEMANTIC_ID, keep_in_env=False)
 lidar_nav_back_wall = _wall("back_wall.urdf", (0.0, 0.5, 0.5), BACK_WALL_SEMANTIC_ID, keep_in_env=False)
 
 
 # ---- config/asset_config/dynamic_env_object_config.py: free-floating objects moved by env_actions ("dynamic_env")
 class dynamic_object_asset_params(object_asset_params):
-    disable_gravity = True   # dynamic_env_object_config.py:28
+    num_assets = 40          # dynamic_env_object_config.py:274
+    disable_gravity = True   # :28
     fix_base_link = False    # :41

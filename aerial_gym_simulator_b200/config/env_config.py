@@ -84,8 +84,8 @@ class EnvWithLidarNavObstaclesCfg(EnvWithObstaclesCfg):
 
 
 class DynamicEnvironmentCfg(EnvWithObstaclesCfg):
-    """config/env_config/dynamic_environment.py: 35 free-floating objects (no panels, no walls) whose twist is set through
-    env.step(actions, env_actions=[N,35,6]) (examples/dynamic_env_example.py:33-45)."""
+    """config/env_config/dynamic_environment.py: 40 free-floating objects (no panels, no walls) whose twist is set through
+    env.step(actions, env_actions=[N,40,6]) (examples/dynamic_env_example.py:33-45)."""
     class env(EnvWithObstaclesCfg.env):
         num_env_actions = 6
         create_ground_plane = True

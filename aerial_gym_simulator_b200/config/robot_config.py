@@ -4,7 +4,8 @@ Articulated robots (ROV, reconfigurable, Morphy) are out of the hot-path scope (
 import numpy as np
 
 from . import RESOURCES_DIRECTORY
-from .sensor_config import BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, OSDome_64_Config, RSLidar_Airy_Config
+from .sensor_config import (BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, OSDome_64_Config, RSLidar_Airy_Config,
+                            pmd_flexx2_config)
 
 PI = np.pi
 QUAD_ALLOCATION = [
@@ -194,6 +195,7 @@ class BaseOctarotorCfg(BaseQuadCfg):
 class LMF2Cfg(BaseQuadCfg):
     class sensor_config(BaseQuadCfg.sensor_config):
         enable_camera = True
+        lidar_config = pmd_flexx2_config  # lmf2_config.py:58 (disabled by default)
 
     class disturbance:
         enable_disturbance = True

@@ -108,6 +108,14 @@ def test_compat_import_paths_of_the_reference():
     from aerial_gym.utils.vae.vae_image_encoder import VAEImageEncoder  # noqa: F401
 
     assert tr.get_task_config("navigation_task") is nav_cfg and nav_cfg.robot_name == "lmf2"
+    # the one-class-per-file sensor catalogue
+    from aerial_gym.config.sensor_config.camera_config.d455_depth_config import RsD455Config
+    from aerial_gym.config.sensor_config.imu_config.vn100_config import VN100Config  # noqa: F401
+    from aerial_gym.config.sensor_config.lidar_config.os1_64_config import OS_1_64_Config
+    from aerial_gym.config.env_config.dynamic_environment import DynamicEnvironmentCfg  # noqa: F401
+
+    assert (RsD455Config.height, RsD455Config.far_out_of_range_value) == (270, 15.0)
+    assert (OS_1_64_Config.max_range, OS_1_64_Config.far_out_of_range_value) == (90.0, 35.0)  # the reference's inherited far value
 
 
 def test_navigation_task_config_matches_reference_values():
@@ -184,6 +192,6 @@ def test_dynamic_env_config():
     """config/env_config/dynamic_environment.py + dynamic_env_object_config.py"""
     env = env_config_registry.make_env("dynamic_env")
     m = env.env_config.asset_type_to_dict_map
-    assert list(m) == ["objects"] and m["objects"].num_assets == 35 and not m["objects"].fix_base_link and m["objects"].disable_gravity
+    assert list(m) == ["objects"] and m["objects"].num_assets == 40 and not m["objects"].fix_base_link and m["objects"].disable_gravity
     assert env.env.num_env_actions == 6 and env.env.write_to_sim_at_every_timestep and env.env.lower_bound_min[2] == 0.0
     assert env.env.num_physics_steps_per_env_step_mean == 10

@@ -71,7 +71,7 @@ def test_dynamic_env_end_to_end():
                                  use_warp=True, headless=True)
     gtd = env.get_obs()
     A = gtd["num_obstacles_in_env"]
-    assert A == 35 and gtd["num_env_actions"] == 6
+    assert A == 40 and gtd["num_env_actions"] == 6
     env.reset()
     ast = gtd["env_asset_state_tensor"]
     twist = torch.zeros(N, A, 6, device=DEV)
