@@ -387,6 +387,10 @@ class EnvManager:
         gtd = self.global_tensor_dict
         self.reset_tensors()
         if env_actions is not None:
+            if self.num_obs_in_env > 1:
+                want = (self.num_envs, self.num_obs_in_env, 6)
+                if tuple(env_actions.shape) != want or env_actions.dtype != torch.float32 or env_actions.device.type != self.device.type:
+                    raise ValueError(f"env_actions must be a float32 {list(want)} tensor on {self.device} (linear + angular velocity per obstacle)")
             if gtd["env_actions"] is None:
                 gtd["env_actions"], gtd["prev_env_actions"] = env_actions, env_actions.clone()
             gtd["prev_env_actions"][:] = gtd["env_actions"]
@@ -419,9 +423,7 @@ class EnvManager:
         from .. import _lib
         gtd, N, A = self.global_tensor_dict, self.num_envs, self.num_obs_in_env
         ast = gtd["env_asset_state_tensor"]
-        if tuple(twist.shape) != (N, A, 6) or twist.dtype != torch.float32 or twist.device != ast.device:
-            raise ValueError(f"env_actions must be a float32 [{N},{A},6] tensor on {ast.device} (linear + angular velocity per obstacle)")
-        twist = twist.contiguous()
+        twist = twist.contiguous()  # shape / dtype / device were checked in step()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(_lib.load().agx_obstacle_step(N, A, C.c_void_p(ast.data_ptr()), ast.stride(1), C.c_void_p(twist.data_ptr()),
                                                  float(self.sim_config.sim.dt), int(n), self._asset_damping[0], self._asset_damping[1],
