@@ -1,0 +1,199 @@
+"""The reference-facing surface end to end ON CPU: task_registry.make_task -> task.reset / step, SimBuilder().build_env ->
+EnvManager.step / reset / render, with the CUDA engines replaced by their CPU twins (tests/_cpu_stack.py: host shadow of the HP1 /
+per-env device code, brute-force ray-cast oracle).  What runs here is the product's own HOST code -- registries, config plumbing,
+RNG call order, reset / curriculum / render bookkeeping, Global-Tensor-Dict aliasing -- i.e. the part of the -m gpu end-to-end
+tests (tests/test_env_task_gpu.py, test_zz_*_gpu.py) that does not need a GPU."""
+import numpy as np
+import pytest
+import torch
+
+import aerial_gym_simulator_b200.task  # noqa: F401
+from aerial_gym_simulator_b200.registry._core import task_registry
+from aerial_gym_simulator_b200.sim import SimBuilder
+from oracle import lidar_nav_oracle as L
+from oracle import obstacle_oracle as OB
+from oracle import sensor_noise_oracle as SN
+
+from ._cpu_stack import cpu_stack
+
+
+@pytest.fixture
+def cpu_task():
+    made = []
+
+    def make(name, **kw):
+        cfg = task_registry.get_task_config(name)
+        old = cfg.device
+        cfg.device = "cpu"
+        made.append((cfg, old))
+        return task_registry.make_task(name, headless=True, **kw)
+    with cpu_stack() as proxy:
+        make.proxy = proxy
+        yield make
+    for cfg, old in made:
+        cfg.device = old
+
+
+def test_position_setpoint_task_surface(cpu_task):
+    task = cpu_task("position_setpoint_task", seed=3, num_envs=70)
+    obs, rew, term, trunc, info = task.reset()
+    assert obs["observations"].shape == (70, 13) and term.dtype == torch.bool and trunc.dtype == torch.bool
+    gtd = task.sim_env.get_obs()
+    base = gtd["robot_state_tensor"]
+    for k in ("robot_position", "robot_orientation", "robot_linvel", "robot_angvel"):
+        assert gtd[k]._base is base  # views of ONE [N,13] row
+    g = torch.Generator().manual_seed(0)
+    for i in range(505):
+        out = task.step((torch.rand(70, 4, generator=g) * 2 - 1) * 0.05)
+        assert out[0] is obs and out[1] is rew and out[2] is term and out[3] is trunc
+        if i == 499:
+            assert not trunc.any() and not term.any() and (task.sim_env.sim_steps == 500).all()
+    assert torch.isfinite(obs["observations"]).all() and (task.sim_env.sim_steps == 4).all()
+    assert int(task.sim_env.engine.episode_count.min()) == 2  # initial reset + truncation at step 501
+    assert torch.equal(obs["observations"][:, 3:7], gtd["robot_orientation"])
+
+
+def test_navigation_task_end_to_end(cpu_task):
+    cfg = task_registry.get_task_config("navigation_task")
+    old = cfg.vae_config.use_vae
+    cfg.vae_config.use_vae = False  # (the encoder is plain torch, covered by test_aux_oracle_golden.py)
+    try:
+        task = cpu_task("navigation_task", seed=5, num_envs=3)
+        od = task.obs_dict
+        assert od["depth_range_pixels"].shape == (3, 1, 135, 240) and od["num_obstacles_in_env"] == 15
+        obs, rew, term, trunc, info = task.reset()
+        for _ in range(2):
+            obs, rew, term, trunc, info = task.step(torch.rand(3, 3) * 2 - 1)
+        assert torch.isfinite(obs["observations"][:, :17]).all() and torch.isfinite(rew).all()
+        assert cpu_task.proxy.calls["agx_nav_reward"] == 2 and cpu_task.proxy.calls["agx_nav_obs"] == 3
+        assert task.sim_env.sensor.captures >= 2 and (od["segmentation_pixels"] >= -2).all()
+        px = od["depth_range_pixels"]
+        assert (px <= 1.0).all() and (px >= -1.0).all() and (px > 0).any()
+    finally:
+        cfg.vae_config.use_vae = old
+
+
+def test_lidar_navigation_task_end_to_end(cpu_task):
+    """CPU twin of tests/test_zz_lidar_nav_gpu.py::test_lidar_navigation_task_end_to_end"""
+    N = 3
+    task = cpu_task("lidar_navigation_task", seed=7, num_envs=N)
+    od = task.obs_dict
+    assert od["depth_range_pixels"].shape == (N, 1, 48, 120, 3) and od["num_obstacles_in_env"] == 25
+    assert task.sim_env.scene.K >= 91
+    obs, rew, term, trunc, info = task.reset()
+    assert obs["observations"].shape == (N, 337) and (obs["observations"][:, 17:] == 0).all()
+    assert (task.target_yaw.abs() <= np.pi).all()
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        a = (torch.rand(N, 4, generator=g) * 2 - 1) * 0.3
+        out = task.step(a)
+        assert out[0] is obs and out[1] is rew
+    assert torch.isfinite(obs["observations"]).all() and torch.isfinite(rew).all()
+    assert torch.equal(obs["observations"][:, 17:], task.downsampled_lidar_data)
+    assert (task.time_to_collision >= 0).all() and (task.time_to_collision <= 10).all()
+    assert torch.allclose(task.current_action[:, 0:3], 2 * a[:, 0:3]) and torch.equal(obs["observations"][:, 13:17], od["robot_actions"])
+    task.add_noise_to_downsampled_lidar_data = lambda x: x
+    task.process_image_observation()
+    pc = od["depth_range_pixels"].squeeze(1)
+    want_ds, want_ttc = L.pool(pc, od["robot_position"], od["robot_linvel"])
+    r = (pc - od["robot_position"].view(N, 1, 1, 3)).norm(dim=-1)
+    near = ((r - 10.0).abs().lt(1e-4) | (r - 0.2).abs().lt(1e-5)).view(N, 16, 3, 20, 6).any(4).any(2)
+    assert (torch.isclose(task._image_ds, want_ds, rtol=1e-5, atol=0) | near).all()
+    assert torch.allclose(task.time_to_collision, want_ttc, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(task.downsampled_lidar_data, (1 / task._image_ds).view(N, -1), rtol=1e-6, atol=0)
+    d = np.load(__file__.replace("test_host_stack_cpu.py", "golden/lidar_nav_task_epilogue.npz"))
+    p = {k: float(v) for k, v in zip(d["param_names"], d["param_values"])}
+    prev_err = task.pos_error_vehicle_frame.clone()
+    task.compute_rewards_and_crashes(od)
+    want, err = L.rewards_and_errors(od["robot_vehicle_orientation"], od["robot_position"], task.target_position, od["robot_euler_angles"],
+                                     task.target_yaw, od["robot_vehicle_linvel"], od["robot_body_angvel"], od["crashes"], task.current_action,
+                                     task.prev_action, task.time_to_collision, task.curriculum_progress_fraction, p)
+    assert torch.allclose(task.rewards, want, rtol=1e-5, atol=2e-4) and torch.allclose(task.pos_error_vehicle_frame, err, rtol=1e-5, atol=1e-5)
+    assert torch.equal(task.pos_error_vehicle_frame_prev, prev_err)
+    u1, u2 = torch.rand(N, 3), torch.rand(N, 3)
+    task.process_obs_for_task(u1, u2)
+    want_obs = L.process_obs(od["robot_vehicle_orientation"], od["robot_position"], task.target_position, od["robot_euler_angles"],
+                             task.target_yaw, od["robot_body_linvel"], od["robot_body_angvel"], od["robot_actions"], task.downsampled_lidar_data, u1, u2)
+    assert torch.allclose(obs["observations"], want_obs, rtol=1e-5, atol=1e-5)
+    task.close()
+
+
+def test_dynamic_env_end_to_end():
+    """CPU twin of tests/test_zz_obstacles_gpu.py::test_dynamic_env_end_to_end"""
+    N = 2
+    with cpu_stack():
+        env = SimBuilder().build_env("base_sim", "dynamic_env", "lmf2", "lmf2_position_control", "cpu", args={"seed": 2}, num_envs=N,
+                                     use_warp=True, headless=True)
+        gtd = env.get_obs()
+        A = gtd["num_obstacles_in_env"]
+        assert A == 40 and gtd["num_env_actions"] == 6
+        env.reset()
+        ast = gtd["env_asset_state_tensor"]
+        twist = torch.zeros(N, A, 6)
+        twist[..., 0], twist[..., 1], twist[..., 5] = -1.0, 0.5, 0.8
+        actions = torch.zeros(N, 4)
+        before, upd = ast.clone(), env.scene.updates
+        env.step(actions=actions, env_actions=twist)
+        want = OB.obstacle_step(before, twist, gtd["dt"], 10, 0.1, 0.1)
+        assert torch.allclose(ast, want, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(ast[..., 0], before[..., 0] - 0.1 * 0.999, atol=1e-4)
+        assert env.scene.updates == upd + 1  # the ray-cast scene was re-posed once for the env step
+        assert torch.equal(env._obj_pose, torch.gather(ast[..., 0:7], 1, env._obj_asset.unsqueeze(-1).expand(-1, -1, 7)))
+        with pytest.raises(ValueError, match="env_actions"):
+            env.step(actions=actions, env_actions=torch.zeros(N, A + 1, 6))
+        env.render()
+        assert env.sensor.captures == 1
+        env2 = SimBuilder().build_env("base_sim", "dynamic_env", "lmf2", "lmf2_position_control", "cpu",
+                                      args={"seed": 2, "refit_dynamic_obstacles": False}, num_envs=N, use_warp=True, headless=True)
+        env2.reset()
+        pose0, ast2 = env2._obj_pose.clone(), env2.get_obs()["env_asset_state_tensor"]
+        before2 = ast2.clone()
+        env2.step(actions=actions, env_actions=twist)
+        assert torch.equal(env2._obj_pose, pose0) and torch.allclose(ast2[..., 0], before2[..., 0] - 0.1 * 0.999, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["device", "torch"])
+def test_env_manager_noisy_lidar(mode):
+    """CPU twin of tests/test_zz_sensor_noise_gpu.py::test_env_manager_noisy_lidar (smaller image: the oracle is brute force)"""
+    from aerial_gym_simulator_b200.config.robot_config import BaseQuadWithLidarCfg
+    from aerial_gym_simulator_b200.config.sensor_config import BaseLidarConfig
+    from aerial_gym_simulator_b200.sensors.noise import apply_noise_and_limits_torch
+
+    class SmallNoisyLidar(BaseLidarConfig):
+        height, width = 16, 32
+    old = BaseQuadWithLidarCfg.sensor_config.lidar_config
+    BaseQuadWithLidarCfg.sensor_config.lidar_config = SmallNoisyLidar
+    try:
+        with cpu_stack():
+            N = 2
+            args = {"seed": 3, "sensor_noise_rng": mode} if mode == "device" else {"seed": 3, "reset_rng": "torch"}
+            env = SimBuilder().build_env("base_sim", "env_with_obstacles", "base_quadrotor_with_lidar", "lee_velocity_control", "cpu", args=args,
+                                         num_envs=N, use_warp=True, headless=True)
+            assert env.sensor.noise_enabled and env.sensor_noise_rng == mode and (env._device_noise is not None) == (mode == "device")
+            assert env.sensor.c.fuse_epilogue == 0
+            env.reset()
+            gtd = env.get_obs()
+            torch.manual_seed(5)
+            env.render()
+            px = gtd["depth_range_pixels"].clone()
+            assert px.shape == (N, 1, 16, 32) and torch.isfinite(px).all() and (px <= 1.0).all() and (px >= -1.0).all()
+            env.sensor.noise_enabled = False  # the raw frame again, without the noise pass
+            env.render()
+            raw = gtd["depth_range_pixels"].clone().numpy()
+            env.sensor.noise_enabled = True
+            hit = raw < 999.0
+            if mode == "device":
+                c = env._device_noise.c
+                want = SN.noise_limits(raw, c.components, c.enable_noise, c.apply_limits, c.normalize, c.std_a, c.std_b, c.std_c, c.mean_offset,
+                                       c.pixel_dropout_prob, c.max_range, c.min_range, c.far_out_of_range_value, c.near_out_of_range_value,
+                                       env._device_noise.seed, 0, 0)
+                assert np.allclose(px.numpy()[hit], want[hit], rtol=1e-4, atol=1e-5) and env._device_noise.frame == 1
+            else:
+                t = torch.tensor(raw)
+                torch.manual_seed(5)
+                apply_noise_and_limits_torch(t, env.sensor_cfg)
+                assert torch.equal(px, t)
+            sel = hit & (raw > 0.3) & (raw < 5.0)
+            assert sel.any() and np.allclose(px.numpy()[sel], (raw[sel] + 0.05) / 10.0, atol=2e-4)
+    finally:
+        BaseQuadWithLidarCfg.sensor_config.lidar_config = old
