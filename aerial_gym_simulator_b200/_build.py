@@ -19,6 +19,7 @@ UNITS = [
     ("hp1_aux.cu", []),
     ("lidar_nav.cu", []),
     ("sensor_noise.cu", []),
+    ("obstacles.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

@@ -10,7 +10,6 @@
 #include "../../include/aerial_gym_b200.h"
 #include "agx_common.cuh"
 #include "lidar_nav_core.cuh"
-#include "obstacle_core.cuh"
 
 namespace {
 using namespace agx;
@@ -97,15 +96,6 @@ lidar_nav_obs_copy_kernel(long long total, int L, const float* __restrict__ lida
     obs[(size_t)e * obs_stride + 17 + k] = lidar_obs[i];
 }
 
-// dynamic_env obstacles: one thread per obstacle (obstacle_core.cuh)
-__global__ void __launch_bounds__(kEnvThreads)
-obstacle_step_kernel(long long total, float* __restrict__ state, int stride, const float* __restrict__ twist, float dt, int substeps,
-                     float lin_damp, float ang_damp) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    obstacle_step_item(i, state, stride, twist, dt, substeps, lin_damp, ang_damp);
-}
-
 inline int blocks_for(long long n) { return (int)((n + kEnvThreads - 1) / kEnvThreads); }
 
 }  // namespace
@@ -176,19 +166,6 @@ int agx_lidar_nav_obs(int num_envs, const float* robot_state, int robot_state_st
     const long long total = (long long)num_envs * num_lidar;
     lidar_nav_obs_copy_kernel<<<blocks_for(total), kEnvThreads, 0, (cudaStream_t)stream>>>(total, num_lidar, lidar_obs, obs, obs_stride);
     return agx_check_launch("lidar_nav_obs_copy_kernel");
-}
-
-int agx_obstacle_step(int num_envs, int num_assets, float* asset_state, int asset_stride, const float* twist, float dt, int substeps,
-                      float linear_damping, float angular_damping, void* stream) {
-    if (num_envs < 0 || num_assets < 0 || substeps < 0) return agx_set_error(AGX_E_INVALID, "agx_obstacle_step: negative size");
-    if (asset_stride < 13) return agx_set_error(AGX_E_INVALID, "agx_obstacle_step: asset_stride < 13");
-    if (!(dt > 0.0f)) return agx_set_error(AGX_E_INVALID, "agx_obstacle_step: dt must be > 0");
-    const long long total = (long long)num_envs * num_assets;
-    if (total == 0 || substeps == 0) return AGX_OK;
-    if (!asset_state) return agx_set_error(AGX_E_NULL, "agx_obstacle_step: asset_state is NULL");
-    obstacle_step_kernel<<<blocks_for(total), kEnvThreads, 0, (cudaStream_t)stream>>>(total, asset_state, asset_stride, twist, dt, substeps,
-                                                                                      linear_damping, angular_damping);
-    return agx_check_launch("obstacle_step_kernel");
 }
 
 }  // extern "C"
