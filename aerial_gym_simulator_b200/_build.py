@@ -20,6 +20,7 @@ UNITS = [
     ("lidar_nav.cu", []),
     ("sensor_noise.cu", []),
     ("obstacles.cu", []),
+    ("e2e_task.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

@@ -75,6 +75,12 @@ class AgxLidarNavRewardParams(C.Structure):
     _fields_ = [("v", C.c_float * 22)]
 
 
+class AgxE2ERewardParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("z_error_scale", "upright_gain2", "upright_exp2", "align_gain1", "align_exp1", "align_gain2",
+                                         "align_exp2", "angvel_gain", "hover_thrust", "towards_gain_pos", "towards_gain_neg",
+                                         "action_diff_gain", "crash_dist")]
+
+
 class AgxImuConfig(C.Structure):
     _fields_ = [("world_frame", C.c_int32), ("enable_noise", C.c_int32), ("enable_bias", C.c_int32), ("sqrt_dt", C.c_float),
                 ("g_world", C.c_float * 3), ("bias_std", C.c_float * 6), ("noise_std", C.c_float * 6), ("max_meas", C.c_float * 6)]
@@ -159,6 +165,8 @@ def load():
         "agx_lidar_nav_reward": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_float, C.POINTER(AgxLidarNavRewardParams)]
                                 + [C.c_void_p] * 4,
         "agx_lidar_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+        "agx_e2e_reward": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(AgxE2ERewardParams)] + [C.c_void_p] * 3,
+        "agx_e2e_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
         "agx_obstacle_step": [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p],
         "agx_hp2_noise_limits": [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(AgxHp2Noise), C.c_uint64, C.c_uint32, C.c_void_p],
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],
@@ -173,7 +181,8 @@ def load():
     if lib.agx_sizeof(3) != C.sizeof(AgxHp2Scene) or lib.agx_sizeof(4) != C.sizeof(AgxHp2Sensor):
         raise AgxError("HP2 ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(5) != C.sizeof(AgxNavRewardParams) or lib.agx_sizeof(6) != C.sizeof(AgxImuConfig) \
-            or lib.agx_sizeof(7) != C.sizeof(AgxLidarNavRewardParams) or lib.agx_sizeof(8) != C.sizeof(AgxHp2Noise):
+            or lib.agx_sizeof(7) != C.sizeof(AgxLidarNavRewardParams) or lib.agx_sizeof(8) != C.sizeof(AgxHp2Noise) \
+            or lib.agx_sizeof(9) != C.sizeof(AgxE2ERewardParams):
         raise AgxError("aux ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
             or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):

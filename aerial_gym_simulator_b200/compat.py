@@ -24,7 +24,8 @@ def install():
         return
     from . import config, control, env_manager, registry, robots, sensors, sim, task, utils
     from .sensors import imu_sensor
-    from .task import lidar_navigation_task, navigation_task, position_setpoint_task
+    from .task import (lidar_navigation_task, navigation_task, position_setpoint_task,
+                       position_setpoint_task_sim2real_end_to_end as e2e_task)
     from .utils import vae_encoder
     from .config import (PACKAGE_DIRECTORY, asset_config, controller_config, env_config, robot_config, sensor_config,
                          sim_config, task_config)
@@ -60,6 +61,12 @@ def install():
         "task.position_setpoint_task": _module("aerial_gym.task.position_setpoint_task", position_setpoint_task=position_setpoint_task,
                                                __path__=[]),
         "task.position_setpoint_task.position_setpoint_task": position_setpoint_task,
+        "task.position_setpoint_task_sim2real_end_to_end": _module(
+            "aerial_gym.task.position_setpoint_task_sim2real_end_to_end", position_setpoint_task_sim2real_end_to_end=e2e_task, __path__=[]),
+        "task.position_setpoint_task_sim2real_end_to_end.position_setpoint_task_sim2real_end_to_end": e2e_task,
+        "task.position_setpoint_task_sim2real_px4": _module(
+            "aerial_gym.task.position_setpoint_task_sim2real_px4", position_setpoint_task_sim2real_px4=e2e_task, __path__=[]),
+        "task.position_setpoint_task_sim2real_px4.position_setpoint_task_sim2real_px4": e2e_task,
         "utils.vae": _module("aerial_gym.utils.vae", vae_image_encoder=vae_encoder, __path__=[]),
         "utils.vae.vae_image_encoder": vae_encoder,
     }
@@ -77,6 +84,12 @@ def install():
             "aerial_gym.config.env_config.env_with_lidar_nav_obstacles", EnvWithLidarNavObstaclesCfg=env_config.EnvWithLidarNavObstaclesCfg),
         "config.env_config.dynamic_environment": _module(
             "aerial_gym.config.env_config.dynamic_environment", DynamicEnvironmentCfg=env_config.DynamicEnvironmentCfg),
+        "config.task_config.position_setpoint_task_sim2real_end_to_end_config": _module(
+            "aerial_gym.config.task_config.position_setpoint_task_sim2real_end_to_end_config",
+            task_config=task_config.position_setpoint_task_sim2real_end_to_end_config),
+        "config.task_config.position_setpoint_task_sim2real_px4_config": _module(
+            "aerial_gym.config.task_config.position_setpoint_task_sim2real_px4_config",
+            task_config=task_config.position_setpoint_task_sim2real_px4_config),
         "config.task_config.position_setpoint_task_config": _module(
             "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
         "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),

@@ -98,3 +98,10 @@ class DynamicEnvironmentCfg(EnvWithObstaclesCfg):
     class env_config:
         include_asset_type = {k: (k == "objects") for k in EnvWithObstaclesCfg.env_config.include_asset_type}
         asset_type_to_dict_map = {"objects": _ac.dynamic_object_asset_params}
+
+
+class EnvCfg2Ms(EmptyEnvCfg):
+    """config/env_config/env_config_2ms.py: the empty env with 5 physics steps per env step (used with the 2 ms sim config)"""
+    class env(EmptyEnvCfg.env):
+        num_physics_steps_per_env_step_mean = 5
+        render_viewer_every_n_steps = 2

@@ -4,8 +4,8 @@ Articulated robots (ROV, reconfigurable, Morphy) are out of the hot-path scope (
 import numpy as np
 
 from . import RESOURCES_DIRECTORY
-from .sensor_config import (BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, OSDome_64_Config, RSLidar_Airy_Config,
-                            pmd_flexx2_config)
+from .sensor_config import (BaseDepthCameraConfig, BaseImuConfig, BaseLidarConfig, BaseNormalFaceIDCameraConfig, OSDome_64_Config,
+                            RSLidar_Airy_Config, StereoCameraConfig, fake_radar_config, pmd_flexx2_config)
 
 PI = np.pi
 QUAD_ALLOCATION = [
@@ -127,6 +127,18 @@ class BaseQuadWithCameraImuCfg(BaseQuadCfg):
 class BaseQuadWithLidarCfg(BaseQuadCfg):
     class sensor_config(BaseQuadCfg.sensor_config):
         enable_lidar = True
+
+
+class BaseQuadWithFaceIDNormalCameraCfg(BaseQuadCfg):
+    class sensor_config(BaseQuadCfg.sensor_config):
+        enable_camera = True
+        camera_config = BaseNormalFaceIDCameraConfig
+
+
+class BaseQuadWithStereoCameraCfg(BaseQuadCfg):
+    class sensor_config(BaseQuadCfg.sensor_config):
+        enable_camera = True
+        camera_config = StereoCameraConfig
 
 
 class BaseQuadRootLinkControlCfg(BaseQuadCfg):
@@ -309,3 +321,44 @@ class LMF1Cfg(X500Cfg):
             motor_time_constant_increasing_min = 0.025
             motor_time_constant_increasing_max = 0.025
             thrust_to_torque_ratio = 0.05
+
+
+class LMF2RadarCfg(LMF2Cfg):
+    """config/robot_config/lmf2_radar_config.py: lmf2 with the 48 x 120 world-frame point-cloud "radar" instead of the camera"""
+    class sensor_config(LMF2Cfg.sensor_config):
+        enable_camera = False
+        enable_lidar = True
+        lidar_config = fake_radar_config
+
+
+class TinyPropCfg(BaseQuadCfg):
+    """config/robot_config/tinyprop_config.py (the sim2real end-to-end quadrotor)"""
+    class init_config:
+        min_init_state = [-0.7, -0.7, -0.7, -PI / 6, -PI / 6, -PI, 1.0, -0.5, -0.5, -0.5, -0.5, -0.5, -0.5]
+        max_init_state = [0.7, 0.7, 0.7, PI / 6, PI / 6, PI, 1.0, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5]
+
+    class disturbance:
+        enable_disturbance = False
+        prob_apply_disturbance = 0.02
+        max_force_and_torque_disturbance = [0.001, 0.001, 0.001, 0.00004, 0.00004, 0.00004]
+
+    class robot_asset(BaseQuadCfg.robot_asset):
+        asset_folder = f"{RESOURCES_DIRECTORY}/robots/tinyprop"
+        file = "tinyprop.urdf"
+        name = "tinyprop"
+
+    class control_allocator_config(BaseQuadCfg.control_allocator_config):
+        application_mask = [5, 6, 7, 8]
+        allocation_matrix = [[0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0], [-0.16, -0.16, 0.16, 0.16],
+                             [-0.16, 0.16, 0.16, -0.16], [-0.01, 0.01, -0.01, 0.01]]
+
+        class motor_model_config(BaseQuadCfg.control_allocator_config.motor_model_config):
+            motor_thrust_constant_min = 0.00001286412
+            motor_thrust_constant_max = 0.00001286412
+            motor_time_constant_increasing_min = 0.047
+            motor_time_constant_increasing_max = 0.047
+            motor_time_constant_decreasing_min = 0.047
+            motor_time_constant_decreasing_max = 0.047
+            max_thrust = 1.2
+            min_thrust = 0.2
+            integration_scheme = "rk4"

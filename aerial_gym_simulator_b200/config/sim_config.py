@@ -43,10 +43,44 @@ class BaseSimHeadlessConfig(BaseSimConfig):
 
 
 class SimCfg2Ms(BaseSimConfig):
+    """sim_config_2ms.py: a stand-alone class in the reference; only these values differ from BaseSimConfig"""
+    class viewer(BaseSimConfig.viewer):
+        camera_follow_transform_local_offset = [-1.0, 0.0, 0.2]
+        camera_follow_position_global_offset = [-1.0, 0.0, 0.4]
+
     class sim(BaseSimConfig.sim):
         dt = 0.002
 
+        class physx(BaseSimConfig.sim.physx):
+            num_velocity_iterations = 2
 
-class SimCfg4Ms(BaseSimConfig):
-    class sim(BaseSimConfig.sim):
+
+class SimCfg4Ms(SimCfg2Ms):
+    class sim(SimCfg2Ms.sim):
         dt = 0.004
+
+
+class BaseSimNoGravityConfig(BaseSimConfig):
+    """base_sim_no_gravity_config.py"""
+    class sim(BaseSimConfig.sim):
+        gravity = [0.0, 0.0, 0.0]
+
+
+class CustomSimConfig(BaseSimConfig):
+    """config/sim_config/custom_sim_config.py: the reference's example of a user-defined sim config (1 ms steps, gravity along +x)"""
+    class sim(BaseSimConfig.sim):
+        dt = 0.001
+        gravity = [+1.0, 0.0, 0.0]
+
+        class physx(BaseSimConfig.sim.physx):
+            num_threads = 5
+            solver_type = 1
+            num_position_iterations = 10
+            num_velocity_iterations = 15
+            contact_offset = 0.01
+            rest_offset = 0.01
+            bounce_threshold_velocity = 0.5
+            max_depenetration_velocity = 1.0
+            max_gpu_contact_pairs = 2**20
+            default_buffer_size_multiplier = 5
+            contact_collection = 0

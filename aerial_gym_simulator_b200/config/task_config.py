@@ -184,3 +184,46 @@ class lidar_navigation_task_config:
         out[:, 0:3] = 2 * clamped[:, 0:3]
         out[:, 3] = clamped[:, 3] * (math.pi / 3)
         return out
+
+
+def _rescale_motor_commands(actions, min_limit, max_limit):
+    """process_actions_for_task of the motor-command tasks (position_setpoint_task_sim2real_end_to_end_config.py:27-32)."""
+    import torch
+
+    actions_clipped = torch.clamp(actions, -1, 1)
+    return actions_clipped * (max_limit - min_limit) / 2 + (max_limit + min_limit) / 2
+
+
+class position_setpoint_task_sim2real_end_to_end_config:
+    """config/task_config/position_setpoint_task_sim2real_end_to_end_config.py (EVAL = False).  The action limits are plain lists
+    here (the reference builds CUDA tensors at import time); the task turns them into tensors on its device."""
+    seed = 56
+    sim_name = "base_sim"
+    env_name = "empty_env"
+    robot_name = "tinyprop"
+    controller_name = "no_control"
+    args = {}
+    num_envs = 4096
+    use_warp = False
+    headless = True
+    device = "cuda:0"
+    privileged_observation_space_dim = 0
+    action_space_dim = 4
+    observation_space_dim = 15
+    episode_len_steps = 600
+    return_state_before_reset = False
+    reward_parameters = {}
+    crash_dist = 1.5
+    action_limit_max = [1.2] * 4
+    action_limit_min = [0.2] * 4
+    process_actions_for_task = staticmethod(_rescale_motor_commands)
+
+
+class position_setpoint_task_sim2real_px4_config(position_setpoint_task_sim2real_end_to_end_config):
+    """config/task_config/position_setpoint_task_sim2real_px4_config.py (EVAL = False)"""
+    robot_name = "x500"
+    num_envs = 24
+    episode_len_steps = 500
+    crash_dist = 6.5
+    action_limit_max = [8.0] * 4
+    action_limit_min = [0.0] * 4

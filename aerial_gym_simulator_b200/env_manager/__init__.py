@@ -8,9 +8,11 @@ env_config_registry.register("empty_env", _ec.EmptyEnvCfg)
 env_config_registry.register("env_with_obstacles", _ec.EnvWithObstaclesCfg)
 env_config_registry.register("env_with_lidar_nav_obstacles", _ec.EnvWithLidarNavObstaclesCfg)
 env_config_registry.register("dynamic_env", _ec.DynamicEnvironmentCfg)
+env_config_registry.register("empty_env_2ms", _ec.EnvCfg2Ms)
 sim_config_registry.register("base_sim", _sc.BaseSimConfig)
 sim_config_registry.register("base_sim_headless", _sc.BaseSimHeadlessConfig)
 sim_config_registry.register("base_sim_2ms", _sc.SimCfg2Ms)
 sim_config_registry.register("base_sim_4ms", _sc.SimCfg4Ms)
+sim_config_registry.register("custom_sim", _sc.CustomSimConfig)
 
 from .env_manager import EnvManager  # noqa: E402,F401

@@ -97,5 +97,7 @@ for _name, _cfg in (
     ("x500", rc.X500Cfg), ("magpie", rc.MagpieCfg), ("base_quadrotor_with_imu", rc.BaseQuadWithImuCfg),
     ("base_quadrotor_with_camera", rc.BaseQuadWithCameraCfg), ("base_quadrotor_with_camera_imu", rc.BaseQuadWithCameraImuCfg),
     ("base_quadrotor_with_lidar", rc.BaseQuadWithLidarCfg),
+    ("base_quadrotor_with_faceid_normal_camera", rc.BaseQuadWithFaceIDNormalCameraCfg),
+    ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg),
 ):
     robot_registry.register(_name, BaseMultirotor, _cfg)

@@ -164,7 +164,7 @@ int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
  * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor,
- * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams, 8 AgxHp2Noise */
+ * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams, 8 AgxHp2Noise, 9 AgxE2ERewardParams */
 uint64_t agx_sizeof(int which);
 
 /* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
@@ -299,6 +299,35 @@ int agx_lidar_nav_obs(int num_envs, const float* robot_state, int robot_state_st
                       const float* target_position, const float* target_yaw, const float* u_vec, const float* u_euler,
                       const float* lidar_obs, int num_lidar, float* obs, int obs_stride, void* stream);
 
+
+/* ---- motor-command ("end to end") position tasks: position_setpoint_task_sim2real_end_to_end / _px4 ------ */
+
+/* the constants in which the two tasks' compute_reward differ
+ * (task/position_setpoint_task_sim2real_end_to_end/...py:267-311 | task/position_setpoint_task_sim2real_px4/...py:268-312) */
+typedef struct AgxE2ERewardParams {
+    float z_error_scale;                 /* 11 | 13        (:283) */
+    float upright_gain2, upright_exp2;   /* 0, 0 | 2.5, 2  (:288) */
+    float align_gain1, align_exp1;       /* 6, 5 | 4, 5    (:292) */
+    float align_gain2, align_exp2;       /* 0, 0 | 2, 2 */
+    float angvel_gain;                   /* 0.3 | 0.75     (:294) */
+    float hover_thrust;                  /* 9.81 * 0.372 / 4 | 9.81 * 1.6559999883174896 / 4   (:297) */
+    float towards_gain_pos, towards_gain_neg; /* 10, 15 | 50, 100 (:301) */
+    float action_diff_gain;              /* 1.3 | 0.5      (:304) */
+    float crash_dist;                    /* task_config.crash_dist */
+} AgxE2ERewardParams;
+
+/* compute_rewards_and_crashes + compute_reward.  robot_state [N,stride] (position 0..2, orientation xyzw 3..6, WORLD linear velocity
+ * 7..9), body_angvel [N,3] (robot_body_angvel, stale like the reference's), target_position [N,3] or NULL (= 0), actions /
+ * prev_actions [N,4] (motor commands after process_actions_for_task), prev_pos_error [N,3]; crashes [N] bool: OR-ed with
+ * |pos error| > crash_dist; rewards [N] out. */
+int agx_e2e_reward(int num_envs, const float* robot_state, int robot_state_stride, const float* body_angvel, const float* target_position,
+                   const float* actions, const float* prev_actions, const float* prev_pos_error, const AgxE2ERewardParams* params,
+                   uint8_t* crashes, float* rewards, void* stream);
+
+/* process_obs_for_task (:204-229): obs[:, 0:15] = noisy position error (3), rotation-6D of the noisy ZYX Euler angles (6), noisy WORLD
+ * linear velocity (3), noisy body rates (3).  noise [N,12]: the four torch.normal draws in the method's order, side by side. */
+int agx_e2e_obs(int num_envs, const float* robot_state, int robot_state_stride, const float* body_angvel, const float* target_position,
+                const float* noise, float* obs, int obs_stride, void* stream);
 
 /* ---- dynamic obstacles ("dynamic_env": env_manager/obstacle_manager.py:40-44 + PhysX) ------------------- */
 

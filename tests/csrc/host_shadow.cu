@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../aerial_gym_simulator_b200/csrc/aux_core.cuh"
+#include "../../aerial_gym_simulator_b200/csrc/e2e_task_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/hp1_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/noise_core.cuh"
@@ -100,6 +101,16 @@ void shadow_nav_obs(int n, const float* state, int stride, const float* veh_q, c
 void shadow_imu_update(int n, const AgxImuConfig* c, const float* force, int force_stride, const float* mass, const float* state, int stride,
                        const float* bav, const float* sensor_q, const float* n_noise, const float* n_bias, float* bias, float* meas) {
     for (int e = 0; e < n; ++e) imu_env(e, *c, force, force_stride, mass, state, stride, bav, sensor_q, n_noise, n_bias, bias, meas);
+}
+
+// stand in for e2e_reward_kernel / e2e_obs_kernel (e2e_task.cu)
+void shadow_e2e_reward(int n, const float* state, int stride, const float* body_angvel, const float* target, const float* act,
+                       const float* prev_act, const float* prev_pos_err, const AgxE2ERewardParams* p, uint8_t* crashes, float* rewards) {
+    for (int e = 0; e < n; ++e) e2e_reward_env(e, state, stride, body_angvel, target, act, prev_act, prev_pos_err, *p, crashes, rewards);
+}
+void shadow_e2e_obs(int n, const float* state, int stride, const float* body_angvel, const float* target, const float* noise, float* obs,
+                    int obs_stride) {
+    for (int e = 0; e < n; ++e) e2e_obs_env(e, state, stride, body_angvel, target, noise, obs, obs_stride);
 }
 
 // stands in for obstacle_step_kernel: one "thread" per obstacle

@@ -71,7 +71,7 @@ def test_sensor_config(mod, name):
     _compare(_ref("sensor_config." + mod, name), getattr(S, name))
 
 
-ROBOTS = {"base_quad_config": "BaseQuadCfg", "base_octarotor_config": "BaseOctarotorCfg", "lmf2_config": "LMF2Cfg", "magpie_config": "MagpieCfg",
+ROBOTS = {"tinyprop_config": "TinyPropCfg", "lmf2_radar_config": "LMF2RadarCfg", "base_quad_config": "BaseQuadCfg", "base_octarotor_config": "BaseOctarotorCfg", "lmf2_config": "LMF2Cfg", "magpie_config": "MagpieCfg",
           "x500_config": "X500Cfg", "lmf1_config": "LMF1Cfg", "base_quad_root_link_control_config": "BaseQuadRootLinkControlCfg"}
 
 
@@ -108,8 +108,19 @@ def test_env_sim_task_asset_configs():
         assert on == set(ours.env_config.asset_type_to_dict_map), (on, set(ours.env_config.asset_type_to_dict_map))
         for k in on:  # every asset class that is switched on: all its parameters
             _compare(ref.env_config.asset_type_to_dict_map[k], ours.env_config.asset_type_to_dict_map[k], skip=("asset_folder",))
-    for name, ours in (("BaseSimConfig", SC.BaseSimConfig),):
-        _compare(_ref("sim_config.base_sim_config", name), ours)
+    for mod, name, ours in (("base_sim_config", "BaseSimConfig", SC.BaseSimConfig), ("base_sim_headless_config", "BaseSimHeadlessConfig", SC.BaseSimHeadlessConfig),
+                            ("sim_config_2ms", "SimCfg2Ms", SC.SimCfg2Ms), ("sim_config_4ms", "SimCfg4Ms", SC.SimCfg4Ms),
+                            ("custom_sim_config", "CustomSimConfig", SC.CustomSimConfig),
+                            ("base_sim_no_gravity_config", "BaseSimNoGravityConfig", SC.BaseSimNoGravityConfig)):
+        _compare(_ref("sim_config." + mod, name), ours)
+    _compare(_ref("env_config.env_config_2ms", "EnvCfg2Ms"), EC.EnvCfg2Ms, skip=("asset_type_to_dict_map", "include_asset_type"))
+    for name in ("BaseQuadWithImuCfg", "BaseQuadWithCameraCfg", "BaseQuadWithCameraImuCfg", "BaseQuadWithLidarCfg",
+                 "BaseQuadWithFaceIDNormalCameraCfg", "BaseQuadWithStereoCameraCfg"):
+        ref, ours = _ref("robot_config.base_quad_config", name), getattr(RC, name)
+        for k in ("enable_camera", "enable_lidar", "enable_imu"):
+            assert getattr(ref.sensor_config, k) == getattr(ours.sensor_config, k), (name, k)
+        for k in ("camera_config", "lidar_config", "imu_config"):
+            assert getattr(ref.sensor_config, k).__name__ == getattr(ours.sensor_config, k).__name__, (name, k)
     for mod, ours in (("position_setpoint_task_config", TC.position_setpoint_task_config), ("navigation_task_config", TC.navigation_task_config),
                       ("lidar_navigation_task_config", TC.lidar_navigation_task_config)):
         _compare(_ref("task_config." + mod, "task_config"), ours, skip=("model_file", "model_folder", "headless", "device"))

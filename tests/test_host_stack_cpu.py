@@ -10,6 +10,7 @@ import torch
 import aerial_gym_simulator_b200.task  # noqa: F401
 from aerial_gym_simulator_b200.registry._core import task_registry
 from aerial_gym_simulator_b200.sim import SimBuilder
+from oracle import e2e_task_oracle as E
 from oracle import lidar_nav_oracle as L
 from oracle import obstacle_oracle as OB
 from oracle import sensor_noise_oracle as SN
@@ -197,3 +198,55 @@ def test_env_manager_noisy_lidar(mode):
             assert sel.any() and np.allclose(px.numpy()[sel], (raw[sel] + 0.05) / 10.0, atol=2e-4)
     finally:
         BaseQuadWithLidarCfg.sensor_config.lidar_config = old
+
+
+@pytest.mark.parametrize("name,tag", [("position_setpoint_task_sim2real_end_to_end", "end_to_end"), ("position_setpoint_task_sim2real_px4", "px4")])
+def test_motor_command_tasks_end_to_end(cpu_task, name, tag):
+    """tinyprop / x500 + no_control: policy actions -> motor commands -> physics -> reward, crash, truncation, (double) reset, noisy
+    rotation-6D observation; every stage against the oracle on the task's own tensors"""
+    N = 40
+    task = cpu_task(name, seed=3, num_envs=N)
+    assert task.sim_env.spec.num_motors == 4 and task.task_config.observation_space_dim == 15
+    obs, rew, term, trunc, info = task.reset()
+    assert obs["observations"].shape == (N, 15) and torch.isfinite(obs["observations"]).all()
+    od = task.obs_dict
+    g = torch.Generator().manual_seed(1)
+    p = dict(E.E2E_PARAMS[tag])
+    for step in range(4):
+        a = torch.rand(N, 4, generator=g) * 2.4 - 1.2  # beyond [-1, 1]: clipped by process_actions_for_task
+        prev_act, prev_err = task.actions.clone(), task.prev_pos_error.clone()
+        task.sim_env.sim_steps[5] = task.task_config.episode_len_steps if step == 2 else task.sim_env.sim_steps[5]  # force one truncation
+        ep_before = task.sim_env.engine.episode_count.clone()
+        out = task.step(a)
+        assert out[0] is obs and out[1] is rew
+        lo, hi = task.action_limit_min, task.action_limit_max
+        assert torch.allclose(task.actions, torch.clamp(a, -1, 1) * (hi - lo) / 2 + (hi + lo) / 2) and torch.equal(task.prev_actions, task.actions)
+        assert torch.equal(prev_act, prev_act)  # (kept for the reward check below)
+        if step == 2:
+            assert bool(trunc[5]) and int(trunc.sum()) == 1
+            assert int(task.sim_env.engine.episode_count[5]) == int(ep_before[5]) + 2  # reset by the env AND again by task.reset_idx (:146-156)
+            assert int(task.sim_env.sim_steps[5]) == 0
+        assert torch.allclose(task.prev_pos_error, task.target_position - od["robot_position"])
+    assert torch.isfinite(rew).all() and torch.isfinite(obs["observations"]).all()
+    # reward stage on the current tensors
+    crashes_in = od["crashes"].clone()
+    task.compute_rewards_and_crashes(od)
+    want, cr = E.compute_reward(task.target_position - od["robot_position"], od["robot_orientation"], od["robot_linvel"], od["robot_body_angvel"],
+                                crashes_in, task.actions, task.prev_actions, task.prev_pos_error, task.task_config.crash_dist, p)
+    assert torch.allclose(task.rewards, want, rtol=1e-5, atol=3e-4) and torch.equal(od["crashes"], cr)
+    # observation stage with given draws
+    noise = torch.randn(N, 12) * 0.01
+    task.process_obs_for_task(noise)
+    want_obs = E.process_obs(od["robot_position"], od["robot_orientation"], od["robot_linvel"], od["robot_body_angvel"], task.target_position, noise)
+    assert torch.allclose(obs["observations"], want_obs, rtol=1e-5, atol=1e-5)
+    r6 = obs["observations"][:, 3:9].view(N, 2, 3)  # two orthonormal rows of a rotation matrix
+    assert torch.allclose((r6 * r6).sum(-1), torch.ones(N, 2), atol=1e-5) and ((r6[:, 0] * r6[:, 1]).sum(-1).abs() < 1e-5).all()
+    # the reference's draw order and scales: four [N,3] normals with std 1e-3, pi/1032, 2e-3, 1e-3
+    calls, real = [], torch.normal
+    torch.normal = lambda mean, std: (calls.append((tuple(mean.shape), float(std))), real(mean=mean, std=std))[1]
+    try:
+        task.process_obs_for_task()
+    finally:
+        torch.normal = real
+    assert calls == [((N, 3), 0.001), ((N, 3), torch.pi / 1032), ((N, 3), 0.002), ((N, 3), 0.001)]
+    task.close()
