@@ -312,29 +312,29 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 d = update_states(s);
                 float ref[M];
                 if (cfg.controller == AGX_CTRL_NONE) {  // update_motor_thrusts_with_forces
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                     for (int i = 0; i < M; ++i) ref[i] = act[i];
                 } else {
                     float wr[6];
                     controller_wrench(cfg, s, d, p.g, act, wr);
                     // f_ref = pinv(A) w   control/control_allocation.py:87-89
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                     for (int i = 0; i < M; ++i) {
                         float acc = 0.0f;
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                         for (int j = 0; j < 6; ++j) acc += cfg.alloc_pinv[i * 6 + j] * wr[j];
                         ref[i] = acc;
                     }
                 }
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                 for (int i = 0; i < M; ++i) p.thrust[i] = motor_update(cfg, p.thrust[i], ref[i], p.tau_inc[i], p.tau_dec[i], p.k[i]);
                 // thrust -> base-frame wrench about the COM (control_allocation.py:103-114 applied
                 // link-local, IGE_env_manager.py:444-449)
                 float w6[6];
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                 for (int j = 0; j < 6; ++j) {
                     float acc = 0.0f;
-#pragma unroll
+AGX_HP1_MOTOR_UNROLL
                     for (int i = 0; i < M; ++i) acc += cfg.wrench_map[j * AGX_MAX_MOTORS + i] * p.thrust[i];
                     w6[j] = acc;
                 }

@@ -7,6 +7,15 @@
 #include "../../include/aerial_gym_b200.h"
 #include "agx_math.cuh"
 
+// Loops over the motors inside one physics sub-step (hp1.cu, between the AGX_SHADOW markers): fully unrolled by default.
+// -DAGX_HP1_ROLL_MOTORS keeps them rolled -- a round-2 experiment for the instruction-fetch side of the latency-bound step
+// (tools/build_variant.py); the arithmetic is the same either way.
+#ifdef AGX_HP1_ROLL_MOTORS
+#define AGX_HP1_MOTOR_UNROLL _Pragma("unroll 1")
+#else
+#define AGX_HP1_MOTOR_UNROLL _Pragma("unroll")
+#endif
+
 namespace agx {
 
 struct EnvState {

@@ -28,17 +28,22 @@ def _extract_kernel_blocks():
 
 
 def build(force=False):
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in _DEPS):
+    # AGX_SHADOW_FLAGS: extra -D flags, to run the CPU suite on a build VARIANT of the device code (tools/build_variant.py)
+    extra = os.environ.get("AGX_SHADOW_FLAGS", "").split()
+    stamp = LIB + ".flags"
+    same_flags = os.path.exists(stamp) and open(stamp).read().split() == extra
+    if not force and same_flags and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in _DEPS):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     _extract_kernel_blocks()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     # host code only is used; nvcc is the compiler because the headers are CUDA headers (float4, __host__ __device__)
     cmd = [nvcc, "-x", "cu", "-DAGX_HOST_SHADOW", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
-           "-Xcompiler", "-fPIC,-ffp-contract=off", "-I", os.path.dirname(LIB), "-shared", "-o", LIB, SRC]
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-I", os.path.dirname(LIB), "-shared", "-o", LIB, SRC] + extra
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("host shadow build failed:\n" + r.stdout + r.stderr)
+    open(stamp, "w").write(" ".join(extra))
     return LIB
 
 
