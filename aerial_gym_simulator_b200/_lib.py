@@ -72,7 +72,7 @@ class AgxNavRewardParams(C.Structure):
 
 
 class AgxLidarNavRewardParams(C.Structure):
-    _fields_ = [("v", C.c_float * 22)]
+    _fields_ = [("v", C.c_float * 22), ("radar_variant", C.c_int32)]
 
 
 class AgxE2ERewardParams(C.Structure):

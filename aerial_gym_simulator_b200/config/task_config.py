@@ -227,3 +227,10 @@ class position_setpoint_task_sim2real_px4_config(position_setpoint_task_sim2real
     crash_dist = 6.5
     action_limit_max = [8.0] * 4
     action_limit_min = [0.0] * 4
+
+
+class radar_navigation_task_config(lidar_navigation_task_config):
+    """config/task_config/radar_navigation_task_config.py: the LiDAR-navigation config on lmf2_radar in env_with_obstacles"""
+    env_name = "env_with_obstacles"
+    robot_name = "lmf2_radar"
+    controller_name = "lmf2_acceleration_control"

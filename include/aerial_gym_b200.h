@@ -276,6 +276,9 @@ int agx_lidar_nav_pool(int num_envs, int height, int width, int pool_h, int pool
  * {x,y,z,yawrate}_absolute_action_penalty_{magnitude,exponent}, collision_penalty */
 typedef struct AgxLidarNavRewardParams {
     float v[22];
+    int32_t radar_variant; /* 0: LiDARNavigationTask.  1: RadarNavigationTask (task/radar_navigation_task/radar_navigation_task.py), whose
+                              compute_reward differs in one term: the x-velocity penalty is taken on clamp(vx, max=0) instead of
+                              clamp(vx, min=0) (:251 there vs lidar_navigation_task.py:619) */
 } AgxLidarNavRewardParams;
 
 /* LiDARNavigationTask.compute_rewards_and_crashes + compute_reward (:471-499, :554-720).

@@ -61,8 +61,20 @@ def add_noise(ds, generator=None):
     return ds
 
 
+def add_noise_radar(ds, generator=None):
+    """RadarNavigationTask.add_noise_to_downsampled_lidar_data (radar_navigation_task.py:7-21): 3 % of the pixels get +U(0.2, 10),
+    then 80 % are invalidated (-1).  In place, returns ds."""
+    g = generator
+    noise_mask = torch.bernoulli(0.03 * torch.ones_like(ds), generator=g)
+    n = int((noise_mask == 1).sum())
+    ds[noise_mask == 1] += (10.0 - 0.2) * torch.rand(n, generator=g) + 0.2
+    invalid = torch.bernoulli(0.8 * torch.ones_like(ds), generator=g)
+    ds[invalid == 1] = -1.0
+    return ds
+
+
 def compute_reward(pos_error, vehicle_linvel, body_angvel, yaw_error, crashes, action, prev_action, time_to_collision,
-                   curriculum_progress_fraction, p):
+                   curriculum_progress_fraction, p, radar_variant=False):
     """compute_reward, lidar_navigation_task.py:554-720 (prev_pos_error is an argument there but is not used).
     p: dict name -> float (LIDAR_NAV_PARAM_NAMES)."""
     f = curriculum_progress_fraction
@@ -79,7 +91,8 @@ def compute_reward(pos_error, vehicle_linvel, body_angvel, yaw_error, crashes, a
                              -0.2 * torch.ones_like(vdc)) * torch.min(dist / 3.0, torch.ones_like(dist))  # :596-599
     vel_mag_pen = _epf(2.0, 2.0, torch.clamp(vn - 3.0, min=0.0))                    # :603-607
     close_to_goal = 1.0 - _erf(1.0, 2.0, dist)                                      # :609-613
-    neg_x_pen = _epf(2.0, 8.0, torch.clamp(vehicle_linvel[:, 0], min=0.0)) * close_to_goal  # :616-620
+    vx = torch.clamp(vehicle_linvel[:, 0], max=0.0) if radar_variant else torch.clamp(vehicle_linvel[:, 0], min=0.0)
+    neg_x_pen = _epf(2.0, 8.0, vx) * close_to_goal  # :616-620 (radar_navigation_task.py:251: max=0.0)
     vel_pen = vel_mag_pen + neg_x_pen                                               # :622
     low_vel = _erf(1.5, 10.0, vn) + _erf(1.5, 0.5, vn)                              # :625
     correct_yaw = _erf(2.0, 0.2, yaw_error) + _erf(4.0, 15.0, yaw_error)            # :630
@@ -104,12 +117,12 @@ def compute_reward(pos_error, vehicle_linvel, body_angvel, yaw_error, crashes, a
 
 
 def rewards_and_errors(vehicle_orientation, position, target, euler, target_yaw, vehicle_linvel, body_angvel, crashes, action,
-                       prev_action, time_to_collision, curriculum_progress_fraction, p):
+                       prev_action, time_to_collision, curriculum_progress_fraction, p, radar_variant=False):
     """compute_rewards_and_crashes, lidar_navigation_task.py:471-499.  Returns (reward, pos_error)."""
     err = O.quat_rotate_inverse(vehicle_orientation, target - position)            # :480-482
     yaw_error = O.ssa(target_yaw - O.ssa(euler)[:, 2])                              # :483-484
     return compute_reward(err, vehicle_linvel, body_angvel, yaw_error, crashes, action, prev_action, time_to_collision,
-                          curriculum_progress_fraction, p), err
+                          curriculum_progress_fraction, p, radar_variant), err
 
 
 def process_obs(vehicle_orientation, position, target, euler, target_yaw, body_linvel, body_angvel, robot_actions, lidar_obs,

@@ -26,6 +26,7 @@ from make_golden_aux import _funcs_from, _Recorder, rand_unit_quat  # noqa: E402
 
 from aerial_gym.utils import math as ref_math  # noqa: E402
 
+RADAR_PATH = os.path.join(_ref_loader.REF_ROOT, "aerial_gym/task/radar_navigation_task/radar_navigation_task.py")
 TASK_PATH = os.path.join(_ref_loader.REF_ROOT, "aerial_gym/task/lidar_navigation_task/lidar_navigation_task.py")
 CFG_PATH = os.path.join(_ref_loader.REF_ROOT, "aerial_gym/config/task_config/lidar_navigation_task_config.py")
 NOISE_SEED = 1234
@@ -110,6 +111,22 @@ def gen_reward_obs(ns, out, seed=41, n=96):
     ttc = torch.rand(n, generator=g) * 10.0
     ttc[:6] = torch.tensor([0.0, 0.05, 0.3, 1.0, 10.0, 0.6])
     lidar = torch.rand(n, 320, generator=g) * 5.0
+    rns = dict(ns)  # RadarNavigationTask: its own module-level compute_reward (one term differs) + its noise method
+    _funcs_from(RADAR_PATH, {"exponential_reward_function", "exponential_penalty_function", "compute_reward"}, rns)
+    rns["erf"], rns["epf"] = rns["exponential_reward_function"], rns["exponential_penalty_function"]
+    _funcs_from(RADAR_PATH, {"compute_rewards_and_crashes", "add_noise_to_downsampled_lidar_data"}, rns, in_class="RadarNavigationTask")
+    for tag, frac in (("c0", 0.0), ("c1", 0.4444444477558136)):
+        mr = types.SimpleNamespace(
+            obs_dict={"robot_position": pos, "robot_vehicle_orientation": veh_q, "robot_orientation": q, "robot_euler_angles": euler,
+                      "robot_vehicle_linvel": veh_linvel, "robot_body_angvel": body_angvel, "crashes": crashes.clone()},
+            target_position=target, device="cpu", pos_error_vehicle_frame_prev=torch.zeros(n, 3),
+            pos_error_vehicle_frame=prev_err.clone(), target_yaw=target_yaw, current_action=act, prev_action=prev_act,
+            time_to_collision=ttc, curriculum_progress_fraction=frac, task_config=types.SimpleNamespace(reward_parameters=pt))
+        out[f"radar_reward_{tag}"] = rns["compute_rewards_and_crashes"](mr, mr.obs_dict)[0].numpy().copy()
+    ds = torch.rand(6, 16, 20, generator=g) * 9.0 + 0.3
+    torch.manual_seed(NOISE_SEED)
+    out["radar_noise_in"] = ds.numpy().copy()
+    out["radar_noise_out"] = rns["add_noise_to_downsampled_lidar_data"](types.SimpleNamespace(device="cpu"), ds.clone()).numpy()
     for tag, frac in (("c0", 0.0), ("c1", 0.4444444477558136)):
         me = types.SimpleNamespace(
             obs_dict={"robot_position": pos, "robot_vehicle_orientation": veh_q, "robot_orientation": q, "robot_euler_angles": euler,

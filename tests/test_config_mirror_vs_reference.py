@@ -122,5 +122,5 @@ def test_env_sim_task_asset_configs():
         for k in ("camera_config", "lidar_config", "imu_config"):
             assert getattr(ref.sensor_config, k).__name__ == getattr(ours.sensor_config, k).__name__, (name, k)
     for mod, ours in (("position_setpoint_task_config", TC.position_setpoint_task_config), ("navigation_task_config", TC.navigation_task_config),
-                      ("lidar_navigation_task_config", TC.lidar_navigation_task_config)):
+                      ("lidar_navigation_task_config", TC.lidar_navigation_task_config), ("radar_navigation_task_config", TC.radar_navigation_task_config)):
         _compare(_ref("task_config." + mod, "task_config"), ours, skip=("model_file", "model_folder", "headless", "device"))

@@ -250,3 +250,28 @@ def test_motor_command_tasks_end_to_end(cpu_task, name, tag):
         torch.normal = real
     assert calls == [((N, 3), 0.001), ((N, 3), torch.pi / 1032), ((N, 3), 0.002), ((N, 3), 0.001)]
     task.close()
+
+
+def test_radar_navigation_task_end_to_end(cpu_task):
+    """RadarNavigationTask = the LiDAR task on lmf2_radar (48 x 120 world-frame "fake radar" cloud) in env_with_obstacles, with the
+    radar noise (80 % of the pooled pixels invalidated) and the radar variant of the reward"""
+    N = 3
+    task = cpu_task("radar_navigation_task", seed=9, num_envs=N)
+    od = task.obs_dict
+    assert od["depth_range_pixels"].shape == (N, 1, 48, 120, 3) and task.sim_env.scene.K >= 44 and task._params.radar_variant == 1
+    assert task.sim_env.robot_cfg.sensor_config.lidar_config.__name__ == "fake_radar_config"
+    obs, rew, term, trunc, info = task.reset()
+    for _ in range(2):
+        obs, rew, term, trunc, info = task.step(torch.rand(N, 4) * 0.6 - 0.3)
+    ds = task.downsampled_lidar_data
+    assert torch.isfinite(ds).all() and 0.6 < float((ds == -1.0).float().mean()) < 0.95  # 1 / (-1): the invalidated pixels
+    assert torch.equal(obs["observations"][:, 17:], ds) and torch.isfinite(rew).all()
+    d = np.load(__file__.replace("test_host_stack_cpu.py", "golden/lidar_nav_task_epilogue.npz"))
+    p = {k: float(v) for k, v in zip(d["param_names"], d["param_values"])}
+    task.compute_rewards_and_crashes(od)
+    args = (od["robot_vehicle_orientation"], od["robot_position"], task.target_position, od["robot_euler_angles"], task.target_yaw,
+            od["robot_vehicle_linvel"], od["robot_body_angvel"], od["crashes"], task.current_action, task.prev_action, task.time_to_collision,
+            task.curriculum_progress_fraction, p)
+    want, _ = L.rewards_and_errors(*args, radar_variant=True)
+    assert torch.allclose(task.rewards, want, rtol=1e-5, atol=2e-4)
+    task.close()

@@ -120,7 +120,7 @@ def test_shadow_pool_matches_oracle_any_shape(H, W, ph, pw):
     np.testing.assert_allclose(ttc, want_ttc.numpy(), rtol=2e-5, atol=1e-6)
 
 
-def _shadow_reward(d_or_arrays, frac, params):
+def _shadow_reward(d_or_arrays, frac, params, radar=False):
     lib = _shadow.load()
     a = d_or_arrays
     n = a["pos"].shape[0]
@@ -130,11 +130,15 @@ def _shadow_reward(d_or_arrays, frac, params):
                                                                   "body_angvel")]
     keep.append(_c(np.asarray(a["crashes"]).astype(np.uint8)))
     keep += [_c(np.asarray(a[k], np.float32)) for k in ("actions", "prev_actions", "time_to_collision")]
-    p = (C.c_float * 22)(*[float(params[k]) for k in L.LIDAR_NAV_PARAM_NAMES])
+    from aerial_gym_simulator_b200 import _lib
+    p = _lib.AgxLidarNavRewardParams()
+    for i, k in enumerate(L.LIDAR_NAV_PARAM_NAMES):
+        p.v[i] = float(params[k])
+    p.radar_variant = int(radar)
     pe = np.array(a["prev_pos_error"], np.float32, copy=True)
     pp, rew = np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
     ptr = [k[1] for k in keep]
-    lib.shadow_lidar_nav_reward(n, ptr[0], 13, *ptr[1:], float(frac), C.cast(p, C.c_void_p), pe.ctypes.data_as(C.c_void_p),
+    lib.shadow_lidar_nav_reward(n, ptr[0], 13, *ptr[1:], float(frac), C.cast(C.byref(p), C.c_void_p), pe.ctypes.data_as(C.c_void_p),
                                 pp.ctypes.data_as(C.c_void_p), rew.ctypes.data_as(C.c_void_p))
     return rew, pe, pp
 
@@ -186,3 +190,30 @@ def test_shadow_obs_matches_reference_fixture(obs_stride, num_lidar):
                              obs.ctypes.data_as(C.c_void_p), obs_stride)
     np.testing.assert_allclose(obs[:, :17 + num_lidar], d["obs"][:, :17 + num_lidar], rtol=1e-5, atol=1e-5)
     assert (obs[:, 17 + num_lidar:] == 7.0).all()  # nothing beyond the requested columns is touched
+
+
+# ------------------------------------------------------------------------------------------------ RadarNavigationTask variant
+@pytest.mark.parametrize("tag", ["c0", "c1"])
+def test_radar_variant_matches_reference_fixture(tag):
+    """RadarNavigationTask's own compute_reward (radar_navigation_task.py: the x-velocity penalty on clamp(vx, max=0)): oracle and
+    device code against the fixture produced by that file's function"""
+    d = np.load(G)
+    ref = d[f"radar_reward_{tag}"]
+    assert not np.array_equal(ref, d[f"reward_{tag}"])  # the variant matters on this input
+    rew, _ = L.rewards_and_errors(_t(d["vehicle_orientation"]), _t(d["pos"]), _t(d["target"]), _t(d["euler"]), _t(d["target_yaw"]),
+                                  _t(d["vehicle_linvel"]), _t(d["body_angvel"]), _t(d["crashes"]), _t(d["actions"]), _t(d["prev_actions"]),
+                                  _t(d["time_to_collision"]), float(d[f"frac_{tag}"]), _params_dict(d), radar_variant=True)
+    assert torch.allclose(rew, _t(ref), rtol=1e-6, atol=1e-6)
+    got, _, _ = _shadow_reward(d, d[f"frac_{tag}"], _params_dict(d), radar=True)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_radar_noise_matches_reference_fixture():
+    from aerial_gym_simulator_b200.task.radar_navigation_task import add_noise_to_downsampled_radar_data
+
+    d = np.load(G)
+    torch.manual_seed(int(d["pool_noise_seed"]))
+    assert torch.equal(L.add_noise_radar(_t(d["radar_noise_in"]).clone()), _t(d["radar_noise_out"]))
+    torch.manual_seed(int(d["pool_noise_seed"]))
+    out = add_noise_to_downsampled_radar_data(_t(d["radar_noise_in"]).clone())
+    assert torch.equal(out, _t(d["radar_noise_out"])) and 0.7 < float((out == -1.0).float().mean()) < 0.9

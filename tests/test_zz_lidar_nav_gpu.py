@@ -221,3 +221,41 @@ def test_lidar_navigation_task_end_to_end():
                              od["robot_actions"].cpu(), task.downsampled_lidar_data.cpu(), u1.cpu(), u2.cpu())
     assert torch.allclose(obs["observations"].cpu(), want_obs, rtol=1e-5, atol=1e-5)
     task.close()
+
+
+@pytest.mark.parametrize("tag", ["c0", "c1"])
+def test_radar_variant_reward_kernel_matches_reference_fixture(tag):
+    """RadarNavigationTask's compute_reward (one term differs from the LiDAR task's)"""
+    d = np.load(G)
+    params, _ = _params(d)
+    params.radar_variant = 1
+    rew, _, _ = _reward_gpu(d, d[f"frac_{tag}"], params)
+    ref = torch.tensor(d[f"radar_reward_{tag}"])
+    assert torch.allclose(rew, ref, rtol=1e-5, atol=1e-4), (rew - ref).abs().max()
+
+
+def test_radar_navigation_task_end_to_end():
+    import aerial_gym_simulator_b200.task  # noqa: F401
+    from aerial_gym_simulator_b200.registry._core import task_registry
+
+    N = 8
+    task = task_registry.make_task("radar_navigation_task", seed=9, num_envs=N, headless=True)
+    od = task.obs_dict
+    assert od["depth_range_pixels"].shape == (N, 1, 48, 120, 3) and task._params.radar_variant == 1
+    obs, rew, term, trunc, info = task.reset()
+    for _ in range(3):
+        obs, rew, term, trunc, info = task.step(torch.rand(N, 4, device=DEV) * 0.6 - 0.3)
+    torch.cuda.synchronize()
+    ds = task.downsampled_lidar_data
+    assert torch.isfinite(ds).all() and 0.6 < float((ds == -1.0).float().mean()) < 0.95
+    assert torch.equal(obs["observations"][:, 17:], ds) and torch.isfinite(rew).all()
+    _, p = _params(np.load(G))
+    task.compute_rewards_and_crashes(od)
+    torch.cuda.synchronize()
+    c = lambda t: t.cpu()
+    want, _ = L.rewards_and_errors(c(od["robot_vehicle_orientation"]), c(od["robot_position"]), c(task.target_position), c(od["robot_euler_angles"]),
+                                   c(task.target_yaw), c(od["robot_vehicle_linvel"]), c(od["robot_body_angvel"]), c(od["crashes"]),
+                                   c(task.current_action), c(task.prev_action), c(task.time_to_collision), task.curriculum_progress_fraction, p,
+                                   radar_variant=True)
+    assert torch.allclose(c(task.rewards), want, rtol=1e-5, atol=2e-4)
+    task.close()
