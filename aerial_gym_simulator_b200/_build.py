@@ -21,6 +21,7 @@ UNITS = [
     ("sensor_noise.cu", []),
     ("obstacles.cu", []),
     ("e2e_task.cu", []),
+    ("sim2real.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

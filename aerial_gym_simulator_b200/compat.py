@@ -25,7 +25,8 @@ def install():
     from . import config, control, env_manager, registry, robots, sensors, sim, task, utils
     from .sensors import imu_sensor
     from .task import (lidar_navigation_task, navigation_task, position_setpoint_task,
-                       position_setpoint_task_sim2real_end_to_end as e2e_task, radar_navigation_task)
+                       position_setpoint_task_sim2real as s2r_task, position_setpoint_task_sim2real_end_to_end as e2e_task,
+                       radar_navigation_task)
     from .utils import vae_encoder
     from .config import (PACKAGE_DIRECTORY, asset_config, controller_config, env_config, robot_config, sensor_config,
                          sim_config, task_config)
@@ -69,6 +70,12 @@ def install():
         "task.position_setpoint_task_sim2real_px4.position_setpoint_task_sim2real_px4": e2e_task,
         "task.radar_navigation_task": _module("aerial_gym.task.radar_navigation_task", radar_navigation_task=radar_navigation_task, __path__=[]),
         "task.radar_navigation_task.radar_navigation_task": radar_navigation_task,
+        "task.position_setpoint_task_sim2real": _module(
+            "aerial_gym.task.position_setpoint_task_sim2real", position_setpoint_task_sim2real=s2r_task, __path__=[]),
+        "task.position_setpoint_task_sim2real.position_setpoint_task_sim2real": s2r_task,
+        "task.position_setpoint_task_acceleration_sim2real": _module(
+            "aerial_gym.task.position_setpoint_task_acceleration_sim2real", position_setpoint_task_acceleration_sim2real=s2r_task, __path__=[]),
+        "task.position_setpoint_task_acceleration_sim2real.position_setpoint_task_acceleration_sim2real": s2r_task,
         "utils.vae": _module("aerial_gym.utils.vae", vae_image_encoder=vae_encoder, __path__=[]),
         "utils.vae.vae_image_encoder": vae_encoder,
     }
@@ -94,6 +101,11 @@ def install():
             task_config=task_config.position_setpoint_task_sim2real_px4_config),
         "config.task_config.radar_navigation_task_config": _module(
             "aerial_gym.config.task_config.radar_navigation_task_config", task_config=task_config.radar_navigation_task_config),
+        "config.task_config.position_setpoint_task_sim2real_config": _module(
+            "aerial_gym.config.task_config.position_setpoint_task_sim2real_config", task_config=task_config.position_setpoint_task_sim2real_config),
+        "config.task_config.position_setpoint_task_acceleration_sim2real_config": _module(
+            "aerial_gym.config.task_config.position_setpoint_task_acceleration_sim2real_config",
+            task_config=task_config.position_setpoint_task_acceleration_sim2real_config),
         "config.task_config.position_setpoint_task_config": _module(
             "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
         "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),

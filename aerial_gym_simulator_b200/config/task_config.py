@@ -234,3 +234,28 @@ class radar_navigation_task_config(lidar_navigation_task_config):
     env_name = "env_with_obstacles"
     robot_name = "lmf2_radar"
     controller_name = "lmf2_acceleration_control"
+
+
+class position_setpoint_task_sim2real_config:
+    """config/task_config/position_setpoint_task_sim2real_config.py"""
+    seed = 1
+    sim_name = "base_sim"
+    env_name = "empty_env"
+    robot_name = "lmf2"
+    controller_name = "lmf2_velocity_control"
+    args = {}
+    num_envs = 16
+    use_warp = False
+    headless = False
+    device = "cuda:0"
+    observation_space_dim = 17
+    privileged_observation_space_dim = 0
+    action_space_dim = 4
+    episode_len_steps = 800
+    return_state_before_reset = False
+    reward_parameters = {}
+
+
+class position_setpoint_task_acceleration_sim2real_config(position_setpoint_task_sim2real_config):
+    """config/task_config/position_setpoint_task_acceleration_sim2real_config.py"""
+    controller_name = "lmf2_acceleration_control"

@@ -332,6 +332,24 @@ int agx_e2e_reward(int num_envs, const float* robot_state, int robot_state_strid
 int agx_e2e_obs(int num_envs, const float* robot_state, int robot_state_stride, const float* body_angvel, const float* target_position,
                 const float* noise, float* obs, int obs_stride, void* stream);
 
+/* ---- setpoint-command sim2real position tasks: position_setpoint_task_sim2real / _acceleration_sim2real (lmf2) ---- */
+
+/* compute_rewards_and_crashes + compute_reward (task/position_setpoint_task_sim2real/...py:230-339, variant 0;
+ * task/position_setpoint_task_acceleration_sim2real/...py:239-356, variant 1).  robot_state [N,stride] (position 0..2, orientation
+ * 3..6), vehicle_orientation [N,4], body_linvel [N,3] (both stale like the reference's), target_position [N,3] or NULL, prev_dist [N]
+ * (distance to the target before the step), actions / prev_actions [N,4]: variant 0 = the task's actions / prev_actions; variant 1 =
+ * the actions (rotated in the kernel by vehicle_orientation -> actions_vehicle_frame [N,4] out, may be NULL) /
+ * prev_actions_vehicle_frame.  crashes [N] bool in/out (|= distance > 10), rewards [N] out (-50 where crashed). */
+int agx_s2r_reward(int num_envs, int variant, const float* robot_state, int robot_state_stride, const float* vehicle_orientation,
+                   const float* body_linvel, const float* target_position, const float* prev_dist, const float* actions,
+                   const float* prev_actions, float* actions_vehicle_frame, uint8_t* crashes, float* rewards, void* stream);
+
+/* process_obs_for_task (:202-228): obs[:, 0:17] = noisy position error, quaternion of the noisy Euler angles, noisy body velocities,
+ * robot_actions.  noise [N,12]: the four torch.randn_like draws (euler, position, body linvel, body angvel) side by side, unscaled.
+ * robot_state's orientation is multiplied by sign(qw) IN PLACE, as the reference does (:204-207). */
+int agx_s2r_obs(int num_envs, float* robot_state, int robot_state_stride, const float* body_linvel, const float* body_angvel,
+                const float* robot_actions, const float* target_position, const float* noise, float* obs, int obs_stride, void* stream);
+
 /* ---- dynamic obstacles ("dynamic_env": env_manager/obstacle_manager.py:40-44 + PhysX) ------------------- */
 
 /* Kinematic advance of every obstacle by `substeps` physics steps of `dt`.  asset_state [N,A,asset_stride] rows

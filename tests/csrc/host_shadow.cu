@@ -18,6 +18,7 @@
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/noise_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/obstacle_core.cuh"
+#include "../../aerial_gym_simulator_b200/csrc/sim2real_core.cuh"
 
 using namespace agx;
 
@@ -111,6 +112,16 @@ void shadow_e2e_reward(int n, const float* state, int stride, const float* body_
 void shadow_e2e_obs(int n, const float* state, int stride, const float* body_angvel, const float* target, const float* noise, float* obs,
                     int obs_stride) {
     for (int e = 0; e < n; ++e) e2e_obs_env(e, state, stride, body_angvel, target, noise, obs, obs_stride);
+}
+
+// stand in for s2r_reward_kernel / s2r_obs_kernel (sim2real.cu)
+void shadow_s2r_reward(int n, int variant, const float* state, int stride, const float* veh_q, const float* body_linvel, const float* target,
+                       const float* prev_dist, const float* act, const float* prev_act, float* act_vehicle_out, uint8_t* crashes, float* rewards) {
+    for (int e = 0; e < n; ++e) s2r_reward_env(e, variant, state, stride, veh_q, body_linvel, target, prev_dist, act, prev_act, act_vehicle_out, crashes, rewards);
+}
+void shadow_s2r_obs(int n, float* state, int stride, const float* body_linvel, const float* body_angvel, const float* robot_actions,
+                    const float* target, const float* noise, float* obs, int obs_stride) {
+    for (int e = 0; e < n; ++e) s2r_obs_env(e, state, stride, body_linvel, body_angvel, robot_actions, target, noise, obs, obs_stride);
 }
 
 // stands in for obstacle_step_kernel: one "thread" per obstacle

@@ -14,6 +14,7 @@ from oracle import e2e_task_oracle as E
 from oracle import lidar_nav_oracle as L
 from oracle import obstacle_oracle as OB
 from oracle import sensor_noise_oracle as SN
+from oracle import sim2real_oracle as S2R
 
 from ._cpu_stack import cpu_stack
 
@@ -274,4 +275,44 @@ def test_radar_navigation_task_end_to_end(cpu_task):
             task.curriculum_progress_fraction, p)
     want, _ = L.rewards_and_errors(*args, radar_variant=True)
     assert torch.allclose(task.rewards, want, rtol=1e-5, atol=2e-4)
+    task.close()
+
+
+@pytest.mark.parametrize("name,variant", [("position_setpoint_task_sim2real", 0), ("position_setpoint_task_acceleration_sim2real", 1)])
+def test_setpoint_sim2real_tasks_end_to_end(cpu_task, name, variant):
+    """lmf2 + velocity / acceleration control: bookkeeping quirks (the caller's action tensor is adopted, and scaled in place by the
+    acceleration task), reward / crash / observation stages against the oracle on the task's own tensors"""
+    N = 16
+    task = cpu_task(name, seed=2, num_envs=N)
+    obs, rew, term, trunc, info = task.reset()
+    assert obs["observations"].shape == (N, 17) and torch.isfinite(obs["observations"]).all()
+    od = task.obs_dict
+    assert (od["robot_orientation"][:, 3] >= 0).all()  # process_obs_for_task normalised the sign in place
+    g = torch.Generator().manual_seed(3)
+    for _ in range(3):
+        a = torch.rand(N, 4, generator=g) * 2 - 1
+        a0, prev = a.clone(), task.actions.clone()
+        pos_before, q_before = od["robot_position"].clone(), od["robot_orientation"].clone()
+        out = task.step(a)
+        assert out[0] is obs and task.actions is a
+        assert torch.equal(a[:, 0:3], 2.0 * a0[:, 0:3]) if variant else torch.equal(a, a0)
+        assert torch.equal(task.prev_actions, prev) and torch.allclose(task.prev_dist, (task.target_position - pos_before).norm(dim=1))
+        if variant:
+            from aerial_gym_simulator_b200.utils.math import quat_rotate
+            assert torch.allclose(task.prev_actions_vehicle_frame[:, 0:3], quat_rotate(q_before, prev[:, 0:3]))
+        assert torch.equal(obs["observations"][:, 13:17], od["robot_actions"])
+    crashes_in = od["crashes"].clone()
+    task.compute_rewards_and_crashes(od)
+    want, cr, act = S2R.reward(variant, od["robot_position"], od["robot_orientation"], od["robot_vehicle_orientation"], od["robot_body_linvel"],
+                               task.target_position, task.prev_dist, task.actions, task.prev_actions_vehicle_frame if variant else task.prev_actions,
+                               crashes_in)
+    assert torch.allclose(task.rewards, want, rtol=1e-5, atol=2e-3) and torch.equal(od["crashes"], cr)
+    if variant:
+        assert torch.allclose(task.actions_vehicle_frame, act, atol=1e-6)
+    noise = torch.randn(N, 12)
+    od["robot_orientation"][::2] *= -1.0
+    pos, q = od["robot_position"].clone(), od["robot_orientation"].clone()
+    task.process_obs_for_task(noise)
+    want_obs, q_after = S2R.process_obs(pos, q, od["robot_body_linvel"], od["robot_body_angvel"], od["robot_actions"], task.target_position, noise)
+    assert torch.allclose(obs["observations"], want_obs, rtol=1e-5, atol=1e-5) and torch.equal(od["robot_orientation"], q_after)
     task.close()
