@@ -362,3 +362,47 @@ class TinyPropCfg(BaseQuadCfg):
             max_thrust = 1.2
             min_thrust = 0.2
             integration_scheme = "rk4"
+
+
+class BaseRandCfg(BaseQuadCfg):
+    """config/robot_config/base_random_config.py: an 8-rotor vehicle with arbitrarily placed, arbitrarily tilted rotors
+    (resources/robots/random/random.urdf) -- the generic case of the per-link wrench map"""
+    class init_config:
+        min_init_state = [0.0, 0.0, 0.0, 0, 0, -PI, 1.0, -0.2, -0.2, -0.2, -0.2, -0.2, -0.2]
+        max_init_state = [1.0, 1.0, 1.0, 0, 0, PI, 1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]
+
+    class disturbance:
+        enable_disturbance = True
+        prob_apply_disturbance = 0.05
+        max_force_and_torque_disturbance = [1.5, 1.5, 1.5, 0.25, 0.25, 0.25]
+
+    class robot_asset(BaseQuadCfg.robot_asset):
+        asset_folder = f"{RESOURCES_DIRECTORY}/robots/random"
+        file = "random.urdf"
+        name = "base_random"
+        angular_damping = 0.0000001
+        linear_damping = 0.0000001
+        min_state_ratio = [0.1, 0.1, 0.1, 0, 0, -PI, 1.0, -0.5, -0.5, -0.5, -0.2, -0.2, -0.2]
+        max_state_ratio = [0.3, 0.9, 0.9, 0, 0, PI, 1.0, 0.5, 0.5, 0.5, 0.2, 0.2, 0.2]
+
+    class control_allocator_config(BaseQuadCfg.control_allocator_config):
+        num_motors = 8
+        application_mask = [1 + 8 + i for i in range(0, 8)]
+        motor_directions = [-1, 1, -1, 1, -1, 1, -1, 1]
+        allocation_matrix = [
+            [5.55111512e-17, -0.321393805, -0.454519478, -0.342020143, 0.96984631, 0.342020143, 0.866025404, -0.754406507],
+            [1.0, -0.342020143, -0.707106781, 0.0, -0.173648178, 0.939692621, 0.5, -0.173648178],
+            [1.66533454e-16, -0.883022222, 0.54167522, 0.939692621, 0.171010072, 1.11022302e-16, 1.11022302e-16, 0.633022222],
+            [0.175, 0.123788742, -0.0569783368, 0.134977168, 0.0336959042, -0.266534135, -0.078839746, -0.0206893989],
+            [0.01, 0.278845133, -0.0432852308, -0.272061766, -0.197793856, 0.0863687139, 0.156554446, -0.17126129],
+            [0.282487373, -0.14173549, -0.0858541103, 0.0384858939, -0.333468026, 0.0836741468, 0.00846777988, -0.0874336259],
+        ]
+
+        class motor_model_config(BaseQuadCfg.control_allocator_config.motor_model_config):
+            use_rps = False
+            motor_time_constant_increasing_min = 0.01
+            motor_time_constant_increasing_max = 0.03
+            motor_time_constant_decreasing_min = 0.005
+            motor_time_constant_decreasing_max = 0.005
+            max_thrust = 5.0
+            min_thrust = -5.0

@@ -98,6 +98,6 @@ for _name, _cfg in (
     ("base_quadrotor_with_camera", rc.BaseQuadWithCameraCfg), ("base_quadrotor_with_camera_imu", rc.BaseQuadWithCameraImuCfg),
     ("base_quadrotor_with_lidar", rc.BaseQuadWithLidarCfg),
     ("base_quadrotor_with_faceid_normal_camera", rc.BaseQuadWithFaceIDNormalCameraCfg),
-    ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg),
+    ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg), ("base_random", rc.BaseRandCfg),
 ):
     robot_registry.register(_name, BaseMultirotor, _cfg)
