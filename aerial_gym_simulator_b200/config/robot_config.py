@@ -406,3 +406,21 @@ class BaseRandCfg(BaseQuadCfg):
             motor_time_constant_decreasing_max = 0.005
             max_thrust = 5.0
             min_thrust = -5.0
+
+
+class BaseROVCfg(BaseOctarotorCfg):
+    """config/robot_config/base_rov_config.py: BlueROV2 with the octarotor's tilted-thruster allocation, no per-env gain randomisation
+    on the robot side, disturbances on"""
+    class init_config:
+        min_init_state = [0.0, 0.0, 0.0, 0, 0, -PI, 1.0, -0.2, -0.2, -0.2, -0.2, -0.2, -0.2]
+        max_init_state = [1.0, 1.0, 1.0, 0, 0, PI, 1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]
+
+    class disturbance:
+        enable_disturbance = True
+        prob_apply_disturbance = 0.05
+        max_force_and_torque_disturbance = [1.5, 1.5, 1.5, 0.25, 0.25, 0.25]
+
+    class robot_asset(BaseOctarotorCfg.robot_asset):
+        asset_folder = f"{RESOURCES_DIRECTORY}/robots/BlueROV"
+        file = "rov.urdf"
+        name = "base_rov"

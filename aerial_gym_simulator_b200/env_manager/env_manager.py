@@ -306,6 +306,11 @@ class EnvManager:
         mask = torch.zeros(N, dtype=torch.bool, device=dev)
         mask[env_ids] = True
         A = gtd["num_obstacles_in_env"]
+        # robots whose reset leaves the motor model alone (BaseROV, robots/base_rov.py:188-201): put it back after the engine's reset
+        motor_names = ("motor_thrust", "tau_inc", "tau_dec", "k_thrust")
+        saved_motors = None
+        if getattr(self.robot, "keeps_motor_state_on_reset", False) and getattr(self, "_motors_initialised", False):
+            saved_motors = {k: getattr(eng, k).clone() for k in motor_names if getattr(eng, k, None) is not None}
         if self.reset_rng == "device":
             # Philox reset of bounds + robot + motor/controller params in one launch; the asset
             # sampling below only needs the new bounds (reference order: bounds -> assets -> robot,
@@ -334,6 +339,10 @@ class EnvManager:
             if self.spec.use_rps:
                 draws["k_thrust"] = r(N, M)
             eng.reset(mask, draws)
+        if saved_motors is not None:
+            for k, t in saved_motors.items():
+                getattr(eng, k)[env_ids] = t[env_ids]
+        self._motors_initialised = True
         if self.sensor is not None and self.sensor_cfg.randomize_placement:  # warp_sensor.py:153-172
             k, S = len(env_ids), self.sensor_cfg.num_sensors
             t0, t1, e0, e1 = self._mount_rng

@@ -91,6 +91,17 @@ class BaseMultirotor:
         )
 
 
+class BaseROV(BaseMultirotor):
+    """robots/base_rov.py: a fully actuated rigid body with eight thrusters (BlueROV2 geometry, gravity on, no buoyancy model in the
+    reference either).  On the HP1 path it differs from BaseMultirotor in two bookkeeping points:
+      * reset_idx does NOT touch the motor model (:188-201: no control_allocator.reset_idx) -- thrusts and time constants survive a
+        reset; EnvManager.reset_idx restores them after the engine's reset (after the very first one, which stands in for
+        MotorModel.init_tensors' initial draw);
+      * robot_euler_angles is left in [0, 2 pi) (:245, no ssa).  Here the GTD tensor keeps the wrapped (-pi, pi] angles of the fused
+        update_states; no controller of the ROV reads it (FullyActuatedController works on quaternions)."""
+    keeps_motor_state_on_reset = True
+
+
 for _name, _cfg in (
     ("base_quadrotor", rc.BaseQuadCfg), ("base_octarotor", rc.BaseOctarotorCfg),
     ("base_quad_root_link_control", rc.BaseQuadRootLinkControlCfg), ("lmf1", rc.LMF1Cfg), ("lmf2", rc.LMF2Cfg),
@@ -101,3 +112,4 @@ for _name, _cfg in (
     ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg), ("base_random", rc.BaseRandCfg),
 ):
     robot_registry.register(_name, BaseMultirotor, _cfg)
+robot_registry.register("base_rov", BaseROV, rc.BaseROVCfg)

@@ -338,3 +338,31 @@ def test_generic_eight_rotor_robot_steps():
         assert torch.allclose(gtd["robot_orientation"].norm(dim=1), torch.ones(32), atol=1e-5)
         v_forward = gtd["robot_vehicle_linvel"][:, 0]  # the velocity controller pulls the vehicle-frame x velocity towards 0.5 m/s
         assert v_forward.mean() > 0.2 and (gtd["robot_position"] - p0).norm(dim=1).mean() > 0.05
+
+
+def test_rov_fully_actuated_and_motor_state_survives_reset():
+    """base_rov + rov_fully_actuated_control (7-D pose command): holds a pose setpoint; BaseROV.reset_idx leaves the motor model alone
+    (robots/base_rov.py:188-201), so thrusts / time constants of a reset env survive (after the first, initialising reset)"""
+    with cpu_stack():
+        N = 24
+        env = SimBuilder().build_env("base_sim", "empty_env", "base_rov", "rov_fully_actuated_control", "cpu", args={"seed": 6}, num_envs=N,
+                                     use_warp=False, headless=True)
+        assert env.spec.num_motors == 8 and env.num_robot_actions == 7 and env.robot.keeps_motor_state_on_reset
+        env.reset()
+        gtd, eng = env.get_obs(), env.engine
+        assert (eng.motor_thrust != 0).any()  # the first reset initialised the motor model
+        a = torch.zeros(N, 7)
+        a[:, 6] = 1.0  # position (0, 0, 0), identity orientation
+        d0 = gtd["robot_position"].norm(dim=1).clone()
+        for _ in range(150):
+            env.step(actions=a)
+        assert torch.isfinite(gtd["robot_state_tensor"]).all() and (gtd["robot_position"].norm(dim=1) < d0).float().mean() > 0.8
+        thrust, tau = eng.motor_thrust.clone(), eng.tau_inc.clone()
+        pos = gtd["robot_position"].clone()
+        ids = torch.tensor([1, 5, 7])
+        env.reset_idx(ids)
+        assert torch.equal(eng.motor_thrust, thrust) and torch.equal(eng.tau_inc, tau)       # motor model untouched, everywhere
+        assert not torch.equal(gtd["robot_position"][ids], pos[ids])                           # ... while the state was re-drawn
+        keep = torch.ones(N, dtype=torch.bool)
+        keep[ids] = False
+        assert torch.equal(gtd["robot_position"][keep], pos[keep])
