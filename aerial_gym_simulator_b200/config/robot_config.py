@@ -424,3 +424,31 @@ class BaseROVCfg(BaseOctarotorCfg):
         asset_folder = f"{RESOURCES_DIRECTORY}/robots/BlueROV"
         file = "rov.urdf"
         name = "base_rov"
+
+
+class MorphyStiffCfg(BaseQuadCfg):
+    """config/robot_config/morphy_stiff_config.py: the Morphy airframe with its arm joints welded (every joint of morphy_stiff.urdf is
+    fixed) -- a plain rigid quadrotor; the compliant-arm Morphy itself needs joint dynamics and is out of scope"""
+    class init_config:
+        min_init_state = [0.0, 0.0, 0.0, 0, 0, -PI / 6, 1.0, -0.2, -0.2, -0.2, -0.2, -0.2, -0.2]
+        max_init_state = [1.0, 1.0, 1.0, 0, 0, PI / 6, 1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]
+
+    class disturbance(BaseQuadCfg.disturbance):
+        enable_disturbance = True
+
+    class robot_asset(BaseQuadCfg.robot_asset):
+        asset_folder = f"{RESOURCES_DIRECTORY}/robots/morphy"
+        file = "morphy_stiff.urdf"
+        flip_visual_attachments = False
+
+    class control_allocator_config(BaseQuadCfg.control_allocator_config):
+        application_mask = [3, 6, 9, 12]
+        allocation_matrix = [[0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0], [-0.0785, -0.0785, 0.0785, 0.0785],
+                             [-0.0785, 0.0785, 0.0785, -0.0785], [-0.01, 0.01, -0.01, 0.01]]
+
+        class motor_model_config(BaseQuadCfg.control_allocator_config.motor_model_config):
+            use_rps = False
+            motor_time_constant_increasing_min = 0.01
+            motor_time_constant_increasing_max = 0.03
+            motor_time_constant_decreasing_min = 0.005
+            motor_time_constant_decreasing_max = 0.005

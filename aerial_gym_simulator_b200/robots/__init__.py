@@ -109,7 +109,7 @@ for _name, _cfg in (
     ("base_quadrotor_with_camera", rc.BaseQuadWithCameraCfg), ("base_quadrotor_with_camera_imu", rc.BaseQuadWithCameraImuCfg),
     ("base_quadrotor_with_lidar", rc.BaseQuadWithLidarCfg),
     ("base_quadrotor_with_faceid_normal_camera", rc.BaseQuadWithFaceIDNormalCameraCfg),
-    ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg), ("base_random", rc.BaseRandCfg),
+    ("base_quadrotor_with_stereo_camera", rc.BaseQuadWithStereoCameraCfg), ("lmf2_radar", rc.LMF2RadarCfg), ("tinyprop", rc.TinyPropCfg), ("base_random", rc.BaseRandCfg), ("morphy_stiff", rc.MorphyStiffCfg),
 ):
     robot_registry.register(_name, BaseMultirotor, _cfg)
 robot_registry.register("base_rov", BaseROV, rc.BaseROVCfg)

@@ -71,7 +71,7 @@ def test_sensor_config(mod, name):
     _compare(_ref("sensor_config." + mod, name), getattr(S, name))
 
 
-ROBOTS = {"base_rov_config": "BaseROVCfg", "base_random_config": "BaseRandCfg", "tinyprop_config": "TinyPropCfg", "lmf2_radar_config": "LMF2RadarCfg", "base_quad_config": "BaseQuadCfg", "base_octarotor_config": "BaseOctarotorCfg", "lmf2_config": "LMF2Cfg", "magpie_config": "MagpieCfg",
+ROBOTS = {"morphy_stiff_config": "MorphyStiffCfg", "base_rov_config": "BaseROVCfg", "base_random_config": "BaseRandCfg", "tinyprop_config": "TinyPropCfg", "lmf2_radar_config": "LMF2RadarCfg", "base_quad_config": "BaseQuadCfg", "base_octarotor_config": "BaseOctarotorCfg", "lmf2_config": "LMF2Cfg", "magpie_config": "MagpieCfg",
           "x500_config": "X500Cfg", "lmf1_config": "LMF1Cfg", "base_quad_root_link_control_config": "BaseQuadRootLinkControlCfg"}
 
 

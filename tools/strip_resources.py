@@ -72,7 +72,7 @@ if __name__ == "__main__":
               "lmf2/model.urdf": "robots/lmf2/model.urdf", "lmf1/model.urdf": "robots/lmf1/model.urdf",
               "x500/model.urdf": "robots/x500/model.urdf", "magpie/model.urdf": "robots/magpie/model.urdf",
               "tinyprop/tinyprop.urdf": "robots/tinyprop/tinyprop.urdf", "random/random.urdf": "robots/random/random.urdf",
-              "BlueROV/rov.urdf": "robots/BlueROV/rov.urdf"}
+              "BlueROV/rov.urdf": "robots/BlueROV/rov.urdf", "morphy/morphy_stiff.urdf": "robots/morphy/morphy_stiff.urdf"}
     for s, d in robots.items():
         sp = os.path.join(SRC, "robots", s)
         if os.path.exists(sp):
