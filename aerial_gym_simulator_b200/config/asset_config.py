@@ -117,3 +117,15 @@ class dynamic_object_asset_params(object_asset_params):
     num_assets = 40          # dynamic_env_object_config.py:274
     disable_gravity = True   # :28
     fix_base_link = False    # :41
+
+
+class tree_asset_params(asset_state_params):
+    """config/asset_config/env_object_config.py:225-270: a trunk + branches made of cylinders, one segmentation id per link"""
+    num_assets = 1
+    asset_folder = f"{_ENV_ASSETS}/trees"
+    min_state_ratio, max_state_ratio = _ratio((0.1, 0.1, 0.0), (0.9, 0.9, 0.0), (0, -PI / 6.0, -PI), (0, PI / 6.0, PI))
+    collapse_fixed_joints = True
+    per_link_semantic = True
+    keep_in_env = True
+    semantic_id = -1
+    color = [70, 200, 100]

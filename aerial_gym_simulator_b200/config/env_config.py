@@ -105,3 +105,17 @@ class EnvCfg2Ms(EmptyEnvCfg):
     class env(EmptyEnvCfg.env):
         num_physics_steps_per_env_step_mean = 5
         render_viewer_every_n_steps = 2
+
+
+class ForestEnvCfg(EnvWithObstaclesCfg):
+    """config/env_config/forest_env.py: a tree (cylinders, per-link segmentation), 35 objects and the floor in a 10 x 10 x 4 m box"""
+    class env(EnvWithObstaclesCfg.env):
+        collision_force_threshold = 0.005
+        lower_bound_min = [-5.0, -5.0, -1.0]
+        lower_bound_max = [-5.0, -5.0, -1.0]
+        upper_bound_min = [5.0, 5.0, 3.0]
+        upper_bound_max = [5.0, 5.0, 3.0]
+
+    class env_config:
+        include_asset_type = {"trees": True, "objects": True, "bottom_wall": True}
+        asset_type_to_dict_map = {"trees": _ac.tree_asset_params, "objects": _ac.object_asset_params, "bottom_wall": _ac.bottom_wall}

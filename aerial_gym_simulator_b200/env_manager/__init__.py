@@ -9,6 +9,7 @@ env_config_registry.register("env_with_obstacles", _ec.EnvWithObstaclesCfg)
 env_config_registry.register("env_with_lidar_nav_obstacles", _ec.EnvWithLidarNavObstaclesCfg)
 env_config_registry.register("dynamic_env", _ec.DynamicEnvironmentCfg)
 env_config_registry.register("empty_env_2ms", _ec.EnvCfg2Ms)
+env_config_registry.register("forest_env", _ec.ForestEnvCfg)
 sim_config_registry.register("base_sim", _sc.BaseSimConfig)
 sim_config_registry.register("base_sim_headless", _sc.BaseSimHeadlessConfig)
 sim_config_registry.register("base_sim_2ms", _sc.SimCfg2Ms)

@@ -182,19 +182,21 @@ class EnvManager:
         gtd["obstacle_linvel"], gtd["obstacle_angvel"] = ast[..., 7:10], ast[..., 10:13]
         lo = np.zeros((N, A, 13), np.float32)
         hi = np.zeros((N, A, 13), np.float32)
-        # templates: every <box> visual of every distinct URDF; an asset with b boxes = b objects
-        tmpl_index, templates, tmpl_obbs, boxes_of = {}, [], [], {}
+        # templates: every <box> / <cylinder> visual of every distinct URDF; an asset with b parts = b objects sharing its pose
+        # (a box is one part, a tessellated cylinder eleven: urdf.visual_parts)
+        tmpl_index, templates, tmpl_obbs, boxes_of, tmpl_link = {}, [], [], {}, []
         for e in range(N):
             for a, (params, path) in enumerate(per_env[e]):
                 lo[e, a], hi[e, a] = params.min_state_ratio, params.max_state_ratio
                 if path not in boxes_of:
                     model = urdf.parse_urdf(path)
                     ids = []
-                    for _, tris, obb in urdf.box_visual_triangles(model, params.use_collision_mesh_instead_of_visual):
+                    for _, link_index, tris, obb in urdf.visual_parts(model, params.use_collision_mesh_instead_of_visual):
                         tmpl_index[(path, len(ids))] = len(templates)
                         ids.append(len(templates))
                         templates.append(tris)
                         tmpl_obbs.append(obb)
+                        tmpl_link.append(link_index)
                     boxes_of[path] = ids
         gtd["asset_min_state_ratio"].copy_(torch.from_numpy(lo))
         gtd["asset_max_state_ratio"].copy_(torch.from_numpy(hi))
@@ -212,14 +214,18 @@ class EnvManager:
         for e in range(N):
             k = 0
             for a, (params, path) in enumerate(per_env[e]):
+                per_link = bool(getattr(params, "per_link_semantic", False))
                 for t in boxes_of[path]:
                     obj_t[e, k], obj_asset[e, k] = t, a
-                    if params.semantic_id < 0:  # per-instance id = counter (warp_asset.py:100-104, warp_env_manager.py:76-80)
+                    if per_link:  # one id per link: link counter + the env's running counter (warp_asset.py:44-70, e.g. the trees)
+                        seg_base[t], seg_mask[t], obj_c[e, k] = tmpl_link[t], 1, seg_ctr
+                    elif params.semantic_id < 0:  # per-instance id = counter (warp_asset.py:100-104, warp_env_manager.py:76-80)
                         seg_base[t], seg_mask[t], obj_c[e, k] = 0, 1, seg_ctr
                     else:
                         seg_base[t], seg_mask[t], obj_c[e, k] = params.semantic_id, 0, 0
                     k += 1
-                seg_ctr += 1
+                # the running counter advances by the number of distinct variable ids the asset used (warp_env_manager.py:90-95)
+                seg_ctr += (max(tmpl_link[t] for t in boxes_of[path]) + 1) if (per_link and boxes_of[path]) else 1
             while k < K:  # pad ragged envs with a repeat of the last object (same pose, same id)
                 obj_t[e, k], obj_c[e, k], obj_asset[e, k] = obj_t[e, k - 1], obj_c[e, k - 1], obj_asset[e, k - 1]
                 k += 1

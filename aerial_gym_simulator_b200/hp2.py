@@ -40,6 +40,25 @@ def box_obb(size: Sequence[float], R=None, p=None) -> np.ndarray:
     return np.concatenate([p, R[:, 0], R[:, 1], R[:, 2], np.asarray(size, dtype=np.float64) / 2.0, [2.0]]).astype(np.float32)
 
 
+def cylinder_triangles(radius: float, length: float, sections: int = 32) -> np.ndarray:
+    """[4*sections,9] object-frame triangles of a URDF <cylinder radius length/> (axis = z, centred): a `sections`-gon prism with fan
+    caps -- what the reference obtains through urdfpy -> trimesh.creation.cylinder (a revolved rectangle, 32 sections by default;
+    assets/warp_asset.py:19-24).  trimesh is not installable here: vertex angles 2 pi k / sections are the published construction,
+    parity against trimesh's own tessellation unpinned."""
+    r, h = float(radius), float(length) / 2.0
+    ang = 2.0 * np.pi * np.arange(sections) / sections
+    ring = np.stack([r * np.cos(ang), r * np.sin(ang)], axis=1)
+    tris = []
+    for k in range(sections):
+        a, b = ring[k], ring[(k + 1) % sections]
+        lo_a, lo_b, hi_a, hi_b = (a[0], a[1], -h), (b[0], b[1], -h), (a[0], a[1], h), (b[0], b[1], h)
+        tris.append(((0.0, 0.0, -h), lo_b, lo_a))   # bottom cap (outward normal -z)
+        tris.append((lo_a, lo_b, hi_b))             # side
+        tris.append((lo_a, hi_b, hi_a))
+        tris.append(((0.0, 0.0, h), hi_a, hi_b))    # top cap (+z)
+    return np.asarray(tris, dtype=np.float32).reshape(-1, 9)
+
+
 def _next_pow2(v: int) -> int:
     p = 1
     while p < v:

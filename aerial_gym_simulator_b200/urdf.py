@@ -202,3 +202,35 @@ def box_visual_triangles(model: UrdfModel, use_collision=False):
             t = (R @ (v.R @ t.T + v.p[:, None]) + p[:, None]).T
             out.append((name, t.reshape(-1, 9).astype(np.float32), box_obb(v.size, R @ v.R, R @ v.p + p)))
     return out
+
+
+def visual_parts(model: UrdfModel, use_collision=False, max_tris=12):
+    """Every <box> / <cylinder> visual of the model as ray-cast scene parts: [(link_name, link_index, triangles [n<=max_tris,9] in the
+    root frame, obb16)].  A box is one part (its 12 triangles + the oriented box the ray-caster uses for the entry-face shortcut,
+    kind 2); a cylinder is tessellated (hp2.cylinder_triangles) and cut into parts of <= max_tris triangles that share the cylinder's
+    bounding box (kind 1: culling only).  link_index counts the links that carry a visual, in urdfpy's link order -- the per-link
+    segmentation counter of assets/warp_asset.py:44-70.  Spheres / meshes are not carried (no shipped obstacle uses them)."""
+    from .hp2 import box_obb, box_triangles, cylinder_triangles
+
+    tf = model.link_transforms()
+    out, link_index = [], 0
+    for name in model.body_order():
+        l = model.links[name]
+        R, p = tf[name]
+        had_visual = False
+        for v in (l.collisions if use_collision else l.visuals):
+            if v.kind == "box":
+                t, obb = box_triangles(v.size), box_obb(v.size, R @ v.R, R @ v.p + p)
+            elif v.kind == "cylinder":
+                t = cylinder_triangles(v.size[0], v.size[1])
+                obb = box_obb((2 * v.size[0], 2 * v.size[0], v.size[1]), R @ v.R, R @ v.p + p)
+                obb[15] = 1.0
+            else:
+                continue
+            had_visual = True
+            t = t.reshape(-1, 3).astype(np.float64)
+            t = (R @ (v.R @ t.T + v.p[:, None]) + p[:, None]).T.reshape(-1, 9).astype(np.float32)
+            for i in range(0, len(t), max_tris):
+                out.append((name, link_index, t[i:i + max_tris], obb))
+        link_index += int(had_visual)
+    return out

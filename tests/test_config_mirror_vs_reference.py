@@ -102,7 +102,7 @@ def test_env_sim_task_asset_configs():
     _compare(_ref("env_config.empty_env", "EmptyEnvCfg"), EC.EmptyEnvCfg, skip=("asset_type_to_dict_map", "include_asset_type", "num_envs", "use_warp"))
     for mod, name, ours in (("env_with_obstacles", "EnvWithObstaclesCfg", EC.EnvWithObstaclesCfg),
                             ("env_with_lidar_nav_obstacles", "EnvWithLidarNavObstaclesCfg", EC.EnvWithLidarNavObstaclesCfg),
-                            ("dynamic_environment", "DynamicEnvironmentCfg", EC.DynamicEnvironmentCfg)):
+                            ("dynamic_environment", "DynamicEnvironmentCfg", EC.DynamicEnvironmentCfg), ("forest_env", "ForestEnvCfg", EC.ForestEnvCfg)):
         ref = _ref("env_config." + mod, name)
         _compare(ref.env, ours.env, skip=("num_envs", "use_warp"))
         on = {k for k, v in ref.env_config.include_asset_type.items() if v}

@@ -366,3 +366,40 @@ def test_rov_fully_actuated_and_motor_state_survives_reset():
         keep = torch.ones(N, dtype=torch.bool)
         keep[ids] = False
         assert torch.equal(gtd["robot_position"][keep], pos[keep])
+
+
+def test_forest_env_trees_as_cylinders_with_per_link_segmentation():
+    """forest_env: one tree (13 cylinder links, tessellated into 32-gon prisms and cut into 12-triangle parts), 35 objects, the floor;
+    per-link segmentation ids (assets/warp_asset.py:44-70) and the running counter advancing by the number of links"""
+    from aerial_gym_simulator_b200.hp2 import cylinder_triangles
+
+    t = cylinder_triangles(0.5, 2.0).reshape(-1, 3, 3).astype(np.float64)
+    assert t.shape == (128, 3, 3)
+    vol = np.einsum("ni,ni->n", t[:, 0], np.cross(t[:, 1], t[:, 2])).sum() / 6.0  # closed, outward-oriented mesh
+    assert abs(vol - 0.5 * 32 * 0.25 * np.sin(2 * np.pi / 32) * 2.0) < 1e-5
+    assert np.abs(np.linalg.norm(t[..., :2], axis=-1)[np.linalg.norm(t[..., :2], axis=-1) > 1e-6] - 0.5).max() < 1e-6
+    with cpu_stack():
+        N = 2
+        env = SimBuilder().build_env("base_sim", "forest_env", "base_quadrotor_with_camera", "lee_velocity_control", "cpu", args={"seed": 1},
+                                     num_envs=N, use_warp=True, headless=True)
+        gtd, sc = env.get_obs(), env.scene
+        assert gtd["num_obstacles_in_env"] == 37 and env.keep_in_env == 2  # tree + floor are kept, the 35 objects follow the curriculum
+        assert sc.K == 13 * 11 + 35 + 1 and sc.L == 12                     # 13 cylinders x ceil(128 / 12) parts + boxes
+        env.reset()
+        env.render()
+        seg = gtd["segmentation_pixels"]
+        ids = torch.unique(seg[seg >= 0]).tolist()
+        assert 13 in ids or any(100 <= i for i in ids)  # floor (fixed id 13) or instances
+        # the tree is the asset listed first among the kept ones or second: its 13 links take 13 consecutive ids, the other assets one each
+        ctr = sc.obj_seg_counter.numpy()
+        base = sc.tmpl_seg_base.numpy()[sc.tmpl_tri_offset.numpy()[sc.obj_template.numpy()]]  # seg base of each object's first triangle
+        mask = sc.tmpl_seg_mask.numpy()[sc.tmpl_tri_offset.numpy()[sc.obj_template.numpy()]]
+        final = base + ctr * mask
+        tree_parts = (env._obj_asset.numpy() == np.argmax(np.bincount(env._obj_asset.numpy()[0])))  # the asset with the most parts
+        assert tree_parts[0].sum() == 143
+        tree_ids = np.unique(final[0][tree_parts[0]])
+        assert len(tree_ids) == 13 and tree_ids.max() - tree_ids.min() == 12
+        others = np.unique(final[0][~tree_parts[0] & (mask[0] == 1)])
+        assert len(others) == 35 and not set(others.tolist()) & set(tree_ids.tolist())
+        assert final[1][mask[1] == 1].min() > final[0][mask[0] == 1].max()  # env 1 continues the running counter
+        assert torch.isfinite(gtd["depth_range_pixels"]).all() and (gtd["depth_range_pixels"] > 0).any()
