@@ -403,3 +403,51 @@ def test_forest_env_trees_as_cylinders_with_per_link_segmentation():
         assert len(others) == 35 and not set(others.tolist()) & set(tree_ids.tolist())
         assert final[1][mask[1] == 1].min() > final[0][mask[0] == 1].max()  # env 1 continues the running counter
         assert torch.isfinite(gtd["depth_range_pixels"]).all() and (gtd["depth_range_pixels"] > 0).any()
+
+
+def test_task_torch_rng_mode_follows_reference_call_order(cpu_task):
+    """CPU twin of tests/test_env_task_gpu.py::test_task_torch_rng_mode_follows_reference_call_order: reset_rng='torch' draws full-size
+    uniforms with torch.rand in the reference's order (bounds lo, bounds hi, state, motor tau_inc, tau_dec, thrust, k), only when an env
+    resets"""
+    from oracle import hp1_oracle as O
+    from tests import _hp1_common as H
+
+    cfg = task_registry.get_task_config("position_setpoint_task")
+    old = cfg.args
+    cfg.args = {"reset_rng": "torch"}
+    try:
+        task = cpu_task("position_setpoint_task", seed=5, num_envs=48)
+    finally:
+        cfg.args = old
+    N = 48
+    calls, orig = [], torch.rand
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        calls.append(out.clone())
+        return out
+    torch.rand = spy
+    try:
+        torch.manual_seed(1234)
+        task.reset()
+    finally:
+        torch.rand = orig
+    assert [tuple(c.shape) for c in calls] == [(N, 3), (N, 3), (N, 13), (N, 4), (N, 4), (N, 4), (N, 4)]
+    eng = task.sim_env.engine
+    model = H.oracle_model_from_spec(task.sim_env.spec)
+    draws = O.ResetDraws(calls[0], calls[1], calls[2], None, None, None, None, calls[3], calls[4], calls[5], calls[6])
+    st = O.make_state(model, N)
+    O.reset_envs(model, st, torch.ones(N, dtype=torch.bool), draws)
+    H.assert_close(eng.root_state, st.root, "reset state (torch rng order)", scale=1.0)
+    H.assert_close(eng.motor_thrust, st.thrust, "reset thrust")
+    first = eng.root_state.clone()
+    torch.manual_seed(1234)
+    task.reset()
+    assert torch.equal(eng.root_state, first)  # same seed, same episode start
+    s0 = torch.get_rng_state().clone()
+    task.step(torch.zeros(N, 4))
+    assert torch.equal(torch.get_rng_state(), s0)  # a step without resets does not consume the generator
+    eng.sim_steps[7] = 500
+    task.step(torch.zeros(N, 4))
+    assert not torch.equal(torch.get_rng_state(), s0)
+    assert int(eng.sim_steps[7]) == 0 and bool(task.truncations[7]) and int(task.truncations.sum()) == 1
