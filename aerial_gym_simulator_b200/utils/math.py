@@ -117,3 +117,76 @@ def exponential_reward_function(magnitude: float, base_width: float, value):
 
 def exponential_penalty_function(magnitude: float, base_width: float, value):
     return magnitude * (torch.exp(-(value * value) / base_width) - 1.0)
+
+
+# ---- the rest of the reference's utils/math.py surface (names user task code may import) --------------------------------------
+def compute_vee_map(skew_matrix):
+    """vee of a batch of skew-symmetric 3x3 matrices (utils/math.py:34-42)."""
+    return torch.stack([-skew_matrix[..., 1, 2], skew_matrix[..., 0, 2], -skew_matrix[..., 0, 1]], dim=-1)
+
+
+def torch_rand_float(lower, upper, shape, device):
+    return (upper - lower) * torch.rand(*shape, device=device) + lower
+
+
+def torch_rand_float_vec(lower, upper, shape, device):
+    return torch.rand(*shape, device=device) * (upper - lower) + lower
+
+
+def torch_random_dir_2(shape, device):
+    angle = torch_rand_float(-math.pi, math.pi, shape, device).squeeze(-1)
+    return torch.stack([torch.cos(angle), torch.sin(angle)], dim=-1)
+
+
+def copysign(a, b):
+    """scalar magnitude a with the sign of every element of the 1-D tensor b"""
+    return torch.full((b.shape[0],), abs(float(a)), device=b.device, dtype=torch.float) * torch.sign(b)
+
+
+def scale(x, lower, upper):
+    return 0.5 * (x + 1.0) * (upper - lower) + lower
+
+
+def unscale(x, lower, upper):
+    return (2.0 * x - upper - lower) / (upper - lower)
+
+
+unscale_np = unscale
+
+
+def to_torch(x, dtype=torch.float, device="cuda:0", requires_grad=False):
+    return torch.tensor(x, dtype=dtype, device=device, requires_grad=requires_grad)
+
+
+def quat_unit(a):
+    return normalize(a)
+
+
+def quat_from_angle_axis(angle, axis):
+    half = (angle / 2).unsqueeze(-1)
+    return quat_unit(torch.cat([normalize(axis) * half.sin(), half.cos()], dim=-1))
+
+
+def normalize_angle(x):
+    return torch.atan2(torch.sin(x), torch.cos(x))
+
+
+def tf_inverse(q, t):
+    q_inv = quat_conjugate(q)
+    return q_inv, -quat_apply(q_inv, t)
+
+
+def tf_vector(q, v):
+    return quat_apply(q, v)
+
+
+def tf_combine(q1, t1, q2, t2):
+    return quat_mul(q1, q2), quat_apply(q1, t2) + t1
+
+
+def get_basis_vector(q, v):
+    return quat_rotate(q, v)
+
+
+def pd_control(pos_error, vel_error, stiffness, damping):
+    return stiffness * pos_error + damping * vel_error
