@@ -175,7 +175,11 @@ def load():
         "agx_host_free": [C.c_void_p],
         "agx_hp2_collide": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     }.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise AgxError(f"{path} does not export {name}: it was built from older sources than include/aerial_gym_b200.h -- "
+                           "rebuild it with `python -m aerial_gym_simulator_b200._build --force`") from None
         fn.restype = C.c_int
         fn.argtypes = args
     lib.agx_hp2_scene_bytes.restype = C.c_uint64
