@@ -22,6 +22,7 @@ UNITS = [
     ("obstacles.cu", []),
     ("e2e_task.cu", []),
     ("sim2real.cu", []),
+    ("disturbance.cu", []),
     ("hp2_raycast.cu", ["-fmad=false"]),
     ("p2p_allgather.cu", []),
 ]

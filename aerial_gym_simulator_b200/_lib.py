@@ -169,6 +169,7 @@ def load():
         "agx_e2e_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
         "agx_s2r_reward": [C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10,
         "agx_s2r_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p],
+        "agx_disturbance_draw": [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_obstacle_step": [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p],
         "agx_hp2_noise_limits": [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(AgxHp2Noise), C.c_uint64, C.c_uint32, C.c_void_p],
         "agx_host_alloc": [C.c_uint64, C.POINTER(C.c_void_p)],

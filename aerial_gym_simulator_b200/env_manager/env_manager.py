@@ -384,10 +384,27 @@ class EnvManager:
         self.truncation_tensor[:] = 0
 
     def _draw_disturbance(self):
-        """apply_disturbance (base_multirotor.py:213-234): bernoulli, rand, rand in that order."""
+        """apply_disturbance (base_multirotor.py:213-234).  reset_rng = "torch": bernoulli, rand, rand in the reference's order.
+        reset_rng = "device" (default): one launch of agx_disturbance_draw (Philox per env, keyed by the global env id and a draw
+        counter) into a persistent [N,6] buffer -- same distributions, no torch RNG launches inside the physics loop."""
         sp, N, dev = self.spec, self.num_envs, self.device
         if not sp.enable_disturbance:
             return None
+        if self.reset_rng == "device":
+            import ctypes as C
+
+            from .. import _lib
+            if getattr(self, "_dist_buf", None) is None:
+                self._dist_buf = torch.zeros(N, 6, device=dev)
+                self._dist_max = (C.c_float * 6)(*[float(v) for v in sp.max_disturbance])
+                self._dist_counter = 0
+                self._dist_seed = (int(self.env_args.get("seed", 0)) ^ 0xD157_0000_D157) & (2**64 - 1)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.load().agx_disturbance_draw(N, int(self.env_args.get("env_id_offset", 0)), float(sp.prob_apply_disturbance),
+                                                        self._dist_max, self._dist_seed, self._dist_counter & 0xFFFFFFFF,
+                                                        C.c_void_p(self._dist_buf.data_ptr()), stream), "agx_disturbance_draw")
+            self._dist_counter += 1
+            return self._dist_buf
         occ = torch.bernoulli(sp.prob_apply_disturbance * torch.ones(N, device=dev))
         mx = torch.tensor(sp.max_disturbance, dtype=torch.float32, device=dev).expand(N, -1)
         f = _lerp(-mx[:, 0:3], mx[:, 0:3], torch.rand(N, 3, device=dev)) * occ.unsqueeze(1)

@@ -350,6 +350,16 @@ int agx_s2r_reward(int num_envs, int variant, const float* robot_state, int robo
 int agx_s2r_obs(int num_envs, float* robot_state, int robot_state_stride, const float* body_linvel, const float* body_angvel,
                 const float* robot_actions, const float* target_position, const float* noise, float* obs, int obs_stride, void* stream);
 
+/* ---- random wrench disturbance, device RNG -------------------------------------------------------------- */
+
+/* BaseMultirotor.apply_disturbance (robots/base_multirotor.py:213-234) as one launch: disturbance [N,6] (device) = with probability
+ * prob a body-0 force ~ U(-max, max)^3 and torque ~ U(-max, max)^3, else zero; feeds AgxHp1Buffers.disturbance.
+ * max_force_and_torque: HOST array of six floats (cfg.disturbance.max_force_and_torque_disturbance).  Device RNG (Philox4x32-10,
+ * counter = (env_id_offset + env, counter, block, 'DIST'), key = seed): same distributions as the reference's torch.bernoulli +
+ * 2 x rand_like, its own stream, independent of sharding; `counter` advances once per physics step. */
+int agx_disturbance_draw(int num_envs, int env_id_offset, float prob, const float* max_force_and_torque, uint64_t seed,
+                         uint32_t counter, float* disturbance, void* stream);
+
 /* ---- dynamic obstacles ("dynamic_env": env_manager/obstacle_manager.py:40-44 + PhysX) ------------------- */
 
 /* Kinematic advance of every obstacle by `substeps` physics steps of `dt`.  asset_state [N,A,asset_stride] rows

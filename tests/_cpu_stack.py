@@ -149,7 +149,7 @@ class _LibProxy:
             "agx_lidar_nav_pool": "shadow_lidar_nav_pool", "agx_lidar_nav_reward": "shadow_lidar_nav_reward",
             "agx_lidar_nav_obs": "shadow_lidar_nav_obs", "agx_obstacle_step": "shadow_obstacle_step",
             "agx_e2e_reward": "shadow_e2e_reward", "agx_e2e_obs": "shadow_e2e_obs",
-            "agx_s2r_reward": "shadow_s2r_reward", "agx_s2r_obs": "shadow_s2r_obs"}
+            "agx_s2r_reward": "shadow_s2r_reward", "agx_s2r_obs": "shadow_s2r_obs", "agx_disturbance_draw": "shadow_disturbance_draw"}
 
     def __init__(self, real):
         self._real, self._sh = real, _shadow.load()

@@ -8,7 +8,7 @@ SRC = os.path.join(HERE, "csrc", "host_shadow.cu")
 LIB = os.path.join(HERE, "_build", "libagx_host_shadow.so")
 _CSRC = os.path.join(HERE, "..", "aerial_gym_simulator_b200", "csrc")
 _HP1_CU = os.path.join(_CSRC, "hp1.cu")
-_DEPS = [SRC, os.path.join(HERE, "csrc", "host_shadow_hp1.inc"), _HP1_CU, os.path.join(_CSRC, "hp1_core.cuh"), os.path.join(_CSRC, "aux_core.cuh"), os.path.join(_CSRC, "e2e_task_core.cuh"), os.path.join(_CSRC, "sim2real_core.cuh"), os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "noise_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
+_DEPS = [SRC, os.path.join(HERE, "csrc", "host_shadow_hp1.inc"), _HP1_CU, os.path.join(_CSRC, "hp1_core.cuh"), os.path.join(_CSRC, "aux_core.cuh"), os.path.join(_CSRC, "e2e_task_core.cuh"), os.path.join(_CSRC, "sim2real_core.cuh"), os.path.join(_CSRC, "disturbance_core.cuh"), os.path.join(_CSRC, "lidar_nav_core.cuh"), os.path.join(_CSRC, "obstacle_core.cuh"), os.path.join(_CSRC, "noise_core.cuh"), os.path.join(_CSRC, "agx_math.cuh"),
          os.path.join(HERE, "..", "include", "aerial_gym_b200.h")]
 _lib = None
 
@@ -79,6 +79,8 @@ def load():
         lib.shadow_s2r_reward.restype = lib.shadow_s2r_obs.restype = None
         lib.shadow_s2r_reward.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9
         lib.shadow_s2r_obs.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+        lib.shadow_disturbance_draw.restype = C.c_int
+        lib.shadow_disturbance_draw.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         lib.shadow_hp1_position_reward.restype = C.c_int
         lib.shadow_hp1_position_reward.argtypes = [C.POINTER(A.AgxHp1Config), C.c_int] + [C.c_void_p] * 8
         _lib = lib

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../aerial_gym_simulator_b200/csrc/aux_core.cuh"
+#include "../../aerial_gym_simulator_b200/csrc/disturbance_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/e2e_task_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/hp1_core.cuh"
 #include "../../aerial_gym_simulator_b200/csrc/lidar_nav_core.cuh"
@@ -122,6 +123,13 @@ void shadow_s2r_reward(int n, int variant, const float* state, int stride, const
 void shadow_s2r_obs(int n, float* state, int stride, const float* body_linvel, const float* body_angvel, const float* robot_actions,
                     const float* target, const float* noise, float* obs, int obs_stride) {
     for (int e = 0; e < n; ++e) s2r_obs_env(e, state, stride, body_linvel, body_angvel, robot_actions, target, noise, obs, obs_stride);
+}
+
+// stands in for disturbance_kernel (disturbance.cu)
+int shadow_disturbance_draw(int n, int env_id_offset, float prob, const float* max6, uint64_t seed, uint32_t counter, float* out) {
+    for (int e = 0; e < n; ++e)
+        disturbance_env((uint32_t)env_id_offset + (uint32_t)e, counter, prob, max6, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), out + (size_t)e * 6);
+    return 0;
 }
 
 // stands in for obstacle_step_kernel: one "thread" per obstacle

@@ -109,3 +109,19 @@ def test_dynamic_env_end_to_end():
     torch.cuda.synchronize()
     assert torch.equal(env2._obj_pose, pose0)                                            # the ray-cast scene stays where it was ...
     assert torch.allclose(ast2[..., 0], before2[..., 0] - 0.1 * 0.999, atol=1e-4)        # ... while the obstacle states moved
+
+
+def test_disturbance_draw_kernel_matches_oracle():
+    """agx_disturbance_draw (device-RNG form of BaseMultirotor.apply_disturbance): integer Philox + two multiplies, so bit-exact"""
+    from oracle import disturbance_oracle as D
+
+    lib, n = _lib.load(), 70001
+    mx = [4.75, 4.75, 4.75, 0.03, 0.03, 0.03]
+    m = (C.c_float * 6)(*mx)
+    out = torch.zeros(n, 6, device=DEV)
+    for off, counter in ((0, 0), (123456, 9)):
+        _lib.check(lib.agx_disturbance_draw(n, off, 0.05, m, 0xFEED_0000_1234, counter, C.c_void_p(out.data_ptr()), None), "agx_disturbance_draw")
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), D.draw(n, off, 0.05, mx, 0xFEED_0000_1234, counter))
+    assert lib.agx_disturbance_draw(n, 0, 1.5, m, 1, 0, C.c_void_p(out.data_ptr()), None) == -1
+    assert lib.agx_disturbance_draw(n, 0, 0.5, None, 1, 0, C.c_void_p(out.data_ptr()), None) == -3
