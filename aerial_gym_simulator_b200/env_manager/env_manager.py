@@ -12,6 +12,7 @@ Differences that are deliberate and documented:
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import os
 import random
@@ -20,6 +21,7 @@ from collections import deque
 import numpy as np
 import torch
 
+from .. import _lib
 from .. import robots  # noqa: F401  (registers robots + controllers)
 from .. import urdf
 from ..hp1 import Hp1Engine
@@ -391,9 +393,6 @@ class EnvManager:
         if not sp.enable_disturbance:
             return None
         if self.reset_rng == "device":
-            import ctypes as C
-
-            from .. import _lib
             if getattr(self, "_dist_buf", None) is None:
                 self._dist_buf = torch.zeros(N, 6, device=dev)
                 self._dist_max = (C.c_float * 6)(*[float(v) for v in sp.max_disturbance])
@@ -450,9 +449,6 @@ class EnvManager:
         The reference leaves its Warp meshes stale until the next reset ("refit() ... expensive", env_manager.py:340-342);
         here re-posing + rebuilding the BVHs of all envs is one more launch, done by default (args['refit_dynamic_obstacles'])
         so the ray-cast sensors and the collision test of the next env step see the obstacles where they are."""
-        import ctypes as C
-
-        from .. import _lib
         gtd, N, A = self.global_tensor_dict, self.num_envs, self.num_obs_in_env
         ast = gtd["env_asset_state_tensor"]
         twist = twist.contiguous()  # shape / dtype / device were checked in step()
