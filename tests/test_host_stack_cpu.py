@@ -451,3 +451,22 @@ def test_task_torch_rng_mode_follows_reference_call_order(cpu_task):
     task.step(torch.zeros(N, 4))
     assert not torch.equal(torch.get_rng_state(), s0)
     assert int(eng.sim_steps[7]) == 0 and bool(task.truncations[7]) and int(task.truncations.sum()) == 1
+
+
+def test_imu_in_env_manager():
+    """CPU twin of tests/test_aux_gpu.py::test_imu_in_env_manager: base_quadrotor_with_imu hovering -- the accelerometer reads +g along
+    body z (specific force from the engine's net body wrench), the gyro the body rates, both within the sensor's noise"""
+    with cpu_stack() as proxy:
+        env = SimBuilder().build_env(sim_name="base_sim", env_name="empty_env", robot_name="base_quadrotor_with_imu",
+                                     controller_name="lee_position_control", args={"seed": 1}, device="cpu", num_envs=32, headless=True)
+        env.reset()
+        gtd = env.get_obs()
+        act = torch.cat([gtd["robot_position"].clone(), torch.zeros(32, 1)], dim=1)  # hold position, yaw 0
+        for _ in range(300):
+            env.step(act)
+            env.render()
+        imu = gtd["imu_measurement"]
+        assert imu.shape == (32, 6) and torch.isfinite(imu).all() and proxy.calls["agx_imu_update"] == 300
+        assert (imu[:, 0:3].norm(dim=1) - 9.81).abs().max() < 1.0
+        assert (imu[:, 3:6] - gtd["robot_body_angvel"]).abs().max() < 0.2
+        assert torch.nn.functional.normalize(imu[:, 0:3], dim=1)[:, 2].min() > 0.9
