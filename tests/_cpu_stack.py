@@ -6,6 +6,7 @@
   * ``_lib.load()``         -> a proxy whose agx_* entry points for the small per-env kernels call their shadow_* twins
                                (same argument lists minus the stream),
   * ``DeviceSensorNoise``   -> the shadow of noise_limits_kernel,
+  * ``IMUSensor``           -> the product class with its CUDA-device check skipped (agx_imu_update goes through the proxy),
   * ``torch.cuda.current_stream`` -> a dummy (the tasks read ``.cuda_stream`` to pass it along).
 Everything above the C ABI -- registries, config plumbing, RNG call order, reset / curriculum / render bookkeeping, tensor
 aliasing in the Global Tensor Dict -- is the PRODUCT's code, running on "cpu" tensors.  TEST INFRASTRUCTURE ONLY: the product
@@ -143,6 +144,18 @@ class CpuDeviceSensorNoise:
         return self.pixels
 
 
+class CpuIMUSensor:
+    """IMUSensor minus its CUDA-device check (the rest -- init_tensors / update / reset -- is the product class's own code)"""
+
+    def __new__(cls, sensor_config, num_envs, device):
+        from aerial_gym_simulator_b200.sensors.imu_sensor import IMUSensor
+        self = object.__new__(IMUSensor)
+        self.cfg, self.num_envs, self.device = sensor_config, int(num_envs), torch.device("cpu")
+        self.lib = _lib.load()
+        self.world_frame, self.gravity_compensation = sensor_config.world_frame, sensor_config.gravity_compensation
+        return self
+
+
 class _LibProxy:
     """agx_* of the small per-env kernels -> shadow_* (same arguments, no stream); everything else -> the real library"""
     _MAP = {"agx_nav_reward": "shadow_nav_reward", "agx_nav_obs": "shadow_nav_obs", "agx_imu_update": "shadow_imu_update",
@@ -174,11 +187,14 @@ class _LibProxy:
 @contextlib.contextmanager
 def cpu_stack():
     import aerial_gym_simulator_b200.env_manager.env_manager as EM
+    import aerial_gym_simulator_b200.sensors as S
     import aerial_gym_simulator_b200.sensors.noise as SN
 
     real_lib = _lib.load()
     proxy = _LibProxy(real_lib)
     saved = (EM.Hp1Engine, EM.RayScene, EM.RaySensor, _lib.load, SN.DeviceSensorNoise, torch.cuda.current_stream)
+    saved_imu = S.IMUSensor
+    S.IMUSensor = CpuIMUSensor
     EM.Hp1Engine, EM.RayScene, EM.RaySensor = CpuHp1Engine, CpuRayScene, CpuRaySensor
     _lib.load = lambda: proxy
     SN.DeviceSensorNoise = CpuDeviceSensorNoise
@@ -187,3 +203,4 @@ def cpu_stack():
         yield proxy
     finally:
         EM.Hp1Engine, EM.RayScene, EM.RaySensor, _lib.load, SN.DeviceSensorNoise, torch.cuda.current_stream = saved
+        S.IMUSensor = saved_imu
