@@ -157,12 +157,14 @@ class CpuIMUSensor:
 
 
 class _LibProxy:
-    """agx_* of the small per-env kernels -> shadow_* (same arguments, no stream); everything else -> the real library"""
+    """agx_* of the small per-env kernels -> the real entry point for its argument validation, then shadow_* (same arguments, no
+    stream) for the arithmetic; everything else -> the real library"""
     _MAP = {"agx_nav_reward": "shadow_nav_reward", "agx_nav_obs": "shadow_nav_obs", "agx_imu_update": "shadow_imu_update",
             "agx_lidar_nav_pool": "shadow_lidar_nav_pool", "agx_lidar_nav_reward": "shadow_lidar_nav_reward",
             "agx_lidar_nav_obs": "shadow_lidar_nav_obs", "agx_obstacle_step": "shadow_obstacle_step",
             "agx_e2e_reward": "shadow_e2e_reward", "agx_e2e_obs": "shadow_e2e_obs",
-            "agx_s2r_reward": "shadow_s2r_reward", "agx_s2r_obs": "shadow_s2r_obs", "agx_disturbance_draw": "shadow_disturbance_draw"}
+            "agx_s2r_reward": "shadow_s2r_reward", "agx_s2r_obs": "shadow_s2r_obs", "agx_disturbance_draw": "shadow_disturbance_draw",
+            "agx_hp2_noise_limits": "shadow_noise_limits"}
 
     def __init__(self, real):
         self._real, self._sh = real, _shadow.load()
@@ -173,8 +175,16 @@ class _LibProxy:
             return getattr(self._real, name)
         fn = getattr(self._sh, self._MAP[name])
 
+        real_fn = getattr(self._real, name)
+
         def call(*args):
             self.calls[name] = self.calls.get(name, 0) + 1
+            # the PRODUCT's host-side argument validation runs first: on a box without a GPU the real entry point either rejects
+            # the arguments (AGX_E_INVALID / AGX_E_NULL, before any launch) or fails at the launch itself (AGX_E_CUDA) -- only
+            # then does the shadow compute
+            rc = real_fn(*args)
+            if rc in (-1, -3):
+                return rc
             args = list(args[:-1])  # drop the stream
             if name == "agx_lidar_nav_pool":
                 args.append(0)  # force_scalar = 0

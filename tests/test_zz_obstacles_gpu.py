@@ -38,7 +38,7 @@ def test_obstacle_step_kernel_matches_oracle(with_twist, substeps, stride):
     tw = torch.randn(n, a, 6, generator=g) * 1.5 if with_twist else None
     if with_twist:
         tw[0, 0, 3:6] = 0.0
-    sd = s.to(DEV).contiguous()
+    sd = s.clone().to(DEV).contiguous()
     twd = tw.to(DEV).contiguous() if with_twist else None
     _lib.check(_lib.load().agx_obstacle_step(n, a, C.c_void_p(sd.data_ptr()), stride, C.c_void_p(twd.data_ptr()) if with_twist else None,
                                              0.01, substeps, 0.1, 0.1, None), "agx_obstacle_step")

@@ -108,10 +108,15 @@ def test_raw_cast_then_device_noise_matches_oracle_chain():
     noise.apply()
     torch.cuda.synchronize()
     want = _oracle(raw, noise.c, 11, 0, 1000)
-    got = sensor.pixels.cpu().numpy()
-    miss = raw > 100.0  # a miss (1000 m) has std = 377 m: it lands beyond max range (far value) or below min range (near value)
+    got = sensor.pixels.cpu().numpy().copy()
+    miss = raw > 100.0  # a miss (1000 m) has std = 377 m: it lands beyond max range (far value) or below min range (near value) ...
     assert np.allclose(got[~miss], want[~miss], rtol=1e-4, atol=1e-5), np.abs(got - want)[~miss].max()
-    assert np.isin(got[miss], np.array([1.0, -1.0], np.float32)).all() and (got <= 1.0).all() and (got >= -1.0).all()
+    clipped = np.isin(got[miss], np.array([1.0, -1.0], np.float32))
+    # ... except the ~1 % of the draws that fall inside [min_range, max_range]: those follow the oracle (a 1e-4 relative error of
+    # the normal draw on std 377 m is 0.04 m = 0.004 after the normalisation)
+    assert clipped.mean() > 0.95 and np.allclose(got[miss][~clipped], want[miss][~clipped], atol=2e-2)
+    assert (np.isin(want[miss], np.array([1.0, -1.0], np.float32)) != clipped).mean() < 1e-3  # same side of the limits as the oracle
+    assert (got <= 1.0).all() and (got >= -1.0).all()
     assert noise.frame == 1
     sensor.capture()
     noise.apply()
