@@ -83,53 +83,18 @@ def install():
         sys.modules["aerial_gym." + name] = mod
         if "." not in name:
             setattr(pkg, name, mod)
-    # reference-style deep config paths
-    deep = {
-        "config.task_config.navigation_task_config": _module(
-            "aerial_gym.config.task_config.navigation_task_config", task_config=task_config.navigation_task_config),
-        "config.task_config.lidar_navigation_task_config": _module(
-            "aerial_gym.config.task_config.lidar_navigation_task_config", task_config=task_config.lidar_navigation_task_config),
-        "config.env_config.env_with_lidar_nav_obstacles": _module(
-            "aerial_gym.config.env_config.env_with_lidar_nav_obstacles", EnvWithLidarNavObstaclesCfg=env_config.EnvWithLidarNavObstaclesCfg),
-        "config.env_config.dynamic_environment": _module(
-            "aerial_gym.config.env_config.dynamic_environment", DynamicEnvironmentCfg=env_config.DynamicEnvironmentCfg),
-        "config.task_config.position_setpoint_task_sim2real_end_to_end_config": _module(
-            "aerial_gym.config.task_config.position_setpoint_task_sim2real_end_to_end_config",
-            task_config=task_config.position_setpoint_task_sim2real_end_to_end_config),
-        "config.task_config.position_setpoint_task_sim2real_px4_config": _module(
-            "aerial_gym.config.task_config.position_setpoint_task_sim2real_px4_config",
-            task_config=task_config.position_setpoint_task_sim2real_px4_config),
-        "config.task_config.radar_navigation_task_config": _module(
-            "aerial_gym.config.task_config.radar_navigation_task_config", task_config=task_config.radar_navigation_task_config),
-        "config.task_config.position_setpoint_task_sim2real_config": _module(
-            "aerial_gym.config.task_config.position_setpoint_task_sim2real_config", task_config=task_config.position_setpoint_task_sim2real_config),
-        "config.task_config.position_setpoint_task_acceleration_sim2real_config": _module(
-            "aerial_gym.config.task_config.position_setpoint_task_acceleration_sim2real_config",
-            task_config=task_config.position_setpoint_task_acceleration_sim2real_config),
-        "config.task_config.position_setpoint_task_config": _module(
-            "aerial_gym.config.task_config.position_setpoint_task_config", task_config=task_config.position_setpoint_task_config),
-        "config.sim_config.base_sim_config": _module("aerial_gym.config.sim_config.base_sim_config", BaseSimConfig=sim_config.BaseSimConfig),
-        "config.env_config.empty_env": _module("aerial_gym.config.env_config.empty_env", EmptyEnvCfg=env_config.EmptyEnvCfg),
-        "config.env_config.env_with_obstacles": _module("aerial_gym.config.env_config.env_with_obstacles",
-                                                        EnvWithObstaclesCfg=env_config.EnvWithObstaclesCfg),
-        "config.robot_config.base_quad_config": _module("aerial_gym.config.robot_config.base_quad_config",
-                                                        **{k: v for k, v in vars(robot_config).items() if k.startswith("BaseQuad")}),
-    }
-    del deep
-    # the reference's one-class-per-file sensor catalogue: config/sensor_config/{lidar,camera,imu}_config/<file>.py
-    catalogue = {
-        "lidar_config": {"base_lidar_config": "BaseLidarConfig", "os0_128_config": "OS_0_128_Config", "os0_64_config": "OS_0_64_Config",
-                         "os1_64_config": "OS_1_64_Config", "os2_64_config": "OS_2_64_Config", "osdome_64_config": "OSDome_64_Config",
-                         "rslidar_airy_config": "RSLidar_Airy_Config", "pmd_flexx2_config": "pmd_flexx2_config",
-                         "st_vl53l5cx_config": "ST_VL53L5CXConfig", "fake_radar_config": "fake_radar_config"},
-        "camera_config": {"base_depth_camera_config": "BaseDepthCameraConfig", "d455_depth_config": "RsD455Config",
-                          "intel_realsense_d455_config": "IntelRealSenseD455Config", "luxonis_oak_d_config": "LuxonisOakDConfig",
-                          "luxonis_oak_d_pro_w_config": "LuxonisOakDProWConfig", "stereo_camera_config": "StereoCameraConfig",
-                          "base_normal_faceID_camera_config": "BaseNormalFaceIDCameraConfig"},
-        "imu_config": {"base_imu_config": "BaseImuConfig", "bosch_bmi088_config": "BoschBMI088Config", "vn100_config": "VN100Config"},
-    }
-    for pkg_name, files in catalogue.items():
-        _module(f"aerial_gym.config.sensor_config.{pkg_name}", __path__=[])
-        for fname, cls in files.items():
-            _module(f"aerial_gym.config.sensor_config.{pkg_name}.{fname}", **{cls: getattr(sensor_config, cls)})
-    _module("aerial_gym.config.sensor_config.base_sensor_config", BaseSensorConfig=sensor_config.BaseSensorConfig)
+    # the reference's one-class-per-file config paths: aerial_gym.config.<kind>_config[.<sub>].<file> (compat_paths.py)
+    from .compat_paths import CONFIG_MODULES
+    flat = {"sim_config": sim_config, "env_config": env_config, "robot_config": robot_config, "controller_config": controller_config,
+            "sensor_config": sensor_config, "asset_config": asset_config, "task_config": task_config}
+    for rel, names in CONFIG_MODULES.items():
+        parts = rel.split(".")
+        for i in range(2, len(parts)):  # intermediate packages (sensor_config.lidar_config, ...)
+            mid = "aerial_gym.config." + ".".join(parts[:i])
+            if mid not in sys.modules:
+                _module(mid, __path__=[])
+        attrs = {}
+        for name, where in names.items():
+            mod_name, attr = where.split(".")
+            attrs[name] = getattr(flat[mod_name], attr)
+        _module("aerial_gym.config." + rel, **attrs)

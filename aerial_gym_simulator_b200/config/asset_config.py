@@ -51,6 +51,33 @@ class asset_state_params:
     min_state_ratio, max_state_ratio = _ratio((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
 
 
+class BaseAssetParams:
+    """config/asset_config/base_asset.py: the older base class (lighter damping and density); kept for import parity"""
+    num_assets = 1
+    asset_folder = _ENV_ASSETS
+    file = None
+    min_position_ratio, max_position_ratio = [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]
+    collision_mask = 1
+    disable_gravity = False
+    replace_cylinder_with_capsule = True
+    flip_visual_attachments = True
+    density = 0.000001
+    angular_damping = linear_damping = 0.0001
+    max_angular_velocity = max_linear_velocity = 100.0
+    armature = 0.001
+    collapse_fixed_joints = True
+    fix_base_link = True
+    color = None
+    keep_in_env = False
+    body_semantic_label = link_semantic_label = 0
+    per_link_semantic = False
+    semantic_masked_links = {}
+    place_force_sensor = False
+    force_sensor_parent_link = "base_link"
+    force_sensor_transform = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+    use_collision_mesh_instead_of_visual = False
+
+
 class panel_asset_params(asset_state_params):
     num_assets = 3
     asset_folder = f"{_ENV_ASSETS}/panels"
@@ -129,3 +156,46 @@ class tree_asset_params(asset_state_params):
     keep_in_env = True
     semantic_id = -1
     color = [70, 200, 100]
+
+
+class thin_asset_params(asset_state_params):
+    """config/asset_config/env_object_config.py:181-222: thin rods (one box each, 1000 files); off by default (num_assets = 0)"""
+    num_assets = 0
+    asset_folder = f"{_ENV_ASSETS}/thin"
+    min_state_ratio, max_state_ratio = _ratio((0.3, 0.05, 0.05), (0.85, 0.95, 0.95), (-PI, -PI, -PI), (PI, PI, PI))
+    collapse_fixed_joints = True
+    per_link_semantic = False
+    semantic_id = -1
+    color = [170, 66, 66]
+
+
+class tile_asset_params(asset_state_params):
+    """config/asset_config/env_object_config.py:123-178.  The reference ships no `tile_meshes` folder either: the class exists so that
+    the env configs' asset_type_to_dict_map is complete; "tiles" is False in every include_asset_type."""
+    num_assets = 1
+    asset_folder = f"{_ENV_ASSETS}/tile_meshes"
+    min_position_ratio, max_position_ratio = [0.3, 0.05, 0.05], [0.85, 0.95, 0.95]
+    specified_position = [-1000.0, -1000.0, -1000.0]
+    min_euler_angles, max_euler_angles = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    min_state_ratio, max_state_ratio = _ratio((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+    keep_in_env = True
+    collapse_fixed_joints = True
+    per_link_semantic = False
+    semantic_id = -1
+
+
+def _variant(base, prefix, **fields):
+    return type(prefix + base.__name__, (base,), dict(fields))
+
+
+# lidar_nav_env_config.py keeps its own tile / tree classes: as env_object_config's, but not kept when the curriculum thins the scene
+lidar_nav_tile_asset_params = _variant(tile_asset_params, "lidar_nav_", keep_in_env=False)
+lidar_nav_tree_asset_params = _variant(tree_asset_params, "lidar_nav_", keep_in_env=False)
+# dynamic_env_object_config.py: EVERY class there floats (gravity off, base link free), and it has six trees
+_FLOATING = dict(disable_gravity=True, fix_base_link=False)
+dynamic_asset_state_params = _variant(asset_state_params, "dynamic_", **_FLOATING)
+dynamic_panel_asset_params = _variant(panel_asset_params, "dynamic_", **_FLOATING)
+dynamic_thin_asset_params = _variant(thin_asset_params, "dynamic_", **_FLOATING)
+dynamic_tree_asset_params = _variant(tree_asset_params, "dynamic_", num_assets=6, **_FLOATING)
+dynamic_left_wall, dynamic_right_wall, dynamic_top_wall, dynamic_bottom_wall, dynamic_front_wall, dynamic_back_wall = (
+    _variant(w, "dynamic_", **_FLOATING) for w in (left_wall, right_wall, top_wall, bottom_wall, front_wall, back_wall))

@@ -4,6 +4,10 @@ from .asset_config import (back_wall, bottom_wall, front_wall, left_wall, object
                            right_wall, top_wall)
 
 
+class BaseEnvCfg:  # config/env_config/base_env_config.py
+    pass
+
+
 class EmptyEnvCfg:
     class env:
         num_envs = 3
@@ -60,9 +64,9 @@ class EnvWithObstaclesCfg:
             "top_wall": True, "bottom_wall": True,
         }
         asset_type_to_dict_map = {
-            "panels": panel_asset_params, "objects": object_asset_params,
+            "panels": panel_asset_params, "thin": _ac.thin_asset_params, "trees": _ac.tree_asset_params, "objects": object_asset_params,
             "left_wall": left_wall, "right_wall": right_wall, "back_wall": back_wall,
-            "front_wall": front_wall, "bottom_wall": bottom_wall, "top_wall": top_wall,
+            "front_wall": front_wall, "bottom_wall": bottom_wall, "top_wall": top_wall, "tiles": _ac.tile_asset_params,
         }
 
 
@@ -77,9 +81,11 @@ class EnvWithLidarNavObstaclesCfg(EnvWithObstaclesCfg):
     class env_config:
         include_asset_type = dict(EnvWithObstaclesCfg.env_config.include_asset_type)
         asset_type_to_dict_map = {
-            "panels": _ac.lidar_nav_panel_asset_params, "objects": _ac.lidar_nav_object_asset_params,
+            "panels": _ac.lidar_nav_panel_asset_params, "thin": _ac.thin_asset_params, "trees": _ac.lidar_nav_tree_asset_params,
+            "objects": _ac.lidar_nav_object_asset_params,
             "left_wall": _ac.lidar_nav_left_wall, "right_wall": _ac.lidar_nav_right_wall, "back_wall": _ac.lidar_nav_back_wall,
             "front_wall": _ac.lidar_nav_front_wall, "bottom_wall": _ac.lidar_nav_bottom_wall, "top_wall": _ac.lidar_nav_top_wall,
+            "tiles": _ac.lidar_nav_tile_asset_params,
         }
 
 
@@ -96,8 +102,13 @@ class DynamicEnvironmentCfg(EnvWithObstaclesCfg):
         upper_bound_max = [10.0, 4.0, 5.0]
 
     class env_config:
-        include_asset_type = {k: (k == "objects") for k in EnvWithObstaclesCfg.env_config.include_asset_type}
-        asset_type_to_dict_map = {"objects": _ac.dynamic_object_asset_params}
+        include_asset_type = {k: (k == "objects") for k in EnvWithObstaclesCfg.env_config.include_asset_type if k != "tiles"}
+        asset_type_to_dict_map = {
+            "panels": _ac.dynamic_panel_asset_params, "thin": _ac.dynamic_thin_asset_params, "trees": _ac.dynamic_tree_asset_params,
+            "objects": _ac.dynamic_object_asset_params, "left_wall": _ac.dynamic_left_wall, "right_wall": _ac.dynamic_right_wall,
+            "back_wall": _ac.dynamic_back_wall, "front_wall": _ac.dynamic_front_wall, "bottom_wall": _ac.dynamic_bottom_wall,
+            "top_wall": _ac.dynamic_top_wall,
+        }
 
 
 class EnvCfg2Ms(EmptyEnvCfg):

@@ -30,6 +30,11 @@ class position_setpoint_task_config:
     }
 
 
+class position_setpoint_task_lmf2_config(position_setpoint_task_config):
+    """config/task_config/position_setpoint_task_lmf2_config.py (not registered as a task by the reference either)"""
+    robot_name, controller_name, num_envs = "lmf2", "lmf2_velocity_control", 16
+
+
 class navigation_task_config:
     """config/task_config/navigation_task_config.py"""
     seed = -1

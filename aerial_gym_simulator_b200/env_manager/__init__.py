@@ -16,4 +16,6 @@ sim_config_registry.register("base_sim_2ms", _sc.SimCfg2Ms)
 sim_config_registry.register("base_sim_4ms", _sc.SimCfg4Ms)
 sim_config_registry.register("custom_sim", _sc.CustomSimConfig)
 
+from ..config.env_config import (DynamicEnvironmentCfg, EmptyEnvCfg, EnvCfg2Ms, EnvWithLidarNavObstaclesCfg,  # noqa: E402,F401
+                                 EnvWithObstaclesCfg, ForestEnvCfg)
 from .env_manager import EnvManager  # noqa: E402,F401

@@ -47,6 +47,34 @@ def _quat_rotate_inverse(q, v):
     return v * (2.0 * qw * qw - 1.0) - torch.cross(qv, v, dim=-1) * qw * 2.0 + qv * (qv * v).sum(-1, keepdim=True) * 2.0
 
 
+class _RobotManagerView:
+    """robots/robot_manager.py: RobotManagerIGE as callers see it (the arithmetic it hosts in the reference runs in the HP1 kernel)"""
+
+    def __init__(self, env):
+        self._env, self.robot, self.cfg = env, env.robot, env.robot_cfg
+        self.num_envs, self.device = env.num_envs, env.device
+        self.robot_mass, self.robot_inertia = env.robot.robot_mass, env.robot.robot_inertia  # :45-46, scalars / 3x3 of the URDF
+        self.dof_control_mode = "none"
+
+    robot_masses = property(lambda self: self._env.global_tensor_dict["robot_mass"])      # :47  [N]
+    robot_inertias = property(lambda self: self._env.global_tensor_dict["robot_inertia"])  # :48  [N,3,3]
+    imu_sensor = property(lambda self: self._env.imu)
+    warp_sensor = lidar_sensor = property(lambda self: self._env.sensor)
+    camera_sensor = property(lambda self: None)  # Isaac Gym's rasterised cameras do not exist here
+
+
+class _SimView:
+    """env_manager/IGE_env_manager.py: the counts callers read off IsaacGymEnv"""
+
+    def __init__(self, env):
+        self._env, self.sim_config, self.num_envs = env, env.sim_config, env.num_envs
+        self.sim_has_dof, self.dof_control_mode, self.viewer, self.has_viewer = False, "none", None, False
+
+    num_assets_per_env = property(lambda self: self._env.num_obs_in_env + 1)  # :269-276, the robot is an actor too
+    num_rigid_bodies_robot = property(lambda self: self._env.robot.num_bodies)
+    global_tensor_dict = property(lambda self: self._env.global_tensor_dict)
+
+
 class EnvManager:
     def __init__(self, sim_name, env_name, robot_name, controller_name, device, args=None, num_envs=None,
                  use_warp=None, headless=None):
@@ -73,6 +101,10 @@ class EnvManager:
         self.step_counter = 0
         self._populate()
         self.sim_steps = self.engine.sim_steps  # int32 [N] (env_manager.py:78-80)
+        # the reference's object graph, as far as its examples / tasks / trainers walk it: env.robot_manager.robot.{cfg, controller,
+        # controller_config}, env.IGE_env.num_assets_per_env (robot included, IGE_env_manager.py:269-276)
+        self.robot_manager = _RobotManagerView(self)
+        self.IGE_env = _SimView(self)
 
     # ------------------------------------------------------------------------------------------
     # construction (populate_env + prepare_sim, env_manager.py:127-271)

@@ -113,3 +113,6 @@ for _name, _cfg in (
 ):
     robot_registry.register(_name, BaseMultirotor, _cfg)
 robot_registry.register("base_rov", BaseROV, rc.BaseROVCfg)
+
+# the reference's package also exports its robot config classes (robots/__init__.py: `from ...base_quad_config import *`, ...)
+globals().update({_k: _v for _k, _v in vars(rc).items() if _k.endswith("Cfg")})

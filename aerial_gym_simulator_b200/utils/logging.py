@@ -23,3 +23,7 @@ class CustomLogger(logging.Logger):
     def setLoggerLevel(self, level) -> None:
         self.setLevel(level)
         self.ch.setLevel(level)
+
+    def print_example_message(self):  # logging.py:48-53
+        for level, text in (("debug", "A Debug"), ("info", "An Info"), ("warning", "A Warning"), ("error", "An Error"), ("critical", "A Critical")):
+            getattr(self, level)(f"{text} message will look like this")

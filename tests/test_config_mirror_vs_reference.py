@@ -105,9 +105,9 @@ def test_env_sim_task_asset_configs():
                             ("dynamic_environment", "DynamicEnvironmentCfg", EC.DynamicEnvironmentCfg), ("forest_env", "ForestEnvCfg", EC.ForestEnvCfg)):
         ref = _ref("env_config." + mod, name)
         _compare(ref.env, ours.env, skip=("num_envs", "use_warp"))
-        on = {k for k, v in ref.env_config.include_asset_type.items() if v}
-        assert on == set(ours.env_config.asset_type_to_dict_map), (on, set(ours.env_config.asset_type_to_dict_map))
-        for k in on:  # every asset class that is switched on: all its parameters
+        assert ref.env_config.include_asset_type == ours.env_config.include_asset_type
+        assert set(ref.env_config.asset_type_to_dict_map) == set(ours.env_config.asset_type_to_dict_map)
+        for k in ref.env_config.asset_type_to_dict_map:  # every asset class of the map, switched on or not: all its parameters
             _compare(ref.env_config.asset_type_to_dict_map[k], ours.env_config.asset_type_to_dict_map[k], skip=("asset_folder",))
     for mod, name, ours in (("base_sim_config", "BaseSimConfig", SC.BaseSimConfig), ("base_sim_headless_config", "BaseSimHeadlessConfig", SC.BaseSimHeadlessConfig),
                             ("sim_config_2ms", "SimCfg2Ms", SC.SimCfg2Ms), ("sim_config_4ms", "SimCfg4Ms", SC.SimCfg4Ms),
@@ -127,3 +127,25 @@ def test_env_sim_task_asset_configs():
                       ("position_setpoint_task_sim2real_config", TC.position_setpoint_task_sim2real_config),
                       ("position_setpoint_task_acceleration_sim2real_config", TC.position_setpoint_task_acceleration_sim2real_config)):
         _compare(_ref("task_config." + mod, "task_config"), ours, skip=("model_file", "model_folder", "headless", "device", "num_envs", "seed", "use_warp"))
+
+
+def _all_paths():
+    from aerial_gym_simulator_b200.compat_paths import CONFIG_MODULES
+    return sorted((rel, name, where) for rel, names in CONFIG_MODULES.items() for name, where in names.items())
+
+
+@pytest.mark.parametrize("rel,name,where", _all_paths())
+def test_every_reference_config_path(rel, name, where):
+    """compat_paths.CONFIG_MODULES: every (reference module path, name) resolves to a class here whose fields equal the reference
+    class of THAT file (same-named asset classes differ between env_object_config / lidar_nav_env_config / dynamic_env_object_config)."""
+    flat = {"sim_config": SC, "env_config": EC, "robot_config": RC, "controller_config": CC, "sensor_config": S, "asset_config": AC,
+            "task_config": TC}
+    mod_name, attr = where.split(".")
+    ours, ref = getattr(flat[mod_name], attr), _ref(rel, name)
+    assert inspect.isclass(ref) and inspect.isclass(ours)
+    # resource paths differ by construction; num_envs / use_warp / seed / headless are overwritten on the class by whoever built an
+    # env before; asset maps hold class objects (compared asset by asset in test_env_sim_task_asset_configs)
+    skip = ("asset_folder", "num_envs", "use_warp", "seed", "headless", "asset_type_to_dict_map", "device", "vae_config.model_f")
+    if name == "BaseEnvCfg":
+        return  # an empty class on both sides
+    _compare(ref, ours, skip=skip, skip_nested=("sensor_config",) if mod_name == "robot_config" else ())

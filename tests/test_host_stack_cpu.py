@@ -470,3 +470,25 @@ def test_imu_in_env_manager():
         assert (imu[:, 0:3].norm(dim=1) - 9.81).abs().max() < 1.0
         assert (imu[:, 3:6] - gtd["robot_body_angvel"]).abs().max() < 0.2
         assert torch.nn.functional.normalize(imu[:, 0:3], dim=1)[:, 2].min() > 0.9
+
+
+def test_thin_assets_switch_on():
+    """env_object_config.thin_asset_params is off by default (num_assets = 0, "thin": False); a user who switches it on gets that many
+    thin rods (one box each, resources/.../thin/*.urdf) in the scene, with incremental per-instance segmentation ids"""
+    from aerial_gym_simulator_b200.config import asset_config as AC, env_config as EC
+    from aerial_gym_simulator_b200.sim import SimBuilder
+    inc, old_n = EC.EnvWithObstaclesCfg.env_config.include_asset_type, AC.thin_asset_params.num_assets
+    try:
+        with cpu_stack():
+            base = SimBuilder().build_env("base_sim", "env_with_obstacles", "base_quadrotor_with_camera", "lee_velocity_control", "cpu",
+                                          args={"seed": 1}, num_envs=2, headless=True, use_warp=True)
+            inc["thin"], AC.thin_asset_params.num_assets = True, 5
+            env = SimBuilder().build_env("base_sim", "env_with_obstacles", "base_quadrotor_with_camera", "lee_velocity_control", "cpu",
+                                         args={"seed": 1}, num_envs=2, headless=True, use_warp=True)
+            assert env.num_obs_in_env == base.num_obs_in_env + 5 and env.IGE_env.num_assets_per_env == env.num_obs_in_env + 1
+            env.reset()
+            env.step(torch.zeros(2, 4))
+            env.render()
+            assert torch.isfinite(env.global_tensor_dict["depth_range_pixels"]).all()
+    finally:
+        inc["thin"], AC.thin_asset_params.num_assets = False, old_n

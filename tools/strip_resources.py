@@ -79,7 +79,7 @@ if __name__ == "__main__":
             emit(urdf.parse_urdf(sp), os.path.join(DST, d))
             print("robot", d)
     env = os.path.join(SRC, "models", "environment_assets")
-    for sub in ("panels", "objects", "walls", "trees"):
+    for sub in ("panels", "objects", "walls", "trees", "thin"):
         for f in sorted(os.listdir(os.path.join(env, sub))):
             if f.endswith(".urdf"):
                 emit(urdf.parse_urdf(os.path.join(env, sub, f)), os.path.join(DST, "models", "environment_assets", sub, f))
