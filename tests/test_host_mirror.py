@@ -166,7 +166,8 @@ def test_lidar_navigation_task_surface_and_config():
     assert (L.height, L.width, L.return_pointcloud, L.pointcloud_in_world_frame, L.normalize_range) == (48, 120, True, True, False)
     env = env_config_registry.make_env("env_with_lidar_nav_obstacles")
     m = env.env_config.asset_type_to_dict_map
-    assert sum(p.num_assets for p in m.values()) == 15 + 70 + 6 and not any(p.keep_in_env for p in m.values())
+    on = [p for k, p in m.items() if env.env_config.include_asset_type.get(k, True)]  # (thin / trees / tiles are in the map, switched off)
+    assert sum(p.num_assets for p in on) == 15 + 70 + 6 and not any(p.keep_in_env for p in m.values())
     assert m["panels"].min_state_ratio[0] == 0.35 and m["objects"].max_state_ratio[0:3] == [1.0, 1.0, 1.0]
     assert env.env.lower_bound_min == [-7.5, -7.5, -5.0] and env.env.upper_bound_max == [7.5, 7.5, 5.0]
     assert ac.panel_asset_params.num_assets == 3 and ac.left_wall.keep_in_env  # the navigation-task scene is untouched
@@ -192,6 +193,8 @@ def test_dynamic_env_config():
     """config/env_config/dynamic_environment.py + dynamic_env_object_config.py"""
     env = env_config_registry.make_env("dynamic_env")
     m = env.env_config.asset_type_to_dict_map
-    assert list(m) == ["objects"] and m["objects"].num_assets == 40 and not m["objects"].fix_base_link and m["objects"].disable_gravity
+    on = [k for k in m if env.env_config.include_asset_type.get(k, True)]
+    assert on == ["objects"] and m["objects"].num_assets == 40 and not m["objects"].fix_base_link and m["objects"].disable_gravity
+    assert all(p.disable_gravity and not p.fix_base_link for p in m.values())  # every class of that file floats
     assert env.env.num_env_actions == 6 and env.env.write_to_sim_at_every_timestep and env.env.lower_bound_min[2] == 0.0
     assert env.env.num_physics_steps_per_env_step_mean == 10
