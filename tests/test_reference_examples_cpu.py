@@ -90,3 +90,32 @@ def test_position_control_example_rov():
         _run("position_control_example_rov.py", 20)
     g, _ = _run("position_control_example_rov.py", 20, subst=[('"fully_actuated_control"', '"rov_fully_actuated_control"')])
     assert g["actions"].shape == (64, 7) and torch.isfinite(g["env_manager"].global_tensor_dict["robot_state_tensor"]).all()
+
+
+@pytest.fixture
+def fake_matplotlib(monkeypatch):
+    """matplotlib is not installed: the camera scripts only use cm.plasma(x) -> RGBA in [0, 1]"""
+    import types
+
+    import numpy as np
+    mpl, cm, image = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.cm"), types.ModuleType("matplotlib.image")
+    cm.plasma = lambda x: np.stack([x, 1.0 - x, 0.5 * np.ones_like(x), np.ones_like(x)], axis=-1)
+    mpl.cm, mpl.image = cm, image
+    for name, mod in (("matplotlib", mpl), ("matplotlib.cm", cm), ("matplotlib.image", image)):
+        monkeypatch.setitem(sys.modules, name, mod)
+
+
+def test_save_camera_stream_example(fake_matplotlib, tmp_path, monkeypatch):
+    """stereo depth camera + segmentation in env_with_obstacles; 2 frames (the gif-saving branch needs 100)"""
+    monkeypatch.chdir(tmp_path)
+    g, _ = _run("save_camera_stream.py", 2)
+    env = g["env_manager"]
+    assert env.sensor is not None and "stereo" in env.robot_manager.robot.cfg.sensor_config.camera_config.__name__.lower()
+    assert len(g["depth_frames"]) == 2 and g["depth_frames"][0].size == (g["image1"].shape[1], g["image1"].shape[0])
+    assert g["seg_image1_normalized"].min() == 0.0 and g["seg_image1_normalized"].max() == 1.0
+
+
+def test_save_camera_stream_normal_faceID_example(fake_matplotlib, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    g, _ = _run("save_camera_stream_normal_faceID.py", 2)
+    assert g["env_manager"].sensor is not None and len(g["merged_image_frames"]) == 2
