@@ -119,3 +119,26 @@ def test_save_camera_stream_normal_faceID_example(fake_matplotlib, tmp_path, mon
     monkeypatch.chdir(tmp_path)
     g, _ = _run("save_camera_stream_normal_faceID.py", 2)
     assert g["env_manager"].sensor is not None and len(g["merged_image_frames"]) == 2
+
+
+def test_user_subclass_of_navigation_task():
+    """examples/dce_rl_navigation/dce_navigation_task.py: a USER subclass of NavigationTask that overrides process_obs_for_task and reads
+    the parent's attributes (obs_dict, task_obs, target_position, image_latents) -- the class-level contract, not only the call surface"""
+    import aerial_gym_simulator_b200.compat as compat
+    compat.install()
+    from aerial_gym_simulator_b200.config.task_config import navigation_task_config
+    path = os.path.join(EX, "dce_rl_navigation", "dce_navigation_task.py")
+    g = {"__name__": "dce_navigation_task", "__file__": path}
+    exec(compile(open(path).read(), path, "exec"), g)
+    cfg = type("cfg", (navigation_task_config,), {"curriculum": type("curriculum", (navigation_task_config.curriculum,), {})})
+    cfg.device, cfg.num_envs = "cpu", 32
+    with cpu_stack() as proxy:
+        task = g["DCE_RL_Navigation_Task"](cfg, seed=1, headless=True)
+        assert task.task_config.num_envs == 16 and task.task_config.action_space_dim == 3 and task.task_config.curriculum.min_level == 36
+        task.reset()
+        for _ in range(2):
+            obs, rew, term, trunc, info = task.step(torch.zeros(16, 3))
+    o = obs["observations"]
+    assert o.shape == (16, 81) and torch.isfinite(o).all() and (o[:, 6] == 0).all()
+    assert torch.allclose(o[:, 0:3].norm(dim=1), torch.ones(16), atol=1e-5)  # the subclass's own layout: unit vector, distance / 5
+    assert torch.equal(o[:, 17:81], task.image_latents) and proxy.calls["agx_nav_reward"] == 2 and "agx_nav_obs" not in proxy.calls
