@@ -192,3 +192,68 @@ def well_conditioned(model, st, actions):
         thr = 5e-3 * model.max_thrust
         ok &= ~((ref > 0) & (ref < thr)).any(dim=1)
     return ok
+
+
+def spec_from_registry(robot_name, controller_name):
+    """the product's own config -> spec path: registries + config mirror + URDF pipeline (robots/__init__.py: make_spec)"""
+    import aerial_gym_simulator_b200.robots  # noqa: F401
+    from aerial_gym_simulator_b200.config.env_config import EmptyEnvCfg
+    from aerial_gym_simulator_b200.config.sim_config import BaseSimConfig
+    from aerial_gym_simulator_b200.registry._core import robot_registry
+    robot, _ = robot_registry.make_robot(robot_name, controller_name, EmptyEnvCfg, "cpu")
+    return robot.make_spec(BaseSimConfig, EmptyEnvCfg)
+
+
+def check_engine_against_step_fixture(eng, spec, om, z, meta, sync=lambda: None):
+    """One engine (CUDA or host shadow, built with debug_wrench=True) against a fixture recorded from the REFERENCE'S OWN
+    BaseMultirotor.step (tests/golden/make_golden*.py): derived states and motor thrusts directly, link forces / torques through the
+    W f reduction.  om: the oracle model (only used to replay the reference's disturbance draws)."""
+    N = meta["N"]
+    dev = eng.root_state.device
+    T = lambda a: torch.tensor(a, device=dev)
+    for s in range(meta["steps"]):
+        eng.root_state.copy_(T(z[f"s{s}_root"]))
+        eng.motor_thrust.copy_(T(z[f"s{s}_thrust_in"]))
+        # per-env parameters: engines built with per_env_params="auto" keep a non-randomised parameter as a constant in
+        # AgxHp1Config instead of an [N, .] array -- then the reference must have used that same constant
+        for k in ("tau_inc", "tau_dec", "k_thrust", "K_pos", "K_vel", "K_rot", "K_angvel"):
+            if k not in z:
+                continue
+            if getattr(eng, k, None) is not None:
+                getattr(eng, k).copy_(T(z[k]))
+            else:
+                lo, hi = getattr(spec, k + "_range")
+                assert np.allclose(lo, hi) and np.allclose(z[k], np.broadcast_to(np.asarray(lo, dtype=np.float64), z[k].shape), rtol=1e-6), \
+                    f"{k}: randomised in the fixture but the engine holds a constant -- build it with per_env_params='all'"
+        dist = None
+        if meta["enable_disturbance"]:
+            om.enable_disturbance, om.prob_apply_disturbance = True, meta["prob_apply_disturbance"]
+            om.max_disturbance = tuple(meta["max_disturbance"])
+            torch.manual_seed(int(z[f"s{s}_seed"]))
+            dist = O.draw_disturbance(om, N).contiguous().to(dev)
+        eng.physics_step(T(z[f"s{s}_actions"]).contiguous(), disturbance=dist)
+        sync()
+        fs = max(1.0, float(np.abs(z[f"s{s}_thrust_out"]).max()))
+        assert_close(eng.motor_thrust, z[f"s{s}_thrust_out"], "thrust vs reference", scale=fs)
+        assert_close(eng.euler, z[f"s{s}_euler"], "euler vs reference", scale=np.pi)
+        assert_close(eng.vehicle_orientation, z[f"s{s}_vehicle_orientation"], "veh q vs reference", scale=1.0)
+        assert_close(eng.body_linvel, z[f"s{s}_body_linvel"], "body v vs reference")
+        assert_close(eng.body_angvel, z[f"s{s}_body_angvel"], "body w vs reference")
+        assert_close(eng.vehicle_linvel, z[f"s{s}_vehicle_linvel"], "veh v vs reference")
+        Fl, Tl = z[f"s{s}_force"].astype(np.float64), z[f"s{s}_torque"].astype(np.float64)
+        mask = meta["application_mask"]
+        F, Tq = Fl.sum(1), Tl.sum(1)
+        if spec.force_application_level == "motor_link":
+            # link-frame forces: rotate into the base frame and take their moment about the COM (identity rotations for every
+            # shipped robot except the tilted octarotor)
+            R = np.asarray(spec.link_R, dtype=np.float64)
+            Fb = np.einsum("mij,nmj->nmi", R, Fl[:, mask, :])
+            Tb = np.einsum("mij,nmj->nmi", R, Tl[:, mask, :])
+            rest = [b for b in range(Fl.shape[1]) if b not in mask]
+            F = Fb.sum(1) + Fl[:, rest, :].sum(1)
+            com = np.asarray(spec.com, dtype=np.float64)
+            Tq = Tb.sum(1) + Tl[:, rest, :].sum(1) + np.cross((np.asarray(spec.link_r) - com)[None], Fb).sum(1)
+            # drag / disturbance sit on body 0: the integrator spec (DESIGN 3) applies them at the base-link origin
+            Tq = Tq + np.cross(-com[None], Fl[:, rest, :].sum(1))
+        assert_close(eng.body_wrench[:, 0:3], F, "F_body vs reference", scale=fs)
+        assert_close(eng.body_wrench[:, 3:6], Tq, "T_body vs reference", scale=max(fs * 0.13, float(np.abs(Tq).max())))

@@ -87,40 +87,22 @@ def test_device_code_matches_reference_golden(path):
     meta = json.loads(bytes(z["meta"]).decode())
     om = oracle_model(meta["robot"], meta["controller"], meta["mass"], meta["inertia"])
     spec = MultirotorSpec(**{f: getattr(om, f) for f in MultirotorSpec.__dataclass_fields__})
-    N = meta["N"]
-    eng = ShadowHp1Engine(spec, N, debug_wrench=True)
-    T = lambda a: torch.tensor(a)
-    for s in range(meta["steps"]):
-        eng.root_state.copy_(T(z[f"s{s}_root"]))
-        eng.motor_thrust.copy_(T(z[f"s{s}_thrust_in"]))
-        eng.tau_inc.copy_(T(z["tau_inc"]))
-        eng.tau_dec.copy_(T(z["tau_dec"]))
-        if "k_thrust" in z and eng.k_thrust is not None:
-            eng.k_thrust.copy_(T(z["k_thrust"]))
-        if "K_pos" in z:
-            eng.K_pos.copy_(T(z["K_pos"])); eng.K_vel.copy_(T(z["K_vel"]))
-            eng.K_rot.copy_(T(z["K_rot"])); eng.K_angvel.copy_(T(z["K_angvel"]))
-        dist = None
-        if meta["enable_disturbance"]:
-            om.enable_disturbance, om.prob_apply_disturbance = True, meta["prob_apply_disturbance"]
-            om.max_disturbance = tuple(meta["max_disturbance"])
-            torch.manual_seed(int(z[f"s{s}_seed"]))
-            dist = O.draw_disturbance(om, N).contiguous()
-        eng.physics_step(T(z[f"s{s}_actions"]).contiguous(), disturbance=dist)
-        fs = max(1.0, float(np.abs(z[f"s{s}_thrust_out"]).max()))
-        H.assert_close(eng.motor_thrust, z[f"s{s}_thrust_out"], "thrust vs reference", scale=fs)
-        H.assert_close(eng.euler, z[f"s{s}_euler"], "euler vs reference", scale=np.pi)
-        H.assert_close(eng.vehicle_orientation, z[f"s{s}_vehicle_orientation"], "veh q vs reference", scale=1.0)
-        H.assert_close(eng.body_linvel, z[f"s{s}_body_linvel"], "body v vs reference")
-        H.assert_close(eng.body_angvel, z[f"s{s}_body_angvel"], "body w vs reference")
-        H.assert_close(eng.vehicle_linvel, z[f"s{s}_vehicle_linvel"], "veh v vs reference")
-        Fl, Tl = z[f"s{s}_force"].astype(np.float64), z[f"s{s}_torque"].astype(np.float64)
-        mask = meta["application_mask"]
-        F, Tq = Fl.sum(1), Tl.sum(1)
-        if spec.force_application_level == "motor_link":
-            Tq = Tq + np.cross((spec.link_r - spec.com)[None], Fl[:, mask, :]).sum(1)
-        H.assert_close(eng.body_wrench[:, 0:3], F, "F_body vs reference", scale=fs)
-        H.assert_close(eng.body_wrench[:, 3:6], Tq, "T_body vs reference", scale=max(fs * 0.13, float(np.abs(Tq).max())))
+    H.check_engine_against_step_fixture(ShadowHp1Engine(spec, meta["N"], debug_wrench=True), spec, om, z, meta)
+
+
+REG_FILES = sorted(glob.glob(os.path.join(GOLD, "hp1_regstep_*.npz")))
+
+
+@pytest.mark.parametrize("path", REG_FILES, ids=[os.path.basename(p)[12:-4] for p in REG_FILES])
+def test_registry_built_spec_matches_reference_golden(path):
+    """as above, for 13 more robot x controller pairs (magpie, x500, lmf1, lmf2, tinyprop, base_random, morphy_stiff, octarotor;
+    steering-angle controller), with the spec built by the PRODUCT's registries / config mirror / URDF pipeline"""
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    spec = H.spec_from_registry(meta["robot"], meta["controller"])
+    assert abs(spec.mass - meta["mass"]) < 1e-9 and np.allclose(spec.inertia, meta["inertia"], rtol=1e-12)
+    om = H.oracle_model_from_spec(spec)
+    H.check_engine_against_step_fixture(ShadowHp1Engine(spec, meta["N"], debug_wrench=True), spec, om, z, meta)
 
 
 def test_position_reward_block_matches_reference():

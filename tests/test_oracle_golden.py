@@ -51,7 +51,22 @@ def _close(a, b, rtol=2e-6, scale=1.0, what=""):
 def test_robot_step_matches_reference(path):
     """a1-a12: derived states, controller wrench, allocation, motor model, per-link wrenches."""
     z, meta = _load(path)
-    model = oracle_model(meta["robot"], meta["controller"], meta["mass"], meta["inertia"])
+    _check_oracle_against_step_fixture(oracle_model(meta["robot"], meta["controller"], meta["mass"], meta["inertia"]), z, meta)
+
+
+REG_FILES = sorted(glob.glob(os.path.join(GOLD, "hp1_regstep_*.npz")))
+
+
+@pytest.mark.parametrize("path", REG_FILES, ids=[os.path.basename(p)[12:-4] for p in REG_FILES])
+def test_robot_step_matches_reference_registry_models(path):
+    """the same for 13 more robot x controller pairs, the oracle model built from the product's registry spec
+    (tests/golden/make_golden_registry.py)"""
+    from tests import _hp1_common as H
+    z, meta = _load(path)
+    _check_oracle_against_step_fixture(H.oracle_model_from_spec(H.spec_from_registry(meta["robot"], meta["controller"])), z, meta)
+
+
+def _check_oracle_against_step_fixture(model, z, meta):
     mask = meta["application_mask"]
     for s in range(meta["steps"]):
         st = _state_from_fixture(model, z, meta, s)
