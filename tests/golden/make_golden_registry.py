@@ -43,6 +43,7 @@ CASES = [
     ("morphy_stiff_attitude", "morphy_stiff", "lee_attitude_control", 4, 62),
     ("octa_position", "base_octarotor", "octarotor_position_control", 4, 63),
     ("octa_acceleration", "base_octarotor", "octarotor_acceleration_control", 4, 64),
+    ("rov_fully_actuated", "base_rov", "rov_fully_actuated_control", 7, 65),  # the reference's BaseROV class (robots/base_rov.py)
 ]
 
 if __name__ == "__main__":
