@@ -122,6 +122,7 @@ class EnvManager:
             per_env_params=self.env_args.get("per_env_params", "auto"), host_io=bool(self.env_args.get("host_io", False)),
             debug_wrench=bool(getattr(self.robot_cfg.sensor_config, "enable_imu", False)))  # the IMU reads the net body force
         eng, gtd = self.engine, self.global_tensor_dict
+        self.robot.controller.bind_engine(eng)  # controller.K_*_tensor_current / set_controller_gains act on the engine's gains
         gtd["crashes"], gtd["truncations"] = eng.terminations, eng.truncations
         self.collision_tensor, self.truncation_tensor = eng.terminations, eng.truncations
         self.num_env_actions = self.cfg.env.num_env_actions

@@ -492,3 +492,42 @@ def test_thin_assets_switch_on():
             assert torch.isfinite(env.global_tensor_dict["depth_range_pixels"]).all()
     finally:
         inc["thin"], AC.thin_asset_params.num_assets = False, old_n
+
+
+@pytest.mark.parametrize("per_env", [False, True])
+def test_controller_gains_can_be_read_and_set_like_the_reference(per_env):
+    """examples/tune_controllers.py reads controller.K_*_tensor_current and calls controller.set_controller_gains(...) between steps
+    (base_lee_controller.py:59-62, 78-85).  Here the gains live in the engine (constants in AgxHp1Config, or per-env arrays)."""
+    from aerial_gym_simulator_b200.sim import SimBuilder
+    with cpu_stack():
+        args = {"seed": 1, "per_env_params": "all"} if per_env else {"seed": 1}
+        env = SimBuilder().build_env("base_sim", "empty_env", "base_quadrotor", "lee_position_control", "cpu", args=args, num_envs=8,
+                                     headless=True)
+        ctrl = env.robot_manager.robot.controller
+        assert torch.allclose(ctrl.K_pos_tensor_current, torch.tensor([2.5, 2.5, 1.5]).expand(8, 3))  # mid-point of the config range
+        assert torch.equal(ctrl.K_rot_tensor_max, torch.tensor([1.2, 1.2, 0.6]).expand(8, 3))
+        env.reset()
+        act = torch.zeros(8, 4)
+        act[:, 0] = 1.0
+
+        def run(gain_scale):
+            env.reset()
+            env.engine.root_state[:, 0:3] = 0.0
+            env.engine.root_state[:, 7:13] = 0.0
+            ctrl.set_controller_gains(gain_scale * torch.tensor([2.5, 2.5, 1.5]), ctrl.K_linvel_tensor_current.clone(),
+                                      ctrl.K_rot_tensor_current.clone(), ctrl.K_angvel_tensor_current.clone())
+            for _ in range(20):
+                env.step(act)
+            return env.global_tensor_dict["robot_position"][:, 0].clone()
+        slow, fast = run(0.5), run(2.0)
+        assert torch.allclose(ctrl.K_pos_tensor_current, 2.0 * torch.tensor([2.5, 2.5, 1.5]).expand(8, 3))
+        assert (fast > slow + 1e-4).all()  # a stiffer position loop moves further towards the setpoint in the same time
+        env.reset()
+        assert torch.allclose(ctrl.K_pos_tensor_current, 2.0 * torch.tensor([2.5, 2.5, 1.5]).expand(8, 3))  # not randomised: a reset keeps them
+        per_env_gain = torch.rand(8, 3) + 1.0
+        if per_env:
+            ctrl.set_controller_gains(per_env_gain, 2.5, 1.0, 0.15)
+            assert torch.equal(ctrl.K_pos_tensor_current, per_env_gain) and (ctrl.K_linvel_tensor_current == 2.5).all()
+        else:
+            with pytest.raises(RuntimeError, match="per_env_params"):
+                ctrl.set_controller_gains(per_env_gain, 2.5, 1.0, 0.15)
