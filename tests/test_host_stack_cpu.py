@@ -512,8 +512,10 @@ def test_controller_gains_can_be_read_and_set_like_the_reference(per_env):
 
         def run(gain_scale):
             env.reset()
-            env.engine.root_state[:, 0:3] = 0.0
-            env.engine.root_state[:, 7:13] = 0.0
+            env.engine.root_state[:] = 0.0  # same start for both runs: origin, level, at rest
+            env.engine.root_state[:, 6] = 1.0
+            env.engine.motor_thrust[:] = 0.25 * 9.81 / 4.0
+            env.engine.refresh()
             ctrl.set_controller_gains(gain_scale * torch.tensor([2.5, 2.5, 1.5]), ctrl.K_linvel_tensor_current.clone(),
                                       ctrl.K_rot_tensor_current.clone(), ctrl.K_angvel_tensor_current.clone())
             for _ in range(20):

@@ -22,8 +22,10 @@ def test_controller_gains_read_and_set(per_env):
 
     def run(scale):
         env.reset()
-        env.engine.root_state[:, 0:3] = 0.0
-        env.engine.root_state[:, 7:13] = 0.0
+        env.engine.root_state[:] = 0.0  # same start for both runs: origin, level, at rest
+        env.engine.root_state[:, 6] = 1.0
+        env.engine.motor_thrust[:] = 0.25 * 9.81 / 4.0
+        env.engine.refresh()
         ctrl.set_controller_gains(scale * mid, ctrl.K_linvel_tensor_current.clone(), ctrl.K_rot_tensor_current.clone(),
                                   ctrl.K_angvel_tensor_current.clone())
         for _ in range(20):
