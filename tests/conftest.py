@@ -21,8 +21,13 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     """GPU tests fail loudly (not skip) when selected on a box without CUDA: a silent skip
-    would hide a missing native path."""
-    return
+    would hide a missing native path.  Each one gets a wall-clock limit (pytest-timeout, where installed): a kernel that
+    never returns must end the run with a failure, not hold the GPU box until the driver's own limit."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900))
 
 
 @pytest.fixture(autouse=True)
