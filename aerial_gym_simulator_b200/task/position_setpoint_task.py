@@ -68,6 +68,8 @@ class PositionSetpointTask(BaseTask):
         self.target_position[:, 0:3] = 0.0
         self.infos = {}
         self.sim_env.reset()
+        if self._overridden("process_obs_for_task"):
+            self.process_obs_for_task()
         return self.get_return_tuple()
 
     def reset_idx(self, env_ids):
@@ -83,6 +85,8 @@ class PositionSetpointTask(BaseTask):
         env, eng = self.sim_env, self.sim_env.engine
         if actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.float().contiguous()
+        if self._overridden("compute_rewards_and_crashes"):
+            return self._step_with_reward_hook(actions)
         if eng.host_io and actions.device.type == "cpu" and not actions.is_pinned():
             eng.host_actions.copy_(actions)  # pageable host memory: stage through the mapped buffer
             actions = eng.host_actions
@@ -102,7 +106,60 @@ class PositionSetpointTask(BaseTask):
         if eng.host_io:
             torch.cuda.current_stream(eng.device).synchronize()  # results are in host memory now
         self.infos = {}
+        if self._overridden("process_obs_for_task"):
+            self.process_obs_for_task()
         return self.get_return_tuple()
 
     def get_return_tuple(self):
+        return (self.task_obs, self.rewards, self.terminations, self.truncations, self.infos)
+
+    # ------------------------------------------------------------------------------------------
+    # The reference's two hooks (position_setpoint_task.py:194-229).  For THIS class they are fused into the step kernel and never
+    # called.  A subclass that overrides one gets the reference's behaviour:
+    #   * only process_obs_for_task overridden: the fused step runs (reward, crash, truncation, reset, default observation in one
+    #     launch), then the override rewrites task_obs -- same point in the sequence as get_return_tuple's call in the reference;
+    #   * compute_rewards_and_crashes overridden: the step runs in the reference's order with the same kernels un-fused
+    #     (physics launch -> the override -> truncation -> reset of finished envs -> observation hook).
+    # The bodies below are what an override reaches through super(): plain torch on the env's device tensors.
+    # ------------------------------------------------------------------------------------------
+    def _overridden(self, name):
+        return getattr(type(self), name) is not getattr(PositionSetpointTask, name)
+
+    def process_obs_for_task(self):
+        od, o = self.obs_dict, self.task_obs["observations"]
+        o[:, 0:3] = self.target_position - od["robot_position"]
+        o[:, 3:7] = od["robot_orientation"]
+        o[:, 7:10] = od["robot_body_linvel"]
+        o[:, 10:13] = od["robot_body_angvel"]
+        self.task_obs["rewards"], self.task_obs["terminations"], self.task_obs["truncations"] = self.rewards, self.terminations, self.truncations
+
+    def compute_rewards_and_crashes(self, obs_dict):
+        """(reward [N], crashes [N] bool) of compute_reward (:245-282); writes the distance crashes into obs_dict["crashes"] like it"""
+        q, crashes = obs_dict["robot_orientation"], obs_dict["crashes"]
+        # the norm is rotation invariant, so the vehicle-frame rotation of the position error (:219-221) drops out
+        dist = torch.norm(self.target_position - obs_dict["robot_position"], dim=1)
+        pos_reward = 3.0 * torch.exp(-8.0 * dist * dist) + 2.0 * torch.exp(-4.0 * dist * dist)
+        up_z = 1.0 - 2.0 * (q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1])  # z component of the body z axis
+        tilt = torch.abs(1.0 - up_z)
+        spin = torch.norm(obs_dict["robot_body_angvel"], dim=1)
+        reward = pos_reward + (20.0 - dist) / 40.0 + pos_reward * (0.2 / (0.1 + tilt * tilt) + 3.0 / (1.0 + spin * spin))
+        crashes |= dist > 8.0
+        return torch.where(crashes, torch.full_like(reward, -20.0), reward), crashes
+
+    def _step_with_reward_hook(self, actions):
+        env, cfg = self.sim_env, self.task_config
+        if env.engine.host_io:
+            raise NotImplementedError("args['host_io'] is a feature of the fused step; a reward override runs the un-fused sequence")
+        self.prev_actions, self.actions = self.actions, actions
+        env.step(actions=actions)                                                     # :163
+        rew, crashes = self.compute_rewards_and_crashes(self.obs_dict)                # :168
+        self.rewards[:], self.terminations[:] = rew, crashes
+        before = self._hook_return_tuple() if cfg.return_state_before_reset else None  # :170-171
+        self.truncations[:] = env.sim_steps > cfg.episode_len_steps                   # :172-174
+        env.post_reward_calculation_step()                                            # :175
+        self.infos = {}
+        return before if before is not None else self._hook_return_tuple()
+
+    def _hook_return_tuple(self):
+        self.process_obs_for_task()
         return (self.task_obs, self.rewards, self.terminations, self.truncations, self.infos)

@@ -198,3 +198,19 @@ def test_dynamic_env_config():
     assert all(p.disable_gravity and not p.fix_base_link for p in m.values())  # every class of that file floats
     assert env.env.num_env_actions == 6 and env.env.write_to_sim_at_every_timestep and env.env.lower_bound_min[2] == 0.0
     assert env.env.num_physics_steps_per_env_step_mean == 10
+
+
+def test_position_task_default_reward_hook_matches_reference_fixture():
+    """PositionSetpointTask.compute_rewards_and_crashes (the torch body a subclass reaches through super(); the base class itself uses
+    the fused kernel) against the fixture recorded from the reference's compute_reward, including pre-set collision flags"""
+    import torch
+
+    from aerial_gym_simulator_b200.task.position_setpoint_task import PositionSetpointTask
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hp1_position_reward.npz"))
+    n = z["pos"].shape[0]
+    fake = type("T", (), {"target_position": torch.zeros(n, 3)})()
+    od = {"robot_position": torch.tensor(z["pos"]), "robot_orientation": torch.tensor(z["quat"]),
+          "robot_body_angvel": torch.tensor(z["body_angvel"]), "crashes": torch.tensor(z["crashes_in"]).clone()}
+    rew, crashes = PositionSetpointTask.compute_rewards_and_crashes(fake, od)
+    assert torch.equal(crashes, torch.tensor(z["crashes_out"])) and crashes is od["crashes"]
+    assert torch.allclose(rew, torch.tensor(z["reward"]), rtol=1e-5, atol=1e-5)

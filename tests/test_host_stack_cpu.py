@@ -533,3 +533,58 @@ def test_controller_gains_can_be_read_and_set_like_the_reference(per_env):
         else:
             with pytest.raises(RuntimeError, match="per_env_params"):
                 ctrl.set_controller_gains(per_env_gain, 2.5, 1.0, 0.15)
+
+
+def _position_task_cfg(**kw):
+    from aerial_gym_simulator_b200.config.task_config import position_setpoint_task_config as C
+    return type("cfg", (C,), dict(device="cpu", num_envs=48, episode_len_steps=6, reward_parameters=dict(C.reward_parameters), **kw))
+
+
+def test_position_task_hooks_can_be_overridden_like_in_the_reference():
+    """position_setpoint_task.py:194-229: process_obs_for_task / compute_rewards_and_crashes are methods a user subclass may override.
+    The base class fuses both into the step kernel; with an override the step keeps the reference's order.  Checked against a fused
+    run of the base class on the same seed (same Philox reset streams): rewards differ exactly by the override's bonus, terminations /
+    truncations / resets coincide, and the default hooks reached through super() reproduce the kernel's values."""
+    from aerial_gym_simulator_b200.task.position_setpoint_task import PositionSetpointTask
+
+    class ObsOnly(PositionSetpointTask):
+        def process_obs_for_task(self):
+            super().process_obs_for_task()
+            self.task_obs["observations"][:, 0:3] *= 0.5
+
+    class RewardToo(PositionSetpointTask):
+        calls = 0
+
+        def compute_rewards_and_crashes(self, obs_dict):
+            type(self).calls += 1
+            rew, crashes = super().compute_rewards_and_crashes(obs_dict)
+            return rew + 1.25, crashes
+
+    with cpu_stack():
+        base = PositionSetpointTask(_position_task_cfg(), seed=5, headless=True)
+        obs_only = ObsOnly(_position_task_cfg(), seed=5, headless=True)
+        rew_too = RewardToo(_position_task_cfg(), seed=5, headless=True)
+        tasks = (base, obs_only, rew_too)
+        for t in tasks:
+            t.reset()
+        assert torch.allclose(obs_only.task_obs["observations"][:, 0:3], 0.5 * base.task_obs["observations"][:, 0:3])
+        g = torch.Generator().manual_seed(0)
+        resets = 0
+        for step in range(16):
+            a = torch.rand(48, 4, generator=g) * 2 - 1
+            if step == 3:  # fly three envs out of the 8 m crash radius
+                for t in tasks:
+                    t.sim_env.engine.root_state[5:8, 0] = 9.0
+            outs = [t.step(a.clone()) for t in tasks]
+            (o0, r0, te0, tr0, _), (o1, r1, te1, tr1, _), (o2, r2, te2, tr2, _) = outs
+            assert torch.equal(te0, te1) and torch.equal(te0, te2) and torch.equal(tr0, tr1) and torch.equal(tr0, tr2), step
+            resets += int((te0 | tr0).sum())
+            if step == 3:
+                assert te0[5:8].all() and int(te0.sum()) == 3  # crashed, and (device RNG) already re-initialised inside the same step
+            assert torch.allclose(r1, r0, rtol=1e-6, atol=1e-6) and torch.allclose(r2, r0 + 1.25, rtol=1e-5, atol=1e-5), step
+            assert torch.allclose(o1["observations"][:, 3:], o0["observations"][:, 3:], atol=1e-6)
+            assert torch.allclose(o1["observations"][:, 0:3], 0.5 * o0["observations"][:, 0:3], atol=1e-6)
+            assert torch.allclose(o2["observations"], o0["observations"], rtol=1e-5, atol=1e-5), step
+            assert torch.equal(base.sim_env.sim_steps, rew_too.sim_env.sim_steps)
+        assert resets == 48 * 2 and RewardToo.calls == 16  # two episodes end per env in 16 steps (6-step episodes), crashed or not
+        assert int(base.sim_env.engine.episode_count.min()) >= 2

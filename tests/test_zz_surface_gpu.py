@@ -53,3 +53,34 @@ def test_object_graph_views():
     torch.cuda.synchronize()
     assert torch.isfinite(env.global_tensor_dict["depth_range_pixels"]).all()
     env.delete_env()
+
+
+def test_position_task_hooks_overridden():
+    """a subclass overriding compute_rewards_and_crashes runs the un-fused sequence (physics launch -> hook -> truncation -> reset ->
+    observation hook); against the fused base class on the same seed: same flags and resets, rewards differ by the override's bonus"""
+    from aerial_gym_simulator_b200.config.task_config import position_setpoint_task_config as C
+    from aerial_gym_simulator_b200.task.position_setpoint_task import PositionSetpointTask
+
+    class RewardToo(PositionSetpointTask):
+        def compute_rewards_and_crashes(self, obs_dict):
+            rew, crashes = super().compute_rewards_and_crashes(obs_dict)
+            return rew + 1.25, crashes
+
+    cfg = lambda: type("cfg", (C,), dict(device=DEV, num_envs=256, episode_len_steps=6, reward_parameters=dict(C.reward_parameters)))
+    base, hooked = PositionSetpointTask(cfg(), seed=5, headless=True), RewardToo(cfg(), seed=5, headless=True)
+    base.reset()
+    hooked.reset()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for step in range(16):
+        a = torch.rand(256, 4, device=DEV, generator=g) * 2 - 1
+        if step == 3:
+            base.sim_env.engine.root_state[5:8, 0] = 9.0
+            hooked.sim_env.engine.root_state[5:8, 0] = 9.0
+        o0, r0, te0, tr0, _ = base.step(a.clone())
+        o1, r1, te1, tr1, _ = hooked.step(a.clone())
+        torch.cuda.synchronize()
+        assert torch.equal(te0, te1) and torch.equal(tr0, tr1), step
+        assert torch.allclose(r1, r0 + 1.25, rtol=1e-5, atol=1e-5) and torch.allclose(o1["observations"], o0["observations"], rtol=1e-5, atol=1e-5), step
+    assert torch.equal(base.sim_env.sim_steps, hooked.sim_env.sim_steps) and int(base.sim_env.engine.episode_count.min()) >= 2
+    base.close()
+    hooked.close()
