@@ -85,8 +85,8 @@ class PositionSetpointTask(BaseTask):
         env, eng = self.sim_env, self.sim_env.engine
         if actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.float().contiguous()
-        if self._overridden("compute_rewards_and_crashes"):
-            return self._step_with_reward_hook(actions)
+        if self._overridden("compute_rewards_and_crashes") or self.task_config.return_state_before_reset:
+            return self._step_with_reward_hook(actions)  # (the fused step resets inside the launch: nothing to return "before")
         if eng.host_io and actions.device.type == "cpu" and not actions.is_pinned():
             eng.host_actions.copy_(actions)  # pageable host memory: stage through the mapped buffer
             actions = eng.host_actions
@@ -156,9 +156,13 @@ class PositionSetpointTask(BaseTask):
         self.rewards[:], self.terminations[:] = rew, crashes
         before = self._hook_return_tuple() if cfg.return_state_before_reset else None  # :170-171
         self.truncations[:] = env.sim_steps > cfg.episode_len_steps                   # :172-174
+        kept = self.task_obs["observations"].clone() if before is not None else None
         env.post_reward_calculation_step()                                            # :175
         self.infos = {}
-        return before if before is not None else self._hook_return_tuple()
+        if before is None:
+            return self._hook_return_tuple()
+        self.task_obs["observations"].copy_(kept)  # (the engine's refresh after a reset rewrites its observation buffer)
+        return before
 
     def _hook_return_tuple(self):
         self.process_obs_for_task()

@@ -588,3 +588,17 @@ def test_position_task_hooks_can_be_overridden_like_in_the_reference():
             assert torch.equal(base.sim_env.sim_steps, rew_too.sim_env.sim_steps)
         assert resets == 48 * 2 and RewardToo.calls == 16  # two episodes end per env in 16 steps (6-step episodes), crashed or not
         assert int(base.sim_env.engine.episode_count.min()) >= 2
+
+
+def test_position_task_return_state_before_reset():
+    """task_config.return_state_before_reset = True (position_setpoint_task.py:170-171): the observation returned for an env that just
+    crashed is the one BEFORE its reset -- served by the un-fused sequence (the fused step resets inside the launch)"""
+    from aerial_gym_simulator_b200.task.position_setpoint_task import PositionSetpointTask
+    with cpu_stack():
+        task = PositionSetpointTask(_position_task_cfg(return_state_before_reset=True), seed=2, headless=True)
+        task.reset()
+        task.sim_env.engine.root_state[3, 0] = 9.5
+        obs, rew, term, trunc, _ = task.step(torch.zeros(48, 4))
+        assert bool(term[3]) and int(term.sum()) == 1 and float(rew[3]) == -20.0
+        assert abs(float(obs["observations"][3, 0]) + 9.5) < 0.2  # target - position of the crashed state, not of the new episode
+        assert abs(float(task.obs_dict["robot_position"][3, 0])) <= 1.0 and int(task.sim_env.sim_steps[3]) == 0  # ... which has begun
