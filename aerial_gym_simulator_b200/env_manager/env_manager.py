@@ -476,6 +476,25 @@ class EnvManager:
         self.engine.sim_steps += 1
         self.step_counter += 1
 
+    def simulate(self, actions, env_actions=None):
+        """ONE physics step (env_manager.py:346-349: pre_physics_step -> physics -> post_physics_step), for callers that drive the loop
+        themselves; step() batches the n physics steps of an env step into as few launches as the env allows"""
+        gtd = self.global_tensor_dict
+        gtd["robot_prev_actions"][:] = gtd["robot_actions"]
+        gtd["robot_actions"][:] = actions
+        self.engine.physics_step(gtd["robot_actions"], disturbance=self._draw_disturbance(), physics_steps=1)
+        if env_actions is not None and self.num_obs_in_env > 1:
+            self._step_obstacles(env_actions, 1)
+
+    def render_viewer(self):
+        return None  # headless by construction: there is no Isaac Gym viewer (env_manager.py:389-391)
+
+    def log_memory_use(self):
+        if self.device.type == "cuda":  # env_manager.py:303-326
+            gb = 1024.0 ** 3
+            print(f"torch.cuda.memory_allocated: {torch.cuda.memory_allocated(self.device) / gb:.3f} GB, "
+                  f"reserved: {torch.cuda.memory_reserved(self.device) / gb:.3f} GB, max reserved: {torch.cuda.max_memory_reserved(self.device) / gb:.3f} GB")
+
     def _step_obstacles(self, twist, n):
         """dynamic_env: the obstacles' twist is overwritten with env_actions [N,A,6] before each of the n physics steps and
         the obstacles move (PhysX in the reference; agx_obstacle_step's kinematic advance here, one launch for the n steps).

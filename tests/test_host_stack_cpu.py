@@ -602,3 +602,23 @@ def test_position_task_return_state_before_reset():
         assert bool(term[3]) and int(term.sum()) == 1 and float(rew[3]) == -20.0
         assert abs(float(obs["observations"][3, 0]) + 9.5) < 0.2  # target - position of the crashed state, not of the new episode
         assert abs(float(task.obs_dict["robot_position"][3, 0])) <= 1.0 and int(task.sim_env.sim_steps[3]) == 0  # ... which has begun
+
+
+def test_simulate_is_one_physics_step():
+    """EnvManager.simulate (env_manager.py:346-349) for callers that drive the physics loop themselves: n calls == one step() of an
+    env with n physics steps per env step (same kernels, same state), minus the env-step bookkeeping (sim_steps, collision flags)"""
+    from aerial_gym_simulator_b200.sim import SimBuilder
+    with cpu_stack():
+        mk = lambda: SimBuilder().build_env("base_sim", "empty_env_2ms", "base_quadrotor", "lee_velocity_control", "cpu", args={"seed": 4},
+                                            num_envs=16, headless=True)
+        a, b = mk(), mk()
+        a.reset()
+        b.reset()
+        assert torch.equal(a.engine.root_state, b.engine.root_state)
+        act = torch.full((16, 4), 0.3)
+        a.step(act)
+        for _ in range(5):  # EnvCfg2Ms: 5 physics steps per env step
+            b.simulate(act)
+        assert torch.allclose(a.engine.root_state, b.engine.root_state, rtol=1e-6, atol=1e-7)
+        assert int(a.sim_steps[0]) == 1 and int(b.sim_steps[0]) == 0
+        assert b.render_viewer() is None and b.log_memory_use() is None
