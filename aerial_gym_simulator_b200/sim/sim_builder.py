@@ -1,24 +1,32 @@
-"""sim/sim_builder.py surface: SimBuilder().build_env(...) -> EnvManager."""
+"""SimBuilder: the factory the reference's examples and tasks go through (sim/sim_builder.py:22-48 there).  It remembers what it was
+last asked for and the EnvManager it made; delete_env() releases that env's device allocations."""
 import torch
 
 from ..env_manager import EnvManager
 
 
 class SimBuilder:
+    _REMEMBERED = ("sim_name", "env_name", "robot_name")
+
     def __init__(self):
-        self.sim_name = self.env_name = self.robot_name = self.env = None
+        self.env = None
+        self._request = {}
+
+    def __getattr__(self, name):  # builder.sim_name / .env_name / .robot_name: the names of the last build_env call (None before)
+        if name in SimBuilder._REMEMBERED:
+            return self.__dict__.get("_request", {}).get(name)
+        raise AttributeError(name)
+
+    def build_env(self, sim_name, env_name, robot_name, controller_name, device, args=None, num_envs=None, use_warp=None, headless=None):
+        request = {k: v for k, v in locals().items() if k != "self"}
+        self._request = request
+        self.env = EnvManager(**request)
+        return self.env
 
     def delete_env(self):
-        if self.env is not None:
-            self.env.delete_env()
-        self.env = None
+        env, self.env = self.env, None
+        if env is not None:
+            env.delete_env()  # frees the engine's and the ray-caster's buffers
         if torch.cuda.is_available():
-            torch.cuda.empty_cache()
             torch.cuda.synchronize()
-
-    def build_env(self, sim_name, env_name, robot_name, controller_name, device, args=None, num_envs=None,
-                  use_warp=None, headless=None):
-        self.sim_name, self.env_name, self.robot_name = sim_name, env_name, robot_name
-        self.env = EnvManager(sim_name=sim_name, env_name=env_name, robot_name=robot_name, controller_name=controller_name,
-                              args=args, device=device, num_envs=num_envs, use_warp=use_warp, headless=headless)
-        return self.env
+            torch.cuda.empty_cache()
