@@ -270,6 +270,12 @@ class EnvManager:
         self.scene = RayScene(templates, seg_base, seg_mask, obj_t, obj_c, self._obj_pose, dev,
                               bounds_min=self.engine.bounds_min, bounds_max=self.engine.bounds_max,
                               tmpl_obb=np.stack(tmpl_obbs))
+        # Until the first reset_idx every actor sits where it was created: at the env origin, identity orientation
+        # (IGE_env_manager.py: create_actor with the default start pose), the robot among them.  Tasks whose reset() does not reset the
+        # sim (NavigationTask.reset, navigation_task.py:162-175) therefore begin in contact: the first step flags a crash and the
+        # first real episode starts with the reset that follows.  Build the scene for that configuration.
+        self._obj_pose[..., 6] = 1.0
+        self.scene.update()
 
     def _build_sensors(self):
         gtd, N, dev = self.global_tensor_dict, self.num_envs, self.device
