@@ -19,7 +19,13 @@ AGX_DEV void disturbance_env(uint32_t env_gid, uint32_t counter, float prob, con
     const float u[6] = {u01(a.y), u01(a.z), u01(a.w), u01(b.x), u01(b.y), u01(b.z)};
     for (int j = 0; j < 6; ++j) {
         const float lo = -max6[j], hi = max6[j];
-        out6[j] = ((hi - lo) * u[j] + lo) * gate;
+        // explicit round-to-nearest multiply THEN add: nvcc would contract (hi-lo)*u+lo into one FMA (one rounding), the numpy oracle
+        // and torch's own (upper - lower) * u + lower round twice -- the bit contract is the two-rounding form
+#if defined(__CUDA_ARCH__)
+        out6[j] = __fmul_rn(__fadd_rn(__fmul_rn(hi - lo, u[j]), lo), gate);
+#else
+        out6[j] = ((hi - lo) * u[j] + lo) * gate;  // host shadow: built with -ffp-contract=off
+#endif
     }
 }
 

@@ -53,7 +53,18 @@ def test_noise_kernel_matches_oracle(name):
     seed, frame = 0x1234_5678_9ABC_DEF0, 7
     for first in (0, (1 << 33) + 5):
         got, want = _gpu(px, n, seed, frame, first), _oracle(px, n, seed, frame, first)
-        assert np.allclose(got, want, rtol=1e-4, atol=2e-4 * max(1.0, float(np.abs(want).max()))), np.abs(got - want).max()
+        ok = np.isclose(got, want, rtol=1e-4, atol=2e-4 * max(1.0, float(np.abs(want).max())))
+        if n.enable_noise and n.apply_limits and not ok.all():
+            # device logf / cosf are a few ulp from numpy's: a noisy value within that distance of a range limit may legitimately land on
+            # the other side of the threshold -- only those values are excused
+            pre = SN.noise_limits(px, n.components, True, False, False, n.std_a, n.std_b, n.std_c, n.mean_offset, n.pixel_dropout_prob,
+                                  n.max_range, n.min_range, n.far_out_of_range_value, n.near_out_of_range_value, seed, frame, first)
+            mag = np.sqrt((pre.reshape(-1, n.components) ** 2).sum(1)) if n.components == 3 else np.abs(pre.reshape(-1))
+            tol = 1e-4 * np.maximum(1.0, np.abs(np.asarray(px, np.float32).reshape(-1, n.components)).max(1)) ** 2
+            near_limit = (np.abs(mag - n.max_range) < tol) | (np.abs(mag - n.min_range) < tol)
+            ok = ok.reshape(-1, n.components).all(1) | near_limit
+            assert near_limit.mean() < 1e-3
+        assert ok.all(), np.abs(got - want).max()
     if not n.enable_noise:
         assert np.array_equal(_gpu(px, n, seed, frame), d[f"{name}_out"])  # limits + normalisation only: the reference's output, bit for bit
     else:
