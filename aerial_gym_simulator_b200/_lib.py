@@ -54,9 +54,13 @@ _HP1_BUF_FIELDS = [
 
 
 class AgxHp1Buffers(C.Structure):
-    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS] + [
-        ("gather_bufs", C.c_void_p), ("gather_flags", C.c_void_p), ("gather_done", C.c_void_p),
-        ("gather_world", C.c_int32), ("gather_rank", C.c_int32), ("gather_epoch", C.c_uint32), ("gather_lag", C.c_int32)]
+    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS] + [("gather_consumed", C.c_void_p), ("gather_need", C.c_uint64)]
+
+
+class AgxObsGatherPush(C.Structure):
+    _fields_ = [("local", fp), ("peer_bufs", fp), ("peer_flags", fp), ("world", C.c_int32), ("rank", C.c_int32),
+                ("bytes", C.c_uint64), ("epoch", C.c_uint32), ("max_ctas", C.c_int32), ("ready_ctr", fp), ("ready_target", C.c_uint64),
+                ("consumed", fp), ("scratch", fp), ("error_word", fp)]
 
 
 _HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",
@@ -157,6 +161,13 @@ def load():
         "agx_hp2_update_scene": [C.POINTER(AgxHp2Scene), C.c_void_p, C.c_void_p],
         "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
         "agx_p2p_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
+        "agx_obs_gather_push": [C.POINTER(AgxObsGatherPush), C.c_void_p],
+        "agx_obs_gather_wait": [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p],
+        "agx_obs_gather_check": [C.c_void_p, C.c_void_p],
+        "agx_obs_gather_set_timeout_ns": [C.c_uint64],
+        "agx_set_spin_timeout_ms": [C.c_uint64],
+        "agx_hp1_check": [C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_hp1_task_step_is_chained": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers)],
         "agx_nav_reward": [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                            C.POINTER(AgxNavRewardParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "agx_nav_obs": [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p],
@@ -192,7 +203,7 @@ def load():
             or lib.agx_sizeof(9) != C.sizeof(AgxE2ERewardParams):
         raise AgxError("aux ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     if lib.agx_sizeof(0) != C.sizeof(AgxHp1Config) or lib.agx_sizeof(1) != C.sizeof(AgxHp1Buffers) \
-            or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws):
+            or lib.agx_sizeof(2) != C.sizeof(AgxHp1ResetDraws) or lib.agx_sizeof(10) != C.sizeof(AgxObsGatherPush):
         raise AgxError("ABI struct size mismatch between _lib.py and libaerial_gym_b200.so")
     _lib = lib
     return lib

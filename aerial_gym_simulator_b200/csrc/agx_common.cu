@@ -43,6 +43,7 @@ uint64_t agx_sizeof(int which) {
         case 6: return sizeof(AgxImuConfig);
         case 7: return sizeof(AgxLidarNavRewardParams);
         case 9: return sizeof(AgxE2ERewardParams);
+        case 10: return sizeof(AgxObsGatherPush);
 #ifdef AGX_HAVE_HP2
         case 3: return sizeof(AgxHp2Scene);
         case 4: return sizeof(AgxHp2Sensor);

@@ -36,13 +36,40 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Every in-kernel wait of the chained step is bounded by WALL-CLOCK time (%globaltimer), not by a poll count, and never traps:
+// on expiry the warp records AGX_HP1_ERR_TIMEOUT in the engine's error word (any_reset[2]) and goes on, later waits give up at
+// once, and the host reports AGX_E_TIMEOUT at its next agx_hp1_check() -- a slow neighbour kernel or a late peer costs a failed
+// run, not a poisoned CUDA context.  agx_set_spin_timeout_ms() changes the bound (default 20 s).
+__device__ unsigned long long g_hp1_spin_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr int kErrWord = 2;  // index into any_reset[]
+template <class Pred>
+__device__ __forceinline__ bool spin_until(Pred ok, int32_t* any_reset) {
+    if (ok()) return true;
+    volatile int32_t* err = any_reset + kErrWord;
+    if (*err) return false;
+    const unsigned long long t0 = globaltimer_ns(), limit = g_hp1_spin_timeout_ns;
+    unsigned polls = 0;
+    while (!ok()) {
+        if ((++polls & 255u) == 0u) {
+            if (*err) return false;
+            if (globaltimer_ns() - t0 > limit) {
+                atomicExch(any_reset + kErrWord, 1);
+                return false;
+            }
+        }
+    }
+    return true;
 }
 
 // ---- tile IO ---------------------------------------------------------------------------
@@ -166,6 +193,27 @@ __device__ __forceinline__ void store_derived(const AgxHp1Buffers& buf, int env,
     if (buf.body_angvel) st3(buf.body_angvel, env, d.wb);
 }
 
+// in-kernel reset of env `env0 + owner` (a15), warp-cooperative: every lane evaluates one Philox block, the owner applies them.
+// Rare (an env resets every ~500 steps) and ~800 instructions: -DAGX_HP1_NOINLINE_RESET keeps it out of the step's straight line.
+#ifdef AGX_HP1_NOINLINE_RESET
+#define AGX_HP1_RESET_FN __device__ __noinline__
+#else
+#define AGX_HP1_RESET_FN __device__ __forceinline__
+#endif
+template <int M>
+AGX_HP1_RESET_FN void reset_one_env(const AgxHp1Config& cfg, const AgxHp1Buffers& buf, int env0, int owner, uint32_t ep, int lane, float* tile,
+                                    EnvState& s, EnvParams<M>& p) {
+    coop_rng_draw<M>(cfg, (uint32_t)(cfg.env_id_offset + env0 + owner), ep, lane, tile);
+    __syncwarp();
+    if (lane == owner) {
+        const int env = env0 + owner;
+        apply_reset_from_tile<M>(cfg, tile, s, p);
+        buf.episode_count[env] = ep + 1u;
+        store_reset_params<M>(buf, env, p);
+    }
+    __syncwarp();
+}
+
 // =========================================================================================
 // main kernel
 // =========================================================================================
@@ -194,8 +242,9 @@ __device__ __forceinline__ void store_derived(const AgxHp1Buffers& buf, int env,
 //   any_reset[4 + (T & 3)]        u32 flag of step T: raised = holds T + 1 (monotonic, never cleared)
 //   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared)
 //   tile_sync[tile], tile_sync[n_tiles + tile]   claim / done counters of the tile
-// With the fused all-gather attached the grid-wide order is kept (griddepcontrol.wait): its handshake
-// assumes one step at a time.
+// (3) Multi-GPU: the step kernel never touches NVLink.  With an observation all-gather attached (agx_obs_gather_push,
+// p2p_allgather.cu, on a side stream) the only coupling is back-pressure on the observation ring: buf.obs is one slot of a ring
+// that the gather kernel reads asynchronously, and a warp may overwrite its slot only when *gather_consumed >= gather_need.
 #ifdef AGX_TIMELINE  // debug builds only (tools/dbg/timeline.py): per-warp start / end globaltimer stamps
 __device__ unsigned long long g_timeline[4][8192];
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -208,9 +257,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define AGX_TL(slot) do { } while (0)
 #endif
 
-template <int M, bool TASK, bool COOP = false>
-__global__ void __launch_bounds__(kThreads, 8)
+#ifndef AGX_HP1_MIN_BLOCKS
+#define AGX_HP1_MIN_BLOCKS 8
+#endif
+template <int M, bool TASK, bool COOP = false, int SPEC = -1>
+__global__ void __launch_bounds__(kThreads, AGX_HP1_MIN_BLOCKS)
 hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant__ AgxHp1Buffers buf, int vec_ok) {
+    using SP = HpSpec<SPEC>;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
@@ -230,21 +283,20 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
         __syncthreads();  // both warps hold their claim before the CTA lets the next launch in
         // programmatic dependent launch: once every CTA of this grid is here, the NEXT step's CTAs may be scheduled
         asm volatile("griddepcontrol.launch_dependents;" ::"r"(step_T) : "memory");
-        if (buf.gather_bufs) asm volatile("griddepcontrol.wait;" ::: "memory");  // fused gather: one step at a time
         if (has_tile) {
             if (lane == 0) {
                 const uint32_t* done = buf.tile_sync + n_tiles + my_tile;
-                unsigned long long spins = 0;
-                while (ld_acquire_gpu_u32(done) != step_T)  // this tile's previous step has published its state
-                    if (++spins > (1ull << 22)) __trap();
+                // this tile's previous step has published its state
+                spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset);
                 if (step_T >= 2u) {  // step T-2 complete everywhere: bounds the skew to two steps in flight
                     const uint32_t P = step_T - 2u;
-                    const volatile unsigned long long* a2 = reinterpret_cast<const volatile unsigned long long*>(buf.any_reset + 8) + (P & 3u);
+                    const unsigned long long* a2 = reinterpret_cast<const unsigned long long*>(buf.any_reset + 8) + (P & 3u);
                     const unsigned long long want = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
-                    spins = 0;
-                    while (*a2 < want)
-                        if (++spins > (1ull << 22)) __trap();
-                    __threadfence();
+                    spin_until([&] { return ld_acquire_gpu_u64(a2) >= want; }, buf.any_reset);
+                }
+                if (buf.gather_consumed) {  // the gather kernel has read the ring slot this step's observation goes into
+                    const unsigned long long need = buf.gather_need;
+                    spin_until([&] { return ld_acquire_gpu_u64(buf.gather_consumed) >= need; }, buf.any_reset);
                 }
             }
             __syncwarp();
@@ -311,12 +363,12 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 // AGX_SHADOW_BEGIN(physics_substep)  -- tests/_shadow.py compiles the text between these markers for the host
                 d = update_states(s);
                 float ref[M];
-                if (cfg.controller == AGX_CTRL_NONE) {  // update_motor_thrusts_with_forces
+                if (SP::controller(cfg) == AGX_CTRL_NONE) {  // update_motor_thrusts_with_forces
 AGX_HP1_MOTOR_UNROLL
                     for (int i = 0; i < M; ++i) ref[i] = act[i];
                 } else {
                     float wr[6];
-                    controller_wrench(cfg, s, d, p.g, act, wr);
+                    controller_wrench<SP>(cfg, s, d, p.g, act, wr);
                     // f_ref = pinv(A) w   control/control_allocation.py:87-89
 AGX_HP1_MOTOR_UNROLL
                     for (int i = 0; i < M; ++i) {
@@ -327,7 +379,7 @@ AGX_HP1_MOTOR_UNROLL
                     }
                 }
 AGX_HP1_MOTOR_UNROLL
-                for (int i = 0; i < M; ++i) p.thrust[i] = motor_update(cfg, p.thrust[i], ref[i], p.tau_inc[i], p.tau_dec[i], p.k[i]);
+                for (int i = 0; i < M; ++i) p.thrust[i] = motor_update<SP>(cfg, p.thrust[i], ref[i], p.tau_inc[i], p.tau_dec[i], p.k[i]);
                 // thrust -> base-frame wrench about the COM (control_allocation.py:103-114 applied
                 // link-local, IGE_env_manager.py:444-449)
                 float w6[6];
@@ -352,7 +404,7 @@ AGX_HP1_MOTOR_UNROLL
                 V3 F{w6[0] + df.x, w6[1] + df.y, w6[2] + df.z};
                 V3 T = V3{w6[3], w6[4], w6[5]} + dtq + cross(neg(com), df);
                 Fx = F.x; Fy = F.y; Fz = F.z; Tx = T.x; Ty = T.y; Tz = T.z;
-                integrate(cfg, s, F, T);
+                integrate<SP>(cfg, s, F, T);
                 // AGX_SHADOW_END(physics_substep)
             }
             if (cfg.physics_steps == 0) d = update_states(s);
@@ -396,16 +448,11 @@ AGX_HP1_MOTOR_UNROLL
                 for (unsigned m = rmask; m; m &= m - 1) {
                     const int owner = __ffs(m) - 1;
                     const uint32_t ep = __shfl_sync(0xffffffffu, my_ep, owner);
-                    coop_rng_draw<M>(cfg, (uint32_t)(cfg.env_id_offset + env0 + owner), ep, lane, tile);
-                    __syncwarp();
+                    reset_one_env<M>(cfg, buf, env0, owner, ep, lane, tile, s, p);
                     if (lane == owner) {
-                        apply_reset_from_tile<M>(cfg, tile, s, p);
-                        buf.episode_count[env] = ep + 1u;
-                        store_reset_params<M>(buf, env, p);
                         steps = 0;  // env_manager.py:301
                         fresh = true;
                     }
-                    __syncwarp();
                 }
             }
             if constexpr (!COOP) {
@@ -437,19 +484,10 @@ AGX_HP1_MOTOR_UNROLL
                     if (lane == 0) atomicAdd(arrive_ctr, 1ull);
                     counted = true;
                     volatile uint32_t* fl = reset_flag;
-                    volatile unsigned long long* cnt = arrive_ctr;
+                    const unsigned long long* cnt = arrive_ctr;
+                    // until the flag rises, or every warp of this step has arrived (then the flag is final)
+                    spin_until([&] { return *fl == flag_tag || ld_acquire_gpu_u64(cnt) >= arrive_target; }, buf.any_reset);
                     any = (*fl == flag_tag);
-                    unsigned long long spins = 0;
-                    while (!any) {
-                        if (*cnt >= arrive_target) {  // every warp of this step has arrived: the flag is final
-                            __threadfence();
-                            any = (*fl == flag_tag);
-                            break;
-                        }
-                        if (++spins > (1ull << 22)) __trap();
-                        __nanosleep(40);
-                        any = (*fl == flag_tag);
-                    }
                 }
                 // ---- derived states for the observation: one common pass for resetting envs (new state)
                 // and, if anybody reset, for everybody else (post-physics state) ------------------------
@@ -474,29 +512,11 @@ AGX_HP1_MOTOR_UNROLL
                 }
                 store_rows13(buf.root_state, env0, n_valid, tile, lane, r, vec_ok);
                 store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
-                __syncwarp();  // (before the peer pushes below: this fence must not wait for NVLink stores)
+                __syncwarp();
                 if (lane == 0) {
                     __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
                     if (!counted) atomicAdd(arrive_ctr, 1ull);
                     st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
-                }
-                if (buf.gather_bufs) {  // the rows are still in the tile: push them into every rank's gathered buffer
-                    const bool vec = vec_ok && n_valid == 32 && (N & 3) == 0;
-                    const size_t row0 = ((size_t)buf.gather_rank * N + env0) * 13;
-                    for (int pr = 0; pr < buf.gather_world; ++pr) {
-                        float* dst = reinterpret_cast<float*>(buf.gather_bufs[pr]) + row0;
-                        if (vec) {
-                            float4* d4 = reinterpret_cast<float4*>(dst);
-                            const float4* t4 = reinterpret_cast<const float4*>(tile);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                int idx = lane + 32 * i;
-                                if (idx < kTileFloats / 4) d4[idx] = t4[idx];
-                            }
-                        } else {
-                            for (int i = lane; i < n_valid * 13; i += 32) dst[i] = tile[i];
-                        }
-                    }
                 }
             }
         }
@@ -515,36 +535,6 @@ AGX_HP1_MOTOR_UNROLL
         }
     }
     AGX_TL(2);
-    if constexpr (COOP) {
-        if (buf.gather_bufs) {
-            // all-gather handshake (same protocol as p2p_allgather_kernel): the last CTA of this rank
-            // publishes the epoch to every peer and waits for every peer's epoch
-            __syncthreads();  // the CTA's peer stores are ordered before thread 0's system-scope fence (cumulativity)
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                const unsigned done = atomicAdd(buf.gather_done, 1u);
-                if (done == gridDim.x - 1) {
-                    *buf.gather_done = 0u;
-                    __threadfence_system();
-                    const int W = buf.gather_world, R = buf.gather_rank;
-                    const uint32_t epoch = buf.gather_epoch;
-                    for (int pr = 0; pr < W; ++pr) st_release_sys_u32(buf.gather_flags[pr] + R, epoch);
-                    // gather_lag = 0: retire only when every peer's rows of THIS step have landed here.
-                    // gather_lag = 1: wait for the previous step's rows only -- this step's handshake then
-                    // overlaps the next step's compute (the consumer reads gathered obs one step late);
-                    // ranks still cannot drift more than one epoch apart (four buffers cover that).
-                    const uint32_t want = epoch - (uint32_t)buf.gather_lag;
-                    const uint32_t* mine = buf.gather_flags[R];
-                    for (int q = 0; q < W; ++q) {
-                        unsigned long long spins = 0;
-                        while ((int32_t)(ld_acquire_sys_u32(mine + q) - want) < 0) {
-                            if (++spins > (1ull << 24)) __trap();  // a missing peer must not hang the GPU forever
-                        }
-                    }
-                }
-            }
-        }
-    }
     AGX_TL(3);
 }
 
@@ -682,13 +672,8 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
             return agx_set_error(AGX_E_NULL, "task step needs sim_steps/obs/reward/terminations/truncations/any_reset");
         if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && !buf->episode_count)
             return agx_set_error(AGX_E_NULL, "device-RNG reset needs episode_count");
-        if (buf->gather_bufs) {
-            if (!buf->gather_flags || !buf->gather_done) return agx_set_error(AGX_E_NULL, "fused gather needs gather_flags/gather_done");
-            if (buf->gather_world < 1 || buf->gather_world > AGX_MAX_PEERS || buf->gather_rank < 0 || buf->gather_rank >= buf->gather_world)
-                return agx_set_error(AGX_E_INVALID, "fused gather: bad world/rank");
-            if (buf->gather_epoch == 0) return agx_set_error(AGX_E_INVALID, "fused gather: epoch starts at 1");
-            if (buf->gather_lag < 0 || buf->gather_lag > 1) return agx_set_error(AGX_E_INVALID, "fused gather: lag must be 0 or 1");
-        }
+        if (buf->gather_consumed && ((uintptr_t)buf->gather_consumed & 7))
+            return agx_set_error(AGX_E_INVALID, "gather_consumed must be 8-byte aligned");
     }
     return AGX_OK;
 }
@@ -696,30 +681,93 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
 inline int vec_ok_of(const AgxHp1Buffers* buf) {
     return (((uintptr_t)buf->root_state | (uintptr_t)buf->obs) & 15) == 0;
 }
-// how many CTAs of the cooperative task kernel can be co-resident on this device (cached)
-inline int coop_capacity(int num_motors) {
-    static int cap4 = -1, cap8 = -1;
-    int& cap = (num_motors == 4) ? cap4 : cap8;
-    if (cap < 0) {
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_motors == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp1_step_kernel<4, true, true>, kThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp1_step_kernel<8, true, true>, kThreads, 0);
-        cap = coop ? sms * per_sm : 0;
-    }
+// ---- instantiation table ------------------------------------------------------------------------------------------------
+// The single-launch task kernel and the physics-only kernel exist in a generic form (every switch read at run time) and in forms
+// specialised (HpSpec) for the controller x motor-model combinations the shipped robots use; a launch picks the match.
+#define AGX_SPEC_FLAGS_ALL (AGX_F_USE_RPS | AGX_F_MOTOR_RK4 | AGX_F_DISCRETE_MIX | AGX_F_GYROSCOPIC)
+#ifndef AGX_HP1_NO_SPEC
+#define AGX_HP1_SPEC_LIST(X)                                                                                      \
+    X(4, AGX_CTRL_ATTITUDE, AGX_SPEC_FLAGS_ALL)      /* base_quadrotor + lee_attitude_control (position task, BASELINE configs[1]) */ \
+    X(4, AGX_CTRL_VELOCITY, AGX_SPEC_FLAGS_ALL)      /* lmf2 / base_quadrotor velocity control (navigation tasks) */      \
+    X(4, AGX_CTRL_POSITION, AGX_SPEC_FLAGS_ALL)                                                                   \
+    X(4, AGX_CTRL_ACCELERATION, AGX_SPEC_FLAGS_ALL)                                                               \
+    X(4, AGX_CTRL_NONE, AGX_SPEC_FLAGS_ALL)          /* motor-command tasks */                                     \
+    X(8, AGX_CTRL_FULLY_ACTUATED, (AGX_F_MOTOR_RK4 | AGX_F_DISCRETE_MIX | AGX_F_GYROSCOPIC)) /* base_octarotor / ROV */ \
+    X(8, AGX_CTRL_VELOCITY, (AGX_F_MOTOR_RK4 | AGX_F_DISCRETE_MIX | AGX_F_GYROSCOPIC))
+#else
+#define AGX_HP1_SPEC_LIST(X)
+#endif
+
+using StepKernel = void (*)(const AgxHp1Config, const AgxHp1Buffers, int);
+template <bool TASK, bool COOP>
+StepKernel pick_kernel(const AgxHp1Config* cfg) {
+    const int id = hp_spec_id(cfg->controller, cfg->flags);
+#define AGX_X(M_, C_, F_) \
+    if (cfg->num_motors == M_ && id == hp_spec_id(C_, F_)) return hp1_step_kernel<M_, TASK, COOP, hp_spec_id(C_, F_)>;
+    AGX_HP1_SPEC_LIST(AGX_X)
+#undef AGX_X
+    return cfg->num_motors == 4 ? hp1_step_kernel<4, TASK, COOP, -1> : hp1_step_kernel<8, TASK, COOP, -1>;
+}
+
+// how many CTAs of the single-launch task kernel can be co-resident on this device (cached per kernel)
+inline int coop_capacity(StepKernel k) {
+    static StepKernel seen[32];
+    static int caps[32], n_seen = 0;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == k) return caps[i];
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
+    const int cap = sms * per_sm;
+    if (n_seen < 32) { seen[n_seen] = k; caps[n_seen] = cap; ++n_seen; }
     return cap;
 }
+// CTA slots kept free for kernels that run BESIDE the chained step (the observation gather's push kernel): the one-sided grid
+// barrier needs every CTA of a step resident, so the step only takes the single-launch path when it fits with this margin
+#ifndef AGX_HP1_COOP_RESERVE
+#define AGX_HP1_COOP_RESERVE 96
+#endif
+constexpr int kCoopReserve = AGX_HP1_COOP_RESERVE;
 inline int grid_for(int n_envs) {
     int tiles = (n_envs + 31) / 32;
     int blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     return blocks < 1 ? 1 : blocks;
 }
 
+// does the fused task step of (cfg, buf) take the single-launch, per-tile chained path?
+inline bool hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* buf) {
+    const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
+    return strict_fused && buf->tile_sync && coop_capacity(pick_kernel<true, true>(cfg)) - kCoopReserve >= grid_for(cfg->num_envs);
+}
+
 }  // namespace
 
 extern "C" {
+
+int agx_hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* buf) {
+    if (!cfg || !buf) return agx_set_error(AGX_E_NULL, "cfg/buf is NULL");
+    if (cfg->num_motors != 4 && cfg->num_motors != 8) return agx_set_error(AGX_E_INVALID, "num_motors must be 4 or 8");
+    return hp1_task_step_is_chained(cfg, buf) ? 1 : 0;
+}
+
+int agx_set_spin_timeout_ms(uint64_t ms) {
+    const unsigned long long ns = (unsigned long long)ms * 1000000ull;
+    int rc = agx_check_cuda(cudaMemcpyToSymbol(g_hp1_spin_timeout_ns, &ns, sizeof(ns)), "agx_set_spin_timeout_ms");
+    return rc ? rc : agx_obs_gather_set_timeout_ns(ns);
+}
+
+// error word of the chained step's bounded waits (any_reset[2]); synchronises the stream
+int agx_hp1_check(const AgxHp1Buffers* buf, void* stream) {
+    if (!buf || !buf->any_reset) return agx_set_error(AGX_E_NULL, "buf/any_reset is NULL");
+    int32_t w = 0;
+    int rc = agx_check_cuda(cudaMemcpyAsync(&w, buf->any_reset + kErrWord, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream), "agx_hp1_check");
+    if (rc) return rc;
+    rc = agx_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "agx_hp1_check");
+    if (rc) return rc;
+    return w ? agx_set_error(AGX_E_TIMEOUT, "a chained-step wait timed out (error word %d): the step kernel was not fully resident "
+                                            "or a producer never arrived", w) : AGX_OK;
+}
 
 #ifdef AGX_TIMELINE
 int agx_dbg_timeline(unsigned long long* host_out) {
@@ -733,8 +781,7 @@ int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void
     if (cfg->num_envs == 0) return AGX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
-    if (cfg->num_motors == 4) hp1_step_kernel<4, false><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
-    else hp1_step_kernel<8, false><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    pick_kernel<false, false>(cfg)<<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     return agx_check_launch("hp1_step_kernel");
 }
 
@@ -751,7 +798,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
     int g = grid_for(cfg->num_envs), v = vec_ok_of(buf);
     const bool strict_fused = (cfg->flags & AGX_F_DEVICE_RNG_RESET) && (cfg->flags & AGX_F_STRICT_STALE_OBS);
     const bool derived = buf->euler || buf->vehicle_orientation || buf->vehicle_linvel || buf->body_linvel || buf->body_angvel;
-    if (strict_fused && !ev_after_main && buf->tile_sync && coop_capacity(cfg->num_motors) >= g) {
+    if (hp1_task_step_is_chained(cfg, buf) && !ev_after_main) {
         // single launch: the whole grid is resident at once (g <= occupancy x SMs), so the in-kernel
         // one-sided barrier cannot starve -- no cooperative-launch API needed for that
         cudaLaunchConfig_t lc = {};
@@ -763,12 +810,12 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = 1;
-        cudaError_t e = (cfg->num_motors == 4) ? cudaLaunchKernelEx(&lc, hp1_step_kernel<4, true, true>, *cfg, *buf, v)
-                                               : cudaLaunchKernelEx(&lc, hp1_step_kernel<8, true, true>, *cfg, *buf, v);
+        cudaError_t e = cudaLaunchKernelEx(&lc, pick_kernel<true, true>(cfg), *cfg, *buf, v);
         return agx_check_cuda(e, "hp1_step_kernel<task, single-launch>");
     }
-    if (cfg->num_motors == 4) hp1_step_kernel<4, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
-    else hp1_step_kernel<8, true><<<g, kThreads, 0, st>>>(*cfg, *buf, v);
+    if (buf->gather_consumed)
+        return agx_set_error(AGX_E_INVALID, "observation-ring back-pressure (gather_consumed) needs the single-launch path");
+    pick_kernel<true, false>(cfg)<<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     rc = agx_check_launch("hp1_step_kernel<task>");
     if (rc) return rc;
     if (ev_after_main) {
@@ -786,11 +833,6 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
             rc = agx_check_launch("hp1_refresh_kernel");
         }
     }
-    if (rc == AGX_OK && buf->gather_bufs && buf->gather_lag != 0)
-        return agx_set_error(AGX_E_INVALID, "gather_lag = 1 needs the cooperative path (grid within one resident wave)");
-    if (rc == AGX_OK && buf->gather_bufs)  // not fused on this path: the stand-alone all-gather kernel follows
-        rc = agx_p2p_allgather(buf->obs, buf->gather_bufs, buf->gather_flags, buf->gather_world, buf->gather_rank,
-                               (uint64_t)cfg->num_envs * 13 * sizeof(float), buf->gather_epoch, buf->gather_done, stream);
     return rc;
 }
 

@@ -37,6 +37,30 @@ struct Gains {
 
 AGX_DEV V3 ld3c(const float* c) { return V3{c[0], c[1], c[2]}; }
 
+// Compile-time specialisation of the step's RUN-TIME switches.  The generic kernel reads the controller id and the motor-model /
+// integrator flags from the launch constants and branches (uniformly) over all eight controller families: ~6,600 SASS instructions of
+// which a warp executes ~2,000, spread over 105 KB of text -- more than the 32 KB L1.5 instruction cache, and every warp streams
+// through it exactly once (ncu: stall_no_instruction leads).  HpSpec<S> with S >= 0 fixes controller (bits 0..3) and the flags
+// USE_RPS | MOTOR_RK4 | DISCRETE_MIX | GYROSCOPIC (bits 4..7) at compile time, so an instantiation contains only the code its robot
+// runs, laid out contiguously; S = -1 keeps every switch dynamic.  Same arithmetic either way (the shadow build and the generic
+// kernel are the S = -1 text); hp1.cu picks the instantiation that matches cfg, falling back to the generic one.
+template <int S>
+struct HpSpec {
+    static constexpr bool kFixed = S >= 0;
+    AGX_DEV static int controller(const AgxHp1Config& cfg) {
+        if constexpr (kFixed) return S & 0xf;
+        else return cfg.controller;
+    }
+    template <int F>
+    AGX_DEV static bool flag(const AgxHp1Config& cfg) {
+        static_assert((F & ~0xf) == 0, "only the four low flags are specialised");
+        if constexpr (kFixed) return ((S >> 4) & F) != 0;
+        else return (cfg.flags & F) != 0;
+    }
+};
+using HpSpecDyn = HpSpec<-1>;
+constexpr int hp_spec_id(int controller, int flags) { return (controller & 0xf) | ((flags & 0xf) << 4); }
+
 AGX_DEV EnvState unpack(const float r[13]) {
     EnvState s;
     s.x = V3{r[0], r[1], r[2]};
@@ -53,7 +77,12 @@ AGX_DEV void pack(const EnvState& s, float r[13]) {
 }
 
 // ---- a1: BaseMultirotor.update_states   robots/base_multirotor.py:287-294 ----------------
+// -DAGX_HP1_NOINLINE_DERIVED (experiment): one out-of-line copy shared by the call at the start of the step and the refresh
+#if defined(AGX_HP1_NOINLINE_DERIVED) && !defined(AGX_HOST_SHADOW)
+__device__ __noinline__ Derived update_states(const EnvState& s) {
+#else
 AGX_DEV Derived update_states(const EnvState& s) {
+#endif
     Derived d;
     V3 e = euler_xyz_0_2pi(s.q);
     d.euler = V3{ssa_0_2pi(e.x), ssa_0_2pi(e.y), ssa_0_2pi(e.z)};
@@ -116,13 +145,14 @@ AGX_DEV Q4 desired_orientation_forces_yaw(V3 f, float yaw) {
 }
 
 // ---- a7: controller dispatch -> wrench[6] (or motor refs for AGX_CTRL_NONE) --------------
+template <class SP = HpSpecDyn>
 AGX_DEV void controller_wrench(const AgxHp1Config& cfg, const EnvState& s, const Derived& d,
                                                   const Gains& g, const float* act, float wr[6]) {
     const V3 grav = ld3c(cfg.gravity);
     const float m = cfg.mass;
 #pragma unroll
     for (int i = 0; i < 6; ++i) wr[i] = 0.0f;
-    const int c = cfg.controller;
+    const int c = SP::controller(cfg);
     const V3 zero3{0.0f, 0.0f, 0.0f};
     if (c == AGX_CTRL_ATTITUDE) {  // controllers/attitude_control.py:16-43
         wr[2] = (act[0] + 1.0f) * m * norm3(grav);
@@ -183,6 +213,7 @@ AGX_DEV float motor_rk4(float ref, float cur, float mix, float max_rate, float d
     float k4 = motor_rate(ref - (cur + dt * k3), mix, max_rate);
     return (dt / 6.0f) * (k1 + 2.0f * k2 + 2.0f * k3 + k4);
 }
+template <class SP = HpSpecDyn>
 AGX_DEV float motor_update(const AgxHp1Config& cfg, float cur, float ref_in, float tau_inc,
                                               float tau_dec, float k) {
     const float dt = cfg.dt;
@@ -190,9 +221,9 @@ AGX_DEV float motor_update(const AgxHp1Config& cfg, float cur, float ref_in, flo
     float err = ref - cur;
     bool decreasing = (cur > 0.0f && err < 0.0f) || (cur < 0.0f && err > 0.0f);  // sign(f)*sign(err) < 0
     float tau = decreasing ? tau_dec : tau_inc;
-    float mix = (cfg.flags & AGX_F_DISCRETE_MIX) ? 1.0f / (dt + tau) : 1.0f / tau;
-    const bool rk4 = cfg.flags & AGX_F_MOTOR_RK4;
-    if (cfg.flags & AGX_F_USE_RPS) {
+    float mix = SP::template flag<AGX_F_DISCRETE_MIX>(cfg) ? 1.0f / (dt + tau) : 1.0f / tau;
+    const bool rk4 = SP::template flag<AGX_F_MOTOR_RK4>(cfg);
+    if (SP::template flag<AGX_F_USE_RPS>(cfg)) {
         float rpm = sqrtf(cur / k);
         float rpm_ref = sqrtf(ref / k);
         if (rk4) rpm += motor_rk4(rpm_ref, rpm, mix, cfg.max_thrust_rate, dt);
@@ -205,6 +236,7 @@ AGX_DEV float motor_update(const AgxHp1Config& cfg, float cur, float ref_in, flo
 
 // ---- a13: rigid-body integrator -- OUR SPEC (DESIGN.md "Integrator spec"; oracle
 // rigid_body_integrate).  Replaces gym.simulate (env_manager/IGE_env_manager.py:477). --------
+template <class SP = HpSpecDyn>
 AGX_DEV void integrate(const AgxHp1Config& cfg, EnvState& s, V3 F, V3 T) {
     const float dt = cfg.dt;
     V3 a = quat_rotate(s.q, F) * (1.0f / cfg.mass) + ld3c(cfg.gravity);
@@ -215,7 +247,7 @@ AGX_DEV void integrate(const AgxHp1Config& cfg, EnvState& s, V3 F, V3 T) {
     const float* J = cfg.inertia;
     const float* Ji = cfg.inertia_inv;
     V3 rhs = T;
-    if (cfg.flags & AGX_F_GYROSCOPIC) {
+    if (SP::template flag<AGX_F_GYROSCOPIC>(cfg)) {
         V3 JW{J[0] * W.x + J[1] * W.y + J[2] * W.z, J[3] * W.x + J[4] * W.y + J[5] * W.z,
               J[6] * W.x + J[7] * W.y + J[8] * W.z};
         rhs = T - cross(W, JW);

@@ -19,6 +19,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long gt_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct PeerTable {
     float4* buf[AGX_MAX_PEERS];
     uint32_t* flag[AGX_MAX_PEERS];
@@ -48,16 +54,158 @@ p2p_allgather_kernel(const float4* __restrict__ local, void* const* __restrict__
             // wait until every peer has published this epoch into OUR flag words
             const uint32_t* mine = t.flag[rank];
             for (int q = 0; q < world; ++q) {
-                unsigned long long spins = 0;
+                const unsigned long long t0 = gt_ns();
+                unsigned polls = 0;
                 while ((int32_t)(ld_acquire_sys(mine + q) - epoch) < 0) {
-                    if (++spins > (1ull << 24)) __trap();  // a missing peer must not hang the GPU forever
+                    // a missing peer must not hang the GPU forever, and a late one must not kill the context: wall-clock bound, no trap
+                    if ((++polls & 255u) == 0u && gt_ns() - t0 > 20ull * 1000ull * 1000ull * 1000ull) break;
                 }
             }
         }
     }
 }
 
+// ---- pipelined form: push (sender) / wait (receiver) ------------------------------------------------------------------
+__device__ unsigned long long g_gather_spin_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// wall-clock bounded wait; on expiry: error word, no trap (see hp1.cu spin_until)
+template <class Pred>
+__device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word) {
+    if (ok()) return true;
+    volatile uint32_t* err = err_word;
+    if (*err) return false;
+    const unsigned long long t0 = globaltimer_ns(), limit = g_gather_spin_timeout_ns;
+    unsigned polls = 0;
+    while (!ok()) {
+        if ((++polls & 63u) == 0u) {
+            if (*err) return false;
+            if (globaltimer_ns() - t0 > limit) {
+                atomicExch(err_word, 1u);
+                return false;
+            }
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+constexpr int kPushThreads = 256;
+constexpr int kPushUnroll = 4;
+
+// <= 32 registers: one push CTA fits beside seven 128-register step CTAs on an SM
+__global__ void __launch_bounds__(kPushThreads, 8)
+obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec) {
+    __shared__ float4* s_dst[AGX_MAX_PEERS];
+    __shared__ int s_npeer;
+    const float4* __restrict__ local = reinterpret_cast<const float4*>(a.local);
+    if (threadIdx.x == 0) {
+        int n = 0;
+        // peers in a rank-dependent rotation: at any moment the ranks store to different destinations
+        for (int k = 1; k <= a.world; ++k) {
+            const int p = (a.rank + k) % a.world;
+            float4* dst = reinterpret_cast<float4*>(a.peer_bufs[p]) + (size_t)a.rank * n_vec;
+            if (dst == local) continue;  // the step wrote its observation straight into the own slot
+            s_dst[n++] = dst;
+        }
+        s_npeer = n;
+        if (a.ready_ctr) {
+            const unsigned long long* c = a.ready_ctr;
+            const unsigned long long want = a.ready_target;
+            spin_until([&] { return ld_acquire_gpu_u64(c) >= want; }, a.error_word);
+        }
+    }
+    __syncthreads();
+    const int np = s_npeer;
+    const size_t stride = (size_t)gridDim.x * kPushThreads;
+    size_t i = (size_t)blockIdx.x * kPushThreads + threadIdx.x;
+    for (; i + (kPushUnroll - 1) * stride < n_vec; i += kPushUnroll * stride) {
+        float4 v[kPushUnroll];
+#pragma unroll
+        for (int u = 0; u < kPushUnroll; ++u) v[u] = __ldcg(local + i + u * stride);  // L2: never a stale L1 line of an earlier step
+        for (int p = 0; p < np; ++p) {
+            float4* d = s_dst[p];
+#pragma unroll
+            for (int u = 0; u < kPushUnroll; ++u) d[i + u * stride] = v[u];
+        }
+    }
+    for (; i < n_vec; i += stride) {
+        const float4 v = __ldcg(local + i);
+        for (int p = 0; p < np; ++p) s_dst[p][i] = v;
+    }
+    __syncthreads();  // the CTA's loads are done and its peer stores are ordered before thread 0's fences (cumulativity)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.scratch + 0, 1u) == gridDim.x - 1) {  // every CTA has finished READING `local`
+            a.scratch[0] = 0u;
+            if (a.consumed) atomicAdd(a.consumed, 1ull);
+        }
+        __threadfence_system();  // waits until this CTA's NVLink stores have been performed
+        if (atomicAdd(a.scratch + 1, 1u) == gridDim.x - 1) {  // ... and so have everybody else's
+            a.scratch[1] = 0u;
+            __threadfence_system();
+            for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + a.rank, a.epoch);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+obs_gather_wait_kernel(const uint32_t* __restrict__ my_flags, int world, uint32_t epoch, uint32_t* error_word) {
+    const int q = threadIdx.x;
+    if (q < world) spin_until([&] { return (int32_t)(ld_acquire_sys(my_flags + q) - epoch) >= 0; }, error_word);
+    __syncwarp();
+    __threadfence_system();
+}
+
 }  // namespace
+
+extern "C" int agx_obs_gather_set_timeout_ns(uint64_t ns) {
+    const unsigned long long v = ns;
+    return agx_check_cuda(cudaMemcpyToSymbol(g_gather_spin_timeout_ns, &v, sizeof(v)), "agx_obs_gather_set_timeout_ns");
+}
+
+extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
+    if (!a || !a->local || !a->peer_bufs || !a->peer_flags || !a->scratch || !a->error_word)
+        return agx_set_error(AGX_E_NULL, "obs_gather_push: NULL argument");
+    if (a->world < 1 || a->world > AGX_MAX_PEERS || a->rank < 0 || a->rank >= a->world)
+        return agx_set_error(AGX_E_INVALID, "obs_gather_push: bad world/rank");
+    if (a->bytes % 16 || ((uintptr_t)a->local & 15)) return agx_set_error(AGX_E_INVALID, "obs_gather_push: bytes and local must be 16-byte aligned");
+    if (a->epoch == 0) return agx_set_error(AGX_E_INVALID, "obs_gather_push: epoch starts at 1");
+    if (((uintptr_t)a->ready_ctr | (uintptr_t)a->consumed) & 7) return agx_set_error(AGX_E_INVALID, "obs_gather_push: counters must be 8-byte aligned");
+    if (a->bytes == 0) return AGX_OK;
+    const size_t n_vec = a->bytes / 16;
+    long long ctas = (long long)((n_vec + (size_t)kPushThreads * kPushUnroll - 1) / ((size_t)kPushThreads * kPushUnroll));
+    const int cap = a->max_ctas > 0 ? a->max_ctas : 64;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    obs_gather_push_kernel<<<(int)ctas, kPushThreads, 0, (cudaStream_t)stream>>>(*a, n_vec);
+    return agx_check_launch("obs_gather_push_kernel");
+}
+
+extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int world, uint32_t epoch, uint32_t* error_word, void* stream) {
+    if (!my_flags || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_wait: NULL argument");
+    if (world < 1 || world > AGX_MAX_PEERS) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world");
+    obs_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags, world, epoch, error_word);
+    return agx_check_launch("obs_gather_wait_kernel");
+}
+
+extern "C" int agx_obs_gather_check(const uint32_t* error_word, void* stream) {
+    if (!error_word) return agx_set_error(AGX_E_NULL, "obs_gather_check: NULL argument");
+    uint32_t w = 0;
+    int rc = agx_check_cuda(cudaMemcpyAsync(&w, error_word, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream), "agx_obs_gather_check");
+    if (rc) return rc;
+    rc = agx_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "agx_obs_gather_check");
+    if (rc) return rc;
+    return w ? agx_set_error(AGX_E_TIMEOUT, "observation gather: a wait timed out (a producer step or a peer never arrived)") : AGX_OK;
+}
 
 extern "C" int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const* peer_flags, int world, int rank,
                                  uint64_t bytes, uint32_t epoch, uint32_t* scratch, void* stream) {

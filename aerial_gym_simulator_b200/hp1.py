@@ -253,10 +253,14 @@ class Hp1Engine:
         # scratch for the light obs patch (only useful when derived states are not materialised)
         self.fresh_vel = z(6, N) if (strict_stale_obs and not materialize_derived) else None
         self._actions_ok = {}
-        self._gather, self.gathered_obs = None, None
+        self._gather, self.gathered_obs, self._own_obs = None, None, self.obs
         self._buf = AgxHp1Buffers()
         self._sync_buffers()
         self._cfg_ref, self._buf_ref = C.byref(self.cfg), C.byref(self._buf)
+        # number of single-launch (chained) task steps since tile_sync / any_reset were zeroed = the step index the kernel's
+        # per-tile claim counters hand out; the gather's push waits on that step's arrival counter
+        self._chain_T = 0
+        self._chain_counts = bool(self.lib.agx_hp1_task_step_is_chained(self._cfg_ref, self._buf_ref))
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._task_step = self.lib.agx_hp1_position_task_step
 
@@ -290,32 +294,54 @@ class Hp1Engine:
                 continue
             setattr(b, name, self._ptr(getattr(self, name, None)))
 
-    def attach_obs_gather(self, gather, lag=0):
-        """Fuse the multi-GPU observation all-gather into the task step (distributed.P2PObsAllGather):
-        the step kernel stores each observation row into every rank's gathered buffer over NVLink and
-        runs the flag handshake itself.  After position_task_step, `gathered_obs` is the complete
-        [world*N, 13] tensor of this step (lag=0) or of the previous step (lag=1: the handshake of
-        step t overlaps the compute of step t+1).  Several engines may share one gather object."""
+    def attach_obs_gather(self, gather):
+        """Run the multi-GPU observation all-gather BESIDE the task steps (distributed.PipelinedObsGather).
+
+        The step kernel itself never touches NVLink.  While a gather is attached, `position_task_step` writes this rank's
+        observation straight into its slot of the next buffer of the gather's ring (`self.obs` is a view of that slot) and
+        enqueues the push kernel (NVLink peer stores + per-peer flags) on the gather's side stream; on the chained single-launch
+        path the push waits for the step's completion counter in device memory, so no event is recorded between the chained
+        launches and the push of step t overlaps the compute of step t+1 (the ring depth bounds how far the steps run ahead).
+        `self.gathered_obs` is the [world*N, 13] buffer of the last step: complete after `gather.wait()` (a tiny kernel on the
+        current stream that retires when every rank's rows have landed).  Several engines may share one gather object."""
         if gather is not None and gather.bytes != self.N * 13 * 4:
             raise ValueError("gather object was built for a different shard size")
+        if gather is not None and self.host_io:
+            raise ValueError("host_io and an attached observation gather are mutually exclusive (obs lives in the gather ring)")
+        if self._gather is not None and gather is None:
+            self._gather.fence()
+            self.obs, self._buf.obs = self._own_obs, self._own_obs.data_ptr()
         self._gather, self.gathered_obs = gather, None
-        b = self._buf
-        if gather is None:
-            b.gather_bufs = b.gather_flags = b.gather_done = None
-            b.gather_world = b.gather_rank = b.gather_epoch = b.gather_lag = 0
-        else:
-            if lag not in (0, 1) or (lag == 1 and getattr(gather, "num_buffers", 2) < 4):
-                raise ValueError("lag must be 0, or 1 with a gather object built with num_buffers=4")
-            b.gather_lag = int(lag)
-            b.gather_flags, b.gather_done = gather.flag_ptrs.data_ptr(), gather.scratch.data_ptr()
-            b.gather_world, b.gather_rank = gather.world, gather.rank
+        self._buf.gather_consumed, self._buf.gather_need = None, 0
+        if gather is not None:
+            self._ready_base = self.any_reset.data_ptr() + 32  # four u64 arrival counters (hp1.cu)
+            self._n_tiles = (self.N + 31) // 32
 
-    def _arm_gather(self):
+    def _arm_gather(self, chained):
+        """before the launch: this step's observation goes into the ring slot of the next epoch"""
         g = self._gather
-        if g is not None:
-            epoch, idx = g.next_epoch()
-            self._buf.gather_bufs, self._buf.gather_epoch = g.buf_ptrs[idx].data_ptr(), epoch
-            self.gathered_obs = g.outs[(epoch - self._buf.gather_lag) % len(g.outs)]
+        epoch, slot = g.next_epoch()
+        self.obs = g.own_slot[slot]
+        self._buf.obs = g.own_slot_ptr[slot]
+        if chained:
+            self._buf.gather_consumed, self._buf.gather_need = g.consumed_ptr, max(0, epoch - g.num_buffers)
+        else:
+            self._buf.gather_consumed, self._buf.gather_need = None, 0
+        return epoch, slot
+
+    def _push_gather(self, chained, epoch, slot):
+        """after the launch: the push of this step's rows"""
+        g = self._gather
+        if chained:
+            T = self._chain_T
+            g.push(self._buf.obs, epoch, slot, ready_ctr=self._ready_base + 8 * (T & 3), ready_target=(T // 4 + 1) * self._n_tiles)
+        else:
+            g.push(self._buf.obs, epoch, slot, stream=self._stream())  # two-launch path: plain stream order
+        self.gathered_obs = g.outs[slot]
+
+    def check(self):
+        """Synchronise the current stream and raise if a bounded in-kernel wait of the chained step expired (AGX_E_TIMEOUT)."""
+        _lib.check(self.lib.agx_hp1_check(self._buf_ref, self._stream()), "agx_hp1_check")
 
     def _stream(self):
         # raw stream handle of torch's current stream (the fast private getter when available: the
@@ -359,8 +385,8 @@ class Hp1Engine:
         self._buf.disturbance = None if disturbance is None else disturbance.data_ptr()
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
-        if self._gather is not None:
-            self._arm_gather()
+        chained = self._chain_counts and mid_event is None  # which path the library takes for this launch
+        armed = self._arm_gather(chained) if self._gather is not None else None
         if mid_event is None:
             rc = self._task_step(self._cfg_ref, self._buf_ref, self._stream())
         else:
@@ -368,6 +394,10 @@ class Hp1Engine:
                                                               C.c_void_p(mid_event.cuda_event))
         if rc:
             _lib.check(rc, "agx_hp1_position_task_step")
+        if armed is not None:
+            self._push_gather(chained, *armed)
+        if chained:
+            self._chain_T += 1
 
     def reset(self, mask: torch.Tensor, draws: Optional[dict] = None):
         """mask: bool [N].  draws: dict of uniform [0,1) tensors keyed like AgxHp1ResetDraws, or None

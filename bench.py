@@ -8,8 +8,11 @@
 
 One "step" = one PositionSetpointTask.step over one batch of 65,536 envs per GPU (weak scaling:
 per-GPU work fixed): fused physics + reward + termination/truncation + in-kernel reset +
-observation and (N > 1) the all-gather of the observation tensor, by default fused into the same
-kernel (NVLink peer stores + flag handshake; --gather p2p|nccl for the stand-alone variants).
+observation and (N > 1) the all-gather of the observation tensor: hand-written NVLink push / wait
+kernels that run BESIDE the chained step launches on a side stream (the push of step t overlaps step
+t+1; the K-th gather has landed on every rank before the closing event; --gather sync|nccl for the
+per-step-awaited and the NCCL variants).  The step of an 8-GPU run must RECEIVE 7 x 3.4 MB of rows:
+`roofline.nvlink_floor_us` = that ingress / 900 GB/s is the floor of the step period at N > 1.
 
 Timing: W >= 3 warm-up steps, then exactly K steps bracketed by barrier + synchronize and one
 CUDA-event pair on the launching stream.  One 65,536-env working set (~12 MB) is smaller than the
@@ -186,7 +189,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from aerial_gym_simulator_b200.distributed import ObsAllGather, P2PObsAllGather
+    from aerial_gym_simulator_b200.distributed import ObsAllGather, PipelinedObsGather
     from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,11 +219,12 @@ def run_ours(args):
     eng = engines[0]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(8)]
-    gather = None
+    gather, nccl_gather = None, None
     if world > 1:
+        nccl_gather = ObsAllGather(N, 13, world * N, dev)  # the library collective: fallback and checker of the hand-written one
         if args.gather != "nccl":
             try:  # symmetric-memory rendezvous (NVLink peer mappings); every rank must take the same branch
-                gather = P2PObsAllGather(N, 13, dev, num_buffers=4 if args.gather == "fused" else 2)
+                gather = PipelinedObsGather(N, 13, dev, num_buffers=4, max_ctas=args.gather_ctas)
                 ok = torch.ones(1, device=dev)
             except Exception as exc:  # noqa: BLE001  -- e.g. a box without P2P between some GPU pair
                 sys.stderr.write(f"[bench rank {rank}] {args.gather} gather unavailable ({exc!r})\n")
@@ -228,18 +232,27 @@ def run_ours(args):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if float(ok.item()) == 0.0:  # somebody failed: everybody uses the library collective, and the line says so
                 args.gather, gather = "nccl", None
-        if args.gather == "nccl":
-            gather = ObsAllGather(N, 13, world * N, dev)
-        if args.gather == "fused":  # the step kernel pushes the rows to every peer and handshakes itself
+        if gather is not None:  # the push kernel of every step runs on the gather's side stream, beside the chained steps
             for e in engines:
                 e.attach_obs_gather(gather)
     stream = torch.cuda.current_stream(dev)
+    last = {"engine": eng}
 
-    def step(i, mid=None, rotate=True):
+    def step(i, mid=None, rotate=True, sync_gather=False):
         e = engines[i % R] if rotate else eng
         e.position_task_step(acts[i % 8], mid_event=mid)
-        if world > 1 and args.gather != "fused":
-            gather(e.obs)
+        last["engine"] = e
+        if world > 1:
+            if gather is None:
+                nccl_gather(e.obs)
+            elif sync_gather or args.gather == "sync":
+                gather.wait()  # this step's rows of every rank are here before the next step is launched
+
+    def drain():
+        """everything the steps enqueued so far -- pushes included -- is ordered before what follows on `stream`"""
+        if gather is not None:
+            gather.fence()
+            gather.wait()
 
     def barrier():
         if world > 1:
@@ -251,6 +264,7 @@ def run_ours(args):
         sampler.start()  # samples across warm-up, the timed region and the follow-up loops
     for i in range(max(W, R)):  # every replica is stepped at least once before timing
         step(i)
+    drain()
     barrier()
 
     # ---- timed region: exactly K steps over rotating replicas ------------------------------------
@@ -260,6 +274,7 @@ def run_ours(args):
     ev0.record(stream)
     for i in range(K):
         step(i)
+    drain()  # N > 1: the K-th gather has landed on this rank too, inside the timed region
     ev1.record(stream)
     t_enqueue = time.perf_counter() - t_wall0  # host time to enqueue the K steps (launches are asynchronous)
     barrier()
@@ -270,25 +285,36 @@ def run_ours(args):
     total_s = float(total_ms.item()) * 1e-3
     value = world * N * K / total_s
 
-    # ---- N > 1, fused gather: same loop with the handshake of step t overlapping step t+1 (lag 1) ----
-    value_lag1 = None
-    if world > 1 and args.gather == "fused":
-        for e in engines:
-            e.attach_obs_gather(gather, lag=1)
-        for i in range(R):
-            step(i)
-        barrier()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        for i in range(K):
-            step(i)
-        l1.record(stream)
-        barrier()
-        lag_ms = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(lag_ms, op=dist.ReduceOp.MAX)
-        value_lag1 = world * N * K / (float(lag_ms.item()) * 1e-3)
-        for e in engines:
-            e.attach_obs_gather(gather, lag=0)
+    # ---- N > 1: (a) self-check -- the gathered buffer of the last timed step equals the library collective's gather of the same
+    # observation, on every rank; (b) the same loop with the gather awaited after EVERY step (what a policy in the loop sees) ----
+    gather_check, value_sync = None, None
+    if world > 1:
+        e = last["engine"]
+        if gather is not None:
+            got = gather.wait().clone()
+            want = nccl_gather(e.obs).clone()
+            okc = torch.tensor([int(torch.equal(got, want))], device=dev)
+            try:
+                gather.check()
+                for e_ in engines:
+                    e_.check()
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"[bench rank {rank}] {exc}\n")
+                okc.zero_()
+            dist.all_reduce(okc, op=dist.ReduceOp.MIN)
+            gather_check = bool(okc.item())
+            for i in range(R):
+                step(i, sync_gather=True)
+            barrier()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record(stream)
+            for i in range(K):
+                step(i, sync_gather=True)
+            l1.record(stream)
+            barrier()
+            sync_ms = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(sync_ms, op=dist.ReduceOp.MAX)
+            value_sync = world * N * K / (float(sync_ms.item()) * 1e-3)
 
     # ---- dominant kernel alone: per-step event pairs.  At this size the fused step is ONE
     # launch (hp1_step_kernel<4,true,coop>), so the pair brackets exactly that kernel; on the
@@ -302,6 +328,7 @@ def run_ours(args):
         k0[i].record(stream)
         e.position_task_step(acts[i % 8])
         k1[i].record(stream)
+    drain()
     barrier()
     main_total = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in zip(k0, k1))], device=dev, dtype=torch.float64)
     if world > 1:
@@ -313,6 +340,7 @@ def run_ours(args):
     a0.record(stream)
     for i in range(K):
         step(i, rotate=False)
+    drain()
     a1.record(stream)
     barrier()
     hot_ms = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
@@ -424,12 +452,14 @@ def run_ours(args):
             "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world,
                                               "obs_all_gather": (args.gather if world > 1 else None)}),
             "value_hot_l2": value_hot,
-            "value_obs_gather_lag1": value_lag1,
+            "value_obs_gather_sync": value_sync,
+            "obs_gather_check": gather_check,
             "wall_s_timed_region": t_wall,
             "host_enqueue_us_per_step": 1e6 * t_enqueue / K,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,true> (the whole fused step is this one launch)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,
+                         "nvlink_floor_us": ((world - 1) * N * 13 * 4 / 900e9 * 1e6) if world > 1 else None,
                          "kernel_ms_avg": main_avg_s * 1e3,
                          "kernel_ms_isolated_event_pair": main_iso_s * 1e3,
                          "note": "at 65,536 envs the launch is ~14 MB: FP32 dependent-chain latency bound, not HBM bound (DESIGN.md). "
@@ -537,9 +567,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "p2p", "nccl"],
-                    help="N>1 observation all-gather: fused into the step kernel (NVLink peer stores + flag handshake, "
-                         "default), the stand-alone P2P kernel, or NCCL")
+    ap.add_argument("--gather", default="pipelined", choices=["pipelined", "sync", "nccl"],
+                    help="N>1 observation all-gather: hand-written NVLink push / wait kernels beside the chained steps, the push of "
+                         "step t overlapping step t+1 (default; actions are pre-generated, as at N=1); the same kernels awaited "
+                         "after every step; or NCCL's all_gather_into_tensor after every step")
+    ap.add_argument("--gather-ctas", type=int, default=64, help="CTAs of the push kernel (it shares the GPU with the step kernel)")
     ap.add_argument("--no-hp2", action="store_true", help="skip the secondary depth rays/sec measurement")
     ap.add_argument("--hp2-envs", type=int, default=8192)
     args = ap.parse_args()

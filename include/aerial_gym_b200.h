@@ -33,6 +33,7 @@ extern "C" {
 #define AGX_E_INVALID (-1)   /* bad argument / unsupported configuration */
 #define AGX_E_CUDA (-2)      /* CUDA runtime error (message in agx_last_error) */
 #define AGX_E_NULL (-3)      /* required pointer is NULL */
+#define AGX_E_TIMEOUT (-4)   /* a bounded in-kernel wait expired (agx_hp1_check / agx_obs_gather_check) */
 
 /* controller ids -- one per reference controller class (aerial_gym/control/__init__.py:42-99) */
 #define AGX_CTRL_NONE 0              /* NoControl                       controllers/no_control.py:29-30 */
@@ -124,6 +125,7 @@ typedef struct AgxHp1Buffers {
     uint8_t* reset_mask;      /* [N] bool, envs reset (or to be reset) this step; may be NULL */
     int32_t* any_reset;       /* [16] device scratch, 16-byte aligned, zero-initialised by the caller once and then always
                                  used with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path);
+                                 [2] error word of the chained step's bounded waits (agx_hp1_check);
                                  [4..7] per-step flags, [8..15] four 64-bit arrival counters (single-launch path, hp1.cu) */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
@@ -132,17 +134,12 @@ typedef struct AgxHp1Buffers {
     uint32_t* tile_sync;      /* [2][ceil(N/32)] device scratch, zero-initialised once: per-tile claim / done counters that
                                  chain consecutive single-launch steps tile by tile (hp1.cu "chained steps").
                                  NULL = the step always takes the two-launch path. */
-    /* multi-GPU: fused observation all-gather (NULL / 0 = off).  When set, the fused task step also
-     * stores every env's observation row into slot `gather_rank` of each rank's gathered buffer
-     * [gather_world * N, 13] over NVLink peer memory, then runs agx_p2p_allgather's flag handshake
-     * (same arguments, same meaning) before it retires -- compute and collective in one launch. */
-    void* const* gather_bufs;        /* DEVICE array of gather_world device pointers (this step's parity) */
-    uint32_t* const* gather_flags;   /* DEVICE array of gather_world device pointers to uint32[>= world] */
-    uint32_t* gather_done;           /* device uint32 (zero-initialised once): CTA completion counter */
-    int32_t gather_world, gather_rank;
-    uint32_t gather_epoch;           /* strictly increasing per step, starting at 1 */
-    int32_t gather_lag;              /* 0: the step retires when all peers' rows of this step are here;
-                                        1: when the PREVIOUS step's are (handshake overlaps the next step) */
+    /* multi-GPU (NULL = off): back-pressure from the observation all-gather that runs BESIDE the chained steps
+     * (agx_obs_gather_push on a side stream reads `obs` asynchronously).  `obs` is then one slot of a ring of observation
+     * buffers chosen by the caller per step, and the step may write it only once *gather_consumed >= gather_need, i.e. once
+     * the push that last read this slot has finished reading.  The step kernel itself never touches NVLink. */
+    const unsigned long long* gather_consumed; /* device u64, bumped by agx_obs_gather_push */
+    uint64_t gather_need;
 } AgxHp1Buffers;
 
 /* explicit uniform draws u in [0,1) for agx_hp1_reset, in the reference's call order */
@@ -164,7 +161,7 @@ int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
  * which = 0 AgxHp1Config, 1 AgxHp1Buffers, 2 AgxHp1ResetDraws, 3 AgxHp2Scene, 4 AgxHp2Sensor,
- * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams, 8 AgxHp2Noise, 9 AgxE2ERewardParams */
+ * 5 AgxNavRewardParams, 6 AgxImuConfig, 7 AgxLidarNavRewardParams, 8 AgxHp2Noise, 9 AgxE2ERewardParams, 10 AgxObsGatherPush */
 uint64_t agx_sizeof(int which);
 
 /* Host buffers the kernels can address directly (pinned, portable, mapped: cudaHostAlloc).
@@ -194,6 +191,18 @@ int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf
  * conditional refresh pass, so a caller can time the dominant kernel alone (bench.py roofline). */
 int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream,
                                         void* ev_after_main);
+
+/* 1 when agx_hp1_position_task_step(cfg, buf) takes the single-launch path whose consecutive launches are chained per
+ * 32-env tile (all CTAs of a step co-resident; device-RNG reset + strict stale observation + tile_sync given), 0 when it takes
+ * the two-launch path, negative on error.  Step T (0-based count of such launches since tile_sync / any_reset were zeroed) is
+ * complete -- observation included -- when the u64 at any_reset + 8 + 2 * (T & 3) has reached (T / 4 + 1) * ceil(N / 32):
+ * that is the (ready_ctr, ready_target) pair agx_obs_gather_push waits on. */
+int agx_hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* buf);
+/* Bound of every in-kernel wait (chained steps, observation gather), wall clock; default 20 s.  On expiry a kernel records an
+ * error word and goes on (no trap, the context survives); the next agx_hp1_check / agx_obs_gather_check returns AGX_E_TIMEOUT. */
+int agx_set_spin_timeout_ms(uint64_t ms);
+/* Synchronises `stream` and returns AGX_E_TIMEOUT if a wait of the chained step expired since any_reset was zeroed. */
+int agx_hp1_check(const AgxHp1Buffers* buf, void* stream);
 
 /* Masked re-initialisation, EnvManager.reset_idx for a robot-only scene
  * (env_manager/env_manager.py:273-301 -> IGE_env_manager.py:513-519, base_multirotor.py:177-205,
@@ -483,6 +492,43 @@ int agx_hp2_collide(const AgxHp2Scene* scene, const float* robot_pose, int robot
  *   epoch                  : strictly increasing per call, starting at 1 */
 int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const* peer_flags, int world, int rank,
                       uint64_t bytes, uint32_t epoch, uint32_t* scratch, void* stream);
+
+/* ---- pipelined observation all-gather (the one collective of the step path) ---------------------------------
+ * Split form of agx_p2p_allgather for use BESIDE the chained steps: the PUSH (sender side) runs on a side stream with a few
+ * CTAs while the next steps compute, the WAIT (receiver side) runs on the consumer's stream just before the gathered buffer is
+ * read.  Neither is on the step kernel's critical path.
+ *
+ * agx_obs_gather_push: optionally spin until *ready_ctr >= ready_target (the step that produces `local` has published it: see
+ * agx_hp1_task_step_is_chained; NULL = `local` is already complete in stream order), copy the `bytes` (multiple of 16) of `local`
+ * into slot `rank` of every rank's gathered buffer (peer_bufs[p] + rank * bytes; the own slot is skipped when `local` already is
+ * that slot), bump *consumed (if given) once `local` has been read, then -- when all stores of this rank have been performed at
+ * system scope -- publish `epoch` into peer_flags[p][rank] on every rank p.  The kernel never waits for a peer.
+ *   peer_bufs / peer_flags : DEVICE arrays of `world` device pointers (symmetric-memory rendezvous)
+ *   scratch                : device uint32[4], zero-initialised once
+ *   error_word             : device uint32, zero-initialised once (agx_obs_gather_check)
+ *   epoch                  : strictly increasing per push, starting at 1
+ *   max_ctas               : upper bound of the grid (0 = default 64): the push shares the GPU with the chained step */
+typedef struct AgxObsGatherPush {
+    const void* local;
+    void* const* peer_bufs;
+    uint32_t* const* peer_flags;
+    int32_t world, rank;
+    uint64_t bytes;
+    uint32_t epoch;
+    int32_t max_ctas;
+    const unsigned long long* ready_ctr;
+    uint64_t ready_target;
+    unsigned long long* consumed;
+    uint32_t* scratch;
+    uint32_t* error_word;
+} AgxObsGatherPush;
+int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream);
+/* Receiver side: one tiny kernel that retires when my_flags[q] >= epoch for every rank q < world (wrap-safe compare), i.e.
+ * when every rank's rows of `epoch` have landed in this rank's gathered buffer; work queued behind it on `stream` may read it. */
+int agx_obs_gather_wait(const uint32_t* my_flags, int world, uint32_t epoch, uint32_t* error_word, void* stream);
+/* Synchronises `stream`; AGX_E_TIMEOUT if a push / wait gave up (bounded by agx_set_spin_timeout_ms). */
+int agx_obs_gather_check(const uint32_t* error_word, void* stream);
+int agx_obs_gather_set_timeout_ns(uint64_t ns);
 
 /* Sensor noise + range limits + normalisation, one pass, device RNG.  Replaces WarpSensor.apply_noise +
  * apply_range_limits + normalize_observation (sensors/warp/warp_sensor.py:202-247) when the sensor's noise model is enabled

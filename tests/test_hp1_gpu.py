@@ -376,43 +376,83 @@ def test_error_paths():
         Hp1Engine(spec, 4, "cpu")
 
 
-class _LoopbackGather:
-    """world = 1 stand-in for distributed.P2PObsAllGather (which needs a process group): same
-    fields, plain device tensors.  Exercises the fused push + flag handshake of the step kernel."""
+@pytest.mark.parametrize("n,two_launch", [(4096, False), (776, False), (4096, True), (65536, False)])
+def test_pipelined_obs_gather_loopback(n, two_launch):
+    """The observation all-gather beside the chained steps, on ONE GPU with an emulated world of 3 (every "peer" buffer is a local
+    tensor): the step writes its rows into the ring slot, the push kernel (side stream, waiting on the step's completion counter in
+    device memory -- or in stream order on the two-launch path) copies them into every peer's buffer and publishes the epoch;
+    ring back-pressure lets at most `num_buffers` steps run ahead.  Results equal those of an engine without a gather, bit for bit."""
+    from aerial_gym_simulator_b200.distributed import PipelinedObsGather
 
-    def __init__(self, n, dev):
-        self.world, self.rank, self.bytes, self.epoch = 1, 0, n * 13 * 4, 0
-        self.outs = [torch.zeros(n, 13, device=dev) for _ in range(2)]
-        self.buf_ptrs = [torch.tensor([o.data_ptr()], dtype=torch.int64, device=dev) for o in self.outs]
-        self.flags = torch.zeros(64, dtype=torch.int32, device=dev)
-        self.flag_ptrs = torch.tensor([self.flags.data_ptr()], dtype=torch.int64, device=dev)
-        self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
-
-    def next_epoch(self):
-        self.epoch += 1
-        return self.epoch, self.epoch % 2
-
-
-@pytest.mark.parametrize("n,two_launch", [(4096, False), (777, False), (4096, True)])
-def test_fused_obs_gather_loopback(n, two_launch):
-    """The observation rows pushed into the gathered buffer by the step kernel (or, on the
-    two-launch path, by the stand-alone all-gather the library appends) equal the local obs."""
     spec = H.spec_for("quad_attitude")
     root, actions, params = H.random_inputs(spec, n, seed=4)
+    ref = Hp1Engine(spec, n, DEV, seed=9, materialize_derived=False)
     eng = Hp1Engine(spec, n, DEV, seed=9, materialize_derived=False)
-    H.load_engine_state(eng, root, params)
-    eng.sim_steps.copy_((torch.arange(n, device=DEV) % 500 + 480).int() % 501)
-    gth = _LoopbackGather(n, DEV)
+    for e in (ref, eng):
+        H.load_engine_state(e, root, params)
+        e.sim_steps.copy_((torch.arange(n, device=DEV) % 500 + 480).int() % 501)
+    gth = PipelinedObsGather(n, 13, DEV, num_buffers=4, loopback_world=3)
     eng.attach_obs_gather(gth)
     mid = None
     if two_launch:
         mid = torch.cuda.Event(enable_timing=True)
         mid.record()
-    if n % 4 and two_launch:
-        pytest.skip("stand-alone all-gather needs 16-byte shards")
-    for step in range(12):
-        eng.position_task_step(actions.to(DEV), mid_event=mid)
+    act = actions.to(DEV)
+    # (1) synchronous use: wait for the epoch after every step
+    for step in range(6):
+        ref.position_task_step(act, mid_event=mid)
+        eng.position_task_step(act, mid_event=mid)
+        gth.loopback_complete(gth.epoch)  # the emulated peers "arrive"
+        got = gth.wait()
         torch.cuda.synchronize()
-        assert torch.equal(eng.gathered_obs, eng.obs), f"step {step}"
-        assert eng.gathered_obs is gth.outs[(step + 1) & 1]
-        assert int(gth.flags[0]) == step + 1 and int(gth.scratch[0]) == 0
+        assert got is eng.gathered_obs and got is gth.outs[(step + 1) % 4]
+        assert torch.equal(eng.obs, ref.obs), f"step {step}"
+        assert torch.equal(got[:n], ref.obs)
+        for peer in (1, 2):  # rank 0's rows landed in slot 0 of every peer's buffer
+            assert torch.equal(gth.peer_outs[(step + 1) % 4][peer][:n], ref.obs), f"step {step} peer {peer}"
+        assert gth.flags[0].item() == step + 1 and gth.peer_flags[1][0].item() == step + 1 and gth.peer_flags[2][0].item() == step + 1
+        assert gth.scratch[:2].tolist() == [0, 0] and gth.consumed.item() == step + 1
+    # (2) free running: 40 steps enqueued back to back, pushes overlap the following steps, the ring throttles
+    for step in range(40):
+        ref.position_task_step(act, mid_event=mid)
+        eng.position_task_step(act, mid_event=mid)
+    gth.loopback_complete(gth.epoch)
+    got = gth.wait()
+    gth.check()
+    eng.check()
+    assert torch.equal(got[:n], ref.obs) and torch.equal(eng.root_state, ref.root_state)
+    assert torch.equal(gth.peer_outs[gth.epoch % 4][2][:n], ref.obs)
+    assert gth.consumed.item() == 46 and gth.flags[0].item() == 46
+    # (3) detach: the engine owns its observation buffer again
+    eng.attach_obs_gather(None)
+    ref.position_task_step(act)
+    eng.position_task_step(act)
+    torch.cuda.synchronize()
+    assert eng.obs is eng._own_obs and torch.equal(eng.obs, ref.obs)
+
+
+def test_chained_step_wait_times_out_instead_of_trapping():
+    """A wait that can never be satisfied (ring back-pressure on a counter nobody bumps) expires by wall clock, the step
+    goes on, agx_hp1_check reports AGX_E_TIMEOUT and the CUDA context survives (no __trap on a late producer)."""
+    from aerial_gym_simulator_b200 import _lib
+
+    lib = _lib.load()
+    spec = H.spec_for("quad_attitude")
+    n = 2048
+    eng = Hp1Engine(spec, n, DEV, seed=1, materialize_derived=False)
+    eng.reset(torch.ones(n, dtype=torch.bool, device=DEV))
+    never = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _lib.check(lib.agx_set_spin_timeout_ms(50), "agx_set_spin_timeout_ms")
+    try:
+        eng._buf.gather_consumed, eng._buf.gather_need = never.data_ptr(), 1
+        eng.position_task_step(torch.zeros(n, 4, device=DEV))
+        with pytest.raises(_lib.AgxError, match="timed out"):
+            eng.check()
+        assert int(eng.any_reset[2]) == 1
+    finally:
+        _lib.check(lib.agx_set_spin_timeout_ms(20000), "agx_set_spin_timeout_ms")
+    # the context is alive and a fresh engine steps normally
+    eng2 = Hp1Engine(spec, n, DEV, seed=1, materialize_derived=False)
+    eng2.reset(torch.ones(n, dtype=torch.bool, device=DEV))
+    eng2.position_task_step(torch.zeros(n, 4, device=DEV))
+    eng2.check()
