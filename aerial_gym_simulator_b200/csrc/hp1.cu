@@ -23,7 +23,10 @@ using namespace agx;
 
 namespace {
 
-constexpr int kWarpsPerBlock = 2;
+#ifndef AGX_HP1_WARPS_PER_BLOCK
+#define AGX_HP1_WARPS_PER_BLOCK 2
+#endif
+constexpr int kWarpsPerBlock = AGX_HP1_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kTileFloats = 32 * 13;
 
@@ -39,6 +42,16 @@ __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -258,7 +271,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #endif
 
 #ifndef AGX_HP1_MIN_BLOCKS
-#define AGX_HP1_MIN_BLOCKS 8
+#define AGX_HP1_MIN_BLOCKS (16 / AGX_HP1_WARPS_PER_BLOCK)  // 16 warps x 128 registers = the register file
 #endif
 template <int M, bool TASK, bool COOP = false, int SPEC = -1>
 __global__ void __launch_bounds__(kThreads, AGX_HP1_MIN_BLOCKS)
@@ -278,21 +291,40 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     if constexpr (COOP) {
         const int my_tile = blockIdx.x * kWarpsPerBlock + warp;
         const bool has_tile = my_tile < n_tiles;
-        if (has_tile && lane == 0) step_T = atomicAdd(buf.tile_sync + my_tile, 1u);  // claim: which step of this tile am I?
+        // The claim, the tile's done-counter and the four arrival counters are fetched TOGETHER (one memory round trip instead of
+        // three in a row: the prologue is pure latency on the warp's critical path).  The two speculative reads are relaxed; once the
+        // claim says which step this is they are checked, and if they already show what the step needs (the steady state) a
+        // gpu-scope fence turns them into acquires.  Otherwise the warp falls back to the acquire spins.
+        uint32_t done_spec = 0;
+        unsigned long long arr_spec[4] = {0ull, 0ull, 0ull, 0ull};
+        const uint32_t* done = buf.tile_sync + n_tiles + (has_tile ? my_tile : 0);
+        const unsigned long long* arrivals = reinterpret_cast<const unsigned long long*>(buf.any_reset + 8);
+        if (has_tile && lane == 0) {
+            step_T = atomicAdd(buf.tile_sync + my_tile, 1u);  // claim: which step of this tile am I?
+            done_spec = ld_relaxed_gpu_u32(done);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) arr_spec[k] = ld_relaxed_gpu_u64(arrivals + k);
+        }
         step_T = __shfl_sync(0xffffffffu, step_T, 0);
-        __syncthreads();  // both warps hold their claim before the CTA lets the next launch in
+        __syncthreads();  // every warp of the CTA holds its claim before the CTA lets the next launch in
         // programmatic dependent launch: once every CTA of this grid is here, the NEXT step's CTAs may be scheduled
         asm volatile("griddepcontrol.launch_dependents;" ::"r"(step_T) : "memory");
         if (has_tile) {
             if (lane == 0) {
-                const uint32_t* done = buf.tile_sync + n_tiles + my_tile;
-                // this tile's previous step has published its state
-                spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset);
+                bool ready = done_spec == step_T;  // this tile's previous step has published its state
+                unsigned long long want2 = 0ull;
+                const uint32_t P = step_T - 2u;
                 if (step_T >= 2u) {  // step T-2 complete everywhere: bounds the skew to two steps in flight
-                    const uint32_t P = step_T - 2u;
-                    const unsigned long long* a2 = reinterpret_cast<const unsigned long long*>(buf.any_reset + 8) + (P & 3u);
-                    const unsigned long long want = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
-                    spin_until([&] { return ld_acquire_gpu_u64(a2) >= want; }, buf.any_reset);
+                    want2 = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
+                    const unsigned sel = P & 3u;  // (selects, not a dynamically indexed local array)
+                    const unsigned long long a = sel == 0u ? arr_spec[0] : sel == 1u ? arr_spec[1] : sel == 2u ? arr_spec[2] : arr_spec[3];
+                    ready = ready && a >= want2;
+                }
+                if (ready) {
+                    __threadfence();  // relaxed reads + fence = acquire
+                } else {
+                    spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset);
+                    if (step_T >= 2u) spin_until([&] { return ld_acquire_gpu_u64(arrivals + (P & 3u)) >= want2; }, buf.any_reset);
                 }
                 if (buf.gather_consumed) {  // the gather kernel has read the ring slot this step's observation goes into
                     const unsigned long long need = buf.gather_need;
@@ -726,7 +758,7 @@ inline int coop_capacity(StepKernel k) {
 // CTA slots kept free for kernels that run BESIDE the chained step (the observation gather's push kernel): the one-sided grid
 // barrier needs every CTA of a step resident, so the step only takes the single-launch path when it fits with this margin
 #ifndef AGX_HP1_COOP_RESERVE
-#define AGX_HP1_COOP_RESERVE 96
+#define AGX_HP1_COOP_RESERVE (192 / AGX_HP1_WARPS_PER_BLOCK)  // 96 two-warp CTAs = 96 x 8192 registers
 #endif
 constexpr int kCoopReserve = AGX_HP1_COOP_RESERVE;
 inline int grid_for(int n_envs) {

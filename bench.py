@@ -25,9 +25,13 @@ Step launches are chained per 32-env tile, not per grid (hp1.cu "chained steps")
 loop the tail of one replica's step overlaps the next replica's step.
 
 Reference arm (`--impl reference`): the reference's Isaac Gym sim_device=cpu pipeline cannot run
-here or on the GPU box (isaacgym is a closed binary, not installed; /root/reference does not
-travel).  It times the oracle port of the same step (oracle/hp1_oracle.py: the reference's torch
-control stack restated + our integrator spec) on the host cores with all torch threads.
+here or on the GPU box (isaacgym is a closed binary, not installed).  What CAN run is the reference's
+own torch control stack: `__graft_entry__.build()` installs the unmodified reference into the
+git-ignored `baseline/_ref` (pip --no-deps; it travels with the snapshot) and oracle/reference_arm.py
+drives its BaseMultirotor.step / compute_reward / reset_idx on the host cores, with the oracle's
+rigid-body integrator standing in for PhysX (`kind: "reference"`).  Where baseline/_ref is missing
+the oracle port of the same step is timed instead (`kind: "port"`).  Rank 0 runs it with every host
+thread, whatever --gpus says (torchrun's OMP_NUM_THREADS=1 is overridden).
 """
 import argparse
 import json
@@ -155,26 +159,58 @@ def time_cpu_port(n_envs, steps, warmup):
     return n_envs * steps / dt, dt / steps, used
 
 
+def host_threads():
+    """threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which is not the host's capacity"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu_reference(n_envs, steps, warmup):
+    """(value, s/step, threads, kind, note): the reference's own control stack from baseline/_ref when it was staged
+    (oracle/reference_arm.py), else the oracle port"""
+    import torch
+
+    torch.set_num_threads(host_threads())
+    from oracle import reference_arm as RA
+
+    if RA.staged():
+        # the reference logs to stdout (its own logger and a print in control_allocation.py): keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            v, per, cores = RA.time_reference(n_envs, steps, warmup)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+        return v, per, cores, "reference", ("unmodified reference control stack (baseline/_ref: BaseMultirotor.step, compute_reward, reset_idx) on torch CPU + "
+                                            "the oracle's rigid-body integrator in place of PhysX (closed binary, not installable); NOT the Isaac Gym CPU pipeline")
+    v, per, cores = time_cpu_port(n_envs, steps, warmup)
+    return v, per, cores, "port", "oracle port of the reference step (baseline/_ref was not staged on this box)"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return 0  # rank 0 alone measures the host: it uses every host thread, whatever the number of GPUs
     n_envs = ENVS_PER_GPU
     # bound the sample: keep the whole run within ~2 minutes of CPU time
-    v1, t1, cores = time_cpu_port(n_envs, 1, 1)
+    _, t1, _, _, _ = time_cpu_reference(n_envs, 1, 1)
     budget = 120.0
     if (args.steps + args.warmup) * t1 > budget:
         n_envs = max(1024, int(n_envs * budget / ((args.steps + args.warmup) * t1)) // 1024 * 1024)
-    value, per_step, cores = time_cpu_port(n_envs, args.steps, max(args.warmup, 1))
-    sample = f"{n_envs} envs x {args.steps} steps, torch CPU fp32, {cores} threads"
+    value, per_step, cores, kind, note = time_cpu_reference(n_envs, args.steps, max(args.warmup, 1))
+    sample = f"{n_envs} envs x {args.steps} steps, torch CPU fp32, {cores} threads (of {host_threads()} available to the process)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, {"l2": "n/a (CPU)", "sample_envs": n_envs,
-                                              "note": "oracle port of the reference step (reference torch control stack restated + integrator spec); "
-                                                      "NOT the Isaac Gym CPU pipeline, which cannot be installed"}),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, {"l2": "n/a (CPU)", "sample_envs": n_envs, "note": note + "; a host measurement: the same "
+                                              "whole-host throughput is reported for every --gpus N (rank 0 runs it with all host threads)"}),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -442,9 +478,9 @@ def run_ours(args):
             pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, per, cores = time_cpu_port(ENVS_PER_GPU, 40, 3)
-            cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                   "sample": f"{ENVS_PER_GPU} envs x 40 steps of the same step, oracle port, torch CPU fp32"}
+            v, per, cores, kind, note = time_cpu_reference(ENVS_PER_GPU, 40, 3)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind,
+                   "sample": f"{ENVS_PER_GPU} envs x 40 steps of the same step, torch CPU fp32: {note}"}
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_s * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
