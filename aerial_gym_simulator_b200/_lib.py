@@ -54,13 +54,13 @@ _HP1_BUF_FIELDS = [
 
 
 class AgxHp1Buffers(C.Structure):
-    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS] + [("gather_consumed", C.c_void_p), ("gather_need", C.c_uint64)]
+    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS]
 
 
 class AgxObsGatherPush(C.Structure):
     _fields_ = [("local", fp), ("peer_bufs", fp), ("peer_flags", fp), ("world", C.c_int32), ("rank", C.c_int32),
                 ("bytes", C.c_uint64), ("epoch", C.c_uint32), ("max_ctas", C.c_int32), ("ready_ctr", fp), ("ready_target", C.c_uint64),
-                ("consumed", fp), ("scratch", fp), ("error_word", fp)]
+                ("scratch", fp), ("error_word", fp), ("flag_slot", C.c_int32), ("pad_", C.c_int32)]
 
 
 _HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",
@@ -162,7 +162,7 @@ def load():
         "agx_hp2_cast": [C.POINTER(AgxHp2Scene), C.POINTER(AgxHp2Sensor), C.c_void_p],
         "agx_p2p_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_obs_gather_push": [C.POINTER(AgxObsGatherPush), C.c_void_p],
-        "agx_obs_gather_wait": [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p],
+        "agx_obs_gather_wait": [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_obs_gather_check": [C.c_void_p, C.c_void_p],
         "agx_obs_gather_set_timeout_ns": [C.c_uint64],
         "agx_set_spin_timeout_ms": [C.c_uint64],

@@ -28,6 +28,14 @@ AGX_DEV void sincos_(float x, float* s, float* c) { sincos_shared_(x, s, c); }
 AGX_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
 #endif
 
+// same idea for atan2f (two per update_states): -DAGX_HP1_NOINLINE_ATAN2, an experiment
+#if defined(AGX_HP1_NOINLINE_ATAN2) && !defined(AGX_HOST_SHADOW)
+__device__ __noinline__ float atan2_shared_(float y, float x) { return atan2f(y, x); }
+AGX_DEV float atan2_(float y, float x) { return atan2_shared_(y, x); }
+#else
+AGX_DEV float atan2_(float y, float x) { return atan2f(y, x); }
+#endif
+
 #define AGX_PI_F 3.14159265358979323846f
 #define AGX_TWO_PI_F 6.28318530717958647692f
 
@@ -126,12 +134,12 @@ AGX_DEV float ssa_0_2pi(float a) {
 AGX_DEV V3 euler_xyz_0_2pi(Q4 q) {
     float sinr_cosp = 2.0f * (q.w * q.x + q.y * q.z);
     float cosr_cosp = q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
-    float roll = atan2f(sinr_cosp, cosr_cosp);
+    float roll = atan2_(sinr_cosp, cosr_cosp);
     float sinp = 2.0f * (q.w * q.y - q.z * q.x);
     float pitch = (fabsf(sinp) >= 1.0f) ? copysignf(0.5f * AGX_PI_F, sinp) : asinf(sinp);
     float siny_cosp = 2.0f * (q.w * q.z + q.x * q.y);
     float cosy_cosp = q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z;
-    float yaw = atan2f(siny_cosp, cosy_cosp);
+    float yaw = atan2_(siny_cosp, cosy_cosp);
     return V3{wrap_0_2pi(roll), wrap_0_2pi(pitch), wrap_0_2pi(yaw)};
 }
 

@@ -255,9 +255,11 @@ AGX_HP1_RESET_FN void reset_one_env(const AgxHp1Config& cfg, const AgxHp1Buffers
 //   any_reset[4 + (T & 3)]        u32 flag of step T: raised = holds T + 1 (monotonic, never cleared)
 //   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared)
 //   tile_sync[tile], tile_sync[n_tiles + tile]   claim / done counters of the tile
-// (3) Multi-GPU: the step kernel never touches NVLink.  With an observation all-gather attached (agx_obs_gather_push,
-// p2p_allgather.cu, on a side stream) the only coupling is back-pressure on the observation ring: buf.obs is one slot of a ring
-// that the gather kernel reads asynchronously, and a warp may overwrite its slot only when *gather_consumed >= gather_need.
+// (3) Multi-GPU: the step kernel never touches NVLink and never waits for the gather.  With an observation all-gather attached
+// (agx_obs_gather_push, p2p_allgather.cu, on side streams) buf.obs is one slot of a ring the push kernels read asynchronously; the
+// HOST keeps a step from overwriting a slot whose push has not finished (stream events) -- an in-kernel wait here would let the
+// blocked step's CTAs and their chained successors hold every CTA slot the pending push needs (measured: round 2, 2 GPUs, deadlock
+// until the wall-clock bound fired, profiles/p2p_2gpu_r2c_ring_backpressure_deadlock.log).
 #ifdef AGX_TIMELINE  // debug builds only (tools/dbg/timeline.py): per-warp start / end globaltimer stamps
 __device__ unsigned long long g_timeline[4][8192];
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -325,10 +327,6 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 } else {
                     spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset);
                     if (step_T >= 2u) spin_until([&] { return ld_acquire_gpu_u64(arrivals + (P & 3u)) >= want2; }, buf.any_reset);
-                }
-                if (buf.gather_consumed) {  // the gather kernel has read the ring slot this step's observation goes into
-                    const unsigned long long need = buf.gather_need;
-                    spin_until([&] { return ld_acquire_gpu_u64(buf.gather_consumed) >= need; }, buf.any_reset);
                 }
             }
             __syncwarp();
@@ -704,8 +702,6 @@ int validate(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, bool task) {
             return agx_set_error(AGX_E_NULL, "task step needs sim_steps/obs/reward/terminations/truncations/any_reset");
         if ((cfg->flags & AGX_F_DEVICE_RNG_RESET) && !buf->episode_count)
             return agx_set_error(AGX_E_NULL, "device-RNG reset needs episode_count");
-        if (buf->gather_consumed && ((uintptr_t)buf->gather_consumed & 7))
-            return agx_set_error(AGX_E_INVALID, "gather_consumed must be 8-byte aligned");
     }
     return AGX_OK;
 }
@@ -845,8 +841,6 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
         cudaError_t e = cudaLaunchKernelEx(&lc, pick_kernel<true, true>(cfg), *cfg, *buf, v);
         return agx_check_cuda(e, "hp1_step_kernel<task, single-launch>");
     }
-    if (buf->gather_consumed)
-        return agx_set_error(AGX_E_INVALID, "observation-ring back-pressure (gather_consumed) needs the single-launch path");
     pick_kernel<true, false>(cfg)<<<g, kThreads, 0, st>>>(*cfg, *buf, v);
     rc = agx_check_launch("hp1_step_kernel<task>");
     if (rc) return rc;

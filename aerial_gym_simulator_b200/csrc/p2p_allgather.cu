@@ -141,18 +141,13 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
         const float4 v = __ldcg(local + i);
         for (int p = 0; p < np; ++p) s_dst[p][i] = v;
     }
-    __syncthreads();  // the CTA's loads are done and its peer stores are ordered before thread 0's fences (cumulativity)
+    __syncthreads();  // the CTA's peer stores are ordered before thread 0's fences (cumulativity)
     if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(a.scratch + 0, 1u) == gridDim.x - 1) {  // every CTA has finished READING `local`
-            a.scratch[0] = 0u;
-            if (a.consumed) atomicAdd(a.consumed, 1ull);
-        }
         __threadfence_system();  // waits until this CTA's NVLink stores have been performed
-        if (atomicAdd(a.scratch + 1, 1u) == gridDim.x - 1) {  // ... and so have everybody else's
-            a.scratch[1] = 0u;
+        if (atomicAdd(a.scratch, 1u) == gridDim.x - 1) {  // ... and so have everybody else's
+            a.scratch[0] = 0u;
             __threadfence_system();
-            for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + a.rank, a.epoch);
+            for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + a.flag_slot * AGX_MAX_PEERS + a.rank, a.epoch);
         }
     }
 }
@@ -179,21 +174,22 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
         return agx_set_error(AGX_E_INVALID, "obs_gather_push: bad world/rank");
     if (a->bytes % 16 || ((uintptr_t)a->local & 15)) return agx_set_error(AGX_E_INVALID, "obs_gather_push: bytes and local must be 16-byte aligned");
     if (a->epoch == 0) return agx_set_error(AGX_E_INVALID, "obs_gather_push: epoch starts at 1");
-    if (((uintptr_t)a->ready_ctr | (uintptr_t)a->consumed) & 7) return agx_set_error(AGX_E_INVALID, "obs_gather_push: counters must be 8-byte aligned");
+    if ((uintptr_t)a->ready_ctr & 7) return agx_set_error(AGX_E_INVALID, "obs_gather_push: ready_ctr must be 8-byte aligned");
+    if (a->flag_slot < 0 || a->flag_slot > 3) return agx_set_error(AGX_E_INVALID, "obs_gather_push: flag_slot must be in [0, 3]");
     if (a->bytes == 0) return AGX_OK;
     const size_t n_vec = a->bytes / 16;
     long long ctas = (long long)((n_vec + (size_t)kPushThreads * kPushUnroll - 1) / ((size_t)kPushThreads * kPushUnroll));
-    const int cap = a->max_ctas > 0 ? a->max_ctas : 64;
+    const int cap = a->max_ctas > 0 ? a->max_ctas : 24;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     obs_gather_push_kernel<<<(int)ctas, kPushThreads, 0, (cudaStream_t)stream>>>(*a, n_vec);
     return agx_check_launch("obs_gather_push_kernel");
 }
 
-extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int world, uint32_t epoch, uint32_t* error_word, void* stream) {
+extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int flag_slot, int world, uint32_t epoch, uint32_t* error_word, void* stream) {
     if (!my_flags || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_wait: NULL argument");
-    if (world < 1 || world > AGX_MAX_PEERS) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world");
-    obs_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags, world, epoch, error_word);
+    if (world < 1 || world > AGX_MAX_PEERS || flag_slot < 0 || flag_slot > 3) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world / flag_slot");
+    obs_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags + flag_slot * AGX_MAX_PEERS, world, epoch, error_word);
     return agx_check_launch("obs_gather_wait_kernel");
 }
 

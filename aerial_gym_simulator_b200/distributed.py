@@ -129,27 +129,32 @@ class P2PObsAllGather:
 
 class PipelinedObsGather:
     """The observation all-gather of SURVEY 8e as two hand-written kernels that run BESIDE the steps instead of inside them
-    (csrc/p2p_allgather.cu: agx_obs_gather_push / agx_obs_gather_wait), over a ring of symmetric-memory buffers:
+    (csrc/p2p_allgather.cu: agx_obs_gather_push / agx_obs_gather_wait), over a ring of `num_buffers` symmetric-memory buffers:
 
     * sender: the step writes its observation straight into this rank's slot of ring buffer `epoch % num_buffers`; `push`
-      (side stream, <= max_ctas CTAs that fit beside the resident step kernel) stores that slot into the same place of every
-      peer's buffer over NVLink and, once its stores have been performed, publishes `epoch` in every rank's flag word;
+      (that ring slot's own side stream, <= max_ctas CTAs that fit beside the resident step kernel) stores it into the same place
+      of every peer's buffer over NVLink and, once its stores have been performed, publishes `epoch` in every rank's flag word of
+      that ring slot.  Pushes into different ring slots run concurrently: one push alone is a chain of latencies (wake-up, L2
+      reads, NVLink drain, two system fences: ~15 us for 3.4 MB), `num_buffers` of them in flight sustain a step period of a
+      few microseconds;
     * receiver: `wait(epoch)` = a one-warp kernel on the consumer's stream that retires when all `world` flags show `epoch`.
 
-    The push never waits for a peer and the step never waits for NVLink; the only back-pressure is the ring (a step may reuse a
-    slot once the push that read it has finished reading, AgxHp1Buffers.gather_consumed).  Equal shards only.
+    The push never waits for a peer and the step kernel never waits for anything of this class.  Re-use of a ring slot is ordered by
+    the HOST: `next_epoch()` makes the current stream wait for the event recorded behind the push that last read the slot -- only
+    when that push has not finished yet, so the chained step launches stay back to back while the gather keeps up.  Equal shards only.
     `loopback_world` (tests, one GPU): emulate a world of that size inside one process -- every "peer" buffer is a local
     buffer, rank 0 is this process; the protocol (ring, flags, counters) runs exactly as on several GPUs."""
 
-    def __init__(self, local_count: int, feat: int, device, group=None, num_buffers: int = 4, max_ctas: int = 64,
+    def __init__(self, local_count: int, feat: int, device, group=None, num_buffers: int = 4, max_ctas: int = 24,
                  loopback_world: int = 0):
         import ctypes as C
 
         from . import _lib
 
         self._C, self._lib, self._check = C, _lib.load(), _lib.check
-        self._Push = _lib.AgxObsGatherPush
         self.device = torch.device(device)
+        if not 1 <= int(num_buffers) <= 4:
+            raise ValueError("num_buffers must be in [1, 4] (flag words: 4 ring slots x AGX_MAX_PEERS)")
         self.num_buffers, self.max_ctas = int(num_buffers), int(max_ctas)
         self.bytes = local_count * feat * 4
         if self.bytes % 16:
@@ -157,12 +162,13 @@ class PipelinedObsGather:
         self.local_count, self.feat = local_count, feat
         i64 = lambda ptrs: torch.tensor(list(ptrs), dtype=torch.int64, device=self.device)
         self._handles = []
+        B = self.num_buffers
         if loopback_world:
             self.world, self.rank = int(loopback_world), 0
-            self.outs = [torch.zeros(self.world * local_count, feat, device=self.device) for _ in range(num_buffers)]
+            self.outs = [torch.zeros(self.world * local_count, feat, device=self.device) for _ in range(B)]
             # "peer" p's gathered buffers: separate local tensors (peer 0 = ours)
-            self.peer_outs = [[self.outs[b]] + [torch.zeros_like(self.outs[b]) for _ in range(self.world - 1)] for b in range(num_buffers)]
-            self.buf_ptrs = [i64(t.data_ptr() for t in self.peer_outs[b]) for b in range(num_buffers)]
+            self.peer_outs = [[self.outs[b]] + [torch.zeros_like(self.outs[b]) for _ in range(self.world - 1)] for b in range(B)]
+            self.buf_ptrs = [i64(t.data_ptr() for t in self.peer_outs[b]) for b in range(B)]
             self.flags = torch.zeros(64, dtype=torch.int32, device=self.device)
             self.peer_flags = [self.flags] + [torch.zeros_like(self.flags) for _ in range(self.world - 1)]
             self.flag_ptrs = i64(t.data_ptr() for t in self.peer_flags)
@@ -172,7 +178,7 @@ class PipelinedObsGather:
             group = group if group is not None else dist.group.WORLD
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
             self.outs, self.buf_ptrs = [], []
-            for _ in range(num_buffers):
+            for _ in range(B):
                 o = symm_mem.empty(self.world * local_count, feat, dtype=torch.float32, device=self.device)
                 h = symm_mem.rendezvous(o, group)
                 o.zero_()
@@ -187,51 +193,69 @@ class PipelinedObsGather:
         r0 = self.rank * local_count
         self.own_slot = [o[r0:r0 + local_count] for o in self.outs]
         self.own_slot_ptr = [t.data_ptr() for t in self.own_slot]
-        self.scratch = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.scratch = torch.zeros(B, 4, dtype=torch.int32, device=self.device)
         self.error_word = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.consumed = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.consumed_ptr = self.consumed.data_ptr()
-        self.side = torch.cuda.Stream(device=self.device, priority=-1)  # its few CTAs go ahead of the next step's
-        self._side_raw = self.side.cuda_stream
-        self._push = self._Push()
-        self._push.peer_flags, self._push.world, self._push.rank = self.flag_ptrs.data_ptr(), self.world, self.rank
-        self._push.bytes, self._push.max_ctas = self.bytes, self.max_ctas
-        self._push.consumed, self._push.scratch, self._push.error_word = self.consumed_ptr, self.scratch.data_ptr(), self.error_word.data_ptr()
-        self._push_ref = C.byref(self._push)
-        self._buf_ptr_raw = [t.data_ptr() for t in self.buf_ptrs]
+        # one side stream + one event per ring slot; high priority: their few CTAs go ahead of the next step's
+        self.streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(B)]
+        self._raw = [st.cuda_stream for st in self.streams]
+        self.events = [torch.cuda.Event() for _ in range(B)]
+        self._pending = [False] * B
+        self._pushes = []
+        for b in range(B):
+            a = _lib.AgxObsGatherPush()
+            a.peer_bufs, a.peer_flags, a.world, a.rank = self.buf_ptrs[b].data_ptr(), self.flag_ptrs.data_ptr(), self.world, self.rank
+            a.bytes, a.max_ctas, a.flag_slot = self.bytes, self.max_ctas, b
+            a.scratch, a.error_word = self.scratch[b].data_ptr(), self.error_word.data_ptr()
+            self._pushes.append((a, C.byref(a)))
         self.epoch = 0
+        self.throttled = 0  # how many times a step had to wait for the push that last read its ring slot
         torch.cuda.synchronize(self.device)
         if not loopback_world:
             dist.barrier(group)  # every rank's flags are zeroed before anybody publishes epoch 1
 
     def next_epoch(self):
-        """(epoch, ring slot) of the next step"""
+        """(epoch, ring slot) of the next step.  The step will overwrite this rank's rows in ring buffer `slot`: the current stream
+        first waits for the push that last read them, if it is still running."""
         self.epoch += 1
-        return self.epoch, self.epoch % self.num_buffers
+        slot = self.epoch % self.num_buffers
+        if self._pending[slot]:
+            ev = self.events[slot]
+            if not ev.query():
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                self.throttled += 1
+            self._pending[slot] = False
+        return self.epoch, slot
 
     def push(self, local_ptr: int, epoch: int, slot: int, ready_ctr: int = 0, ready_target: int = 0, stream=None):
-        """enqueue the push of `local_ptr` (this rank's rows, device pointer) as `epoch` into ring slot `slot`: on the side stream
-        (the kernel spins on *ready_ctr >= ready_target before reading) or, with `stream`, in that stream's order"""
-        p = self._push
-        p.local, p.peer_bufs, p.epoch = local_ptr, self._buf_ptr_raw[slot], epoch
-        p.ready_ctr, p.ready_target = (ready_ctr or None), ready_target
-        rc = self._lib.agx_obs_gather_push(self._push_ref, self._side_raw if stream is None else stream)
+        """enqueue the push of `local_ptr` (this rank's rows, device pointer) as `epoch` into ring slot `slot`: on the slot's side
+        stream (the kernel spins on *ready_ctr >= ready_target before reading) or, with `stream`, in that stream's order"""
+        a, ref = self._pushes[slot]
+        a.local, a.epoch = local_ptr, epoch
+        a.ready_ctr, a.ready_target = (ready_ctr or None), ready_target
+        rc = self._lib.agx_obs_gather_push(ref, self._raw[slot] if stream is None else stream)
         if rc:
             self._check(rc, "agx_obs_gather_push")
+        if stream is None:
+            self.events[slot].record(self.streams[slot])
+            self._pending[slot] = True
 
     def wait(self, epoch: Optional[int] = None, stream=None):
         """make `stream` (default: the current one) wait until every rank's rows of `epoch` (default: the latest) are here;
         returns the gathered [world*N, feat] buffer of that epoch"""
         epoch = self.epoch if epoch is None else epoch
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        self._check(self._lib.agx_obs_gather_wait(self.flags.data_ptr(), self.world, epoch, self.error_word.data_ptr(), st), "agx_obs_gather_wait")
-        return self.outs[epoch % self.num_buffers]
+        slot = epoch % self.num_buffers
+        self._check(self._lib.agx_obs_gather_wait(self.flags.data_ptr(), slot, self.world, epoch, self.error_word.data_ptr(), st),
+                    "agx_obs_gather_wait")
+        return self.outs[slot]
 
     def fence(self):
         """the current stream waits for every push enqueued so far (before anything overwrites what a push may still read)"""
-        ev = torch.cuda.Event()
-        ev.record(self.side)
-        torch.cuda.current_stream(self.device).wait_event(ev)
+        cur = torch.cuda.current_stream(self.device)
+        for b in range(self.num_buffers):
+            if self._pending[b]:
+                cur.wait_event(self.events[b])
+                self._pending[b] = False
 
     def check(self):
         """synchronise and raise if a push / wait gave up (AGX_E_TIMEOUT)"""
@@ -240,6 +264,7 @@ class PipelinedObsGather:
                     "agx_obs_gather_check")
 
     def loopback_complete(self, epoch: int):
-        """loopback only: play the other ranks -- copy nothing (their rows are not simulated), just publish their flags"""
+        """loopback only: play the other ranks -- their rows are not simulated, only their flags of this epoch's ring slot"""
+        slot = epoch % self.num_buffers
         for q in range(1, self.world):
-            self.flags[q] = epoch
+            self.flags[slot * 16 + q] = epoch

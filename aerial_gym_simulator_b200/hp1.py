@@ -299,9 +299,10 @@ class Hp1Engine:
 
         The step kernel itself never touches NVLink.  While a gather is attached, `position_task_step` writes this rank's
         observation straight into its slot of the next buffer of the gather's ring (`self.obs` is a view of that slot) and
-        enqueues the push kernel (NVLink peer stores + per-peer flags) on the gather's side stream; on the chained single-launch
-        path the push waits for the step's completion counter in device memory, so no event is recorded between the chained
-        launches and the push of step t overlaps the compute of step t+1 (the ring depth bounds how far the steps run ahead).
+        enqueues the push kernel (NVLink peer stores + per-peer flags) on the ring slot's side stream; on the chained single-launch
+        path the push waits for the step's completion counter in device memory, so nothing is recorded between the chained
+        launches and the push of step t overlaps the compute of the following steps (a step only waits -- by a stream event, on
+        the host's initiative -- when the push that last read its ring slot is still running).
         `self.gathered_obs` is the [world*N, 13] buffer of the last step: complete after `gather.wait()` (a tiny kernel on the
         current stream that retires when every rank's rows have landed).  Several engines may share one gather object."""
         if gather is not None and gather.bytes != self.N * 13 * 4:
@@ -312,7 +313,6 @@ class Hp1Engine:
             self._gather.fence()
             self.obs, self._buf.obs = self._own_obs, self._own_obs.data_ptr()
         self._gather, self.gathered_obs = gather, None
-        self._buf.gather_consumed, self._buf.gather_need = None, 0
         if gather is not None:
             self._ready_base = self.any_reset.data_ptr() + 32  # four u64 arrival counters (hp1.cu)
             self._n_tiles = (self.N + 31) // 32
@@ -323,10 +323,6 @@ class Hp1Engine:
         epoch, slot = g.next_epoch()
         self.obs = g.own_slot[slot]
         self._buf.obs = g.own_slot_ptr[slot]
-        if chained:
-            self._buf.gather_consumed, self._buf.gather_need = g.consumed_ptr, max(0, epoch - g.num_buffers)
-        else:
-            self._buf.gather_consumed, self._buf.gather_need = None, 0
         return epoch, slot
 
     def _push_gather(self, chained, epoch, slot):

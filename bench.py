@@ -452,9 +452,26 @@ def run_ours(args):
     h2d = N * 4 * 4
     d2h = N * 13 * 4 + N * 4 + 2 * N
 
-    hp2 = None
+    hp2 = cfg3 = cfg4 = sweep = nav = None
     if not args.no_hp2:
-        hp2 = run_hp2_depth(dev, world, rank, args)
+        hp2 = run_hp2_config(dev, world, rank, label="depth+seg camera 64x48, 44-box scene (north_star target config)",
+                             metric="depth rays/sec (64x48 depth+seg camera, 44-box scene)", E=args.hp2_envs, K=44, cfg=_CamCfg,
+                             frames=max(5, min(K, 50)), extent=5.0, seed=7, cpu_sample_envs=8)
+    if not args.no_configs:
+        # BASELINE.json configs[2]: navigation_task sensor side -- 270x480 depth camera, 1024-obstacle scene, 8192 envs
+        cam3 = type("Cam270x480", (_CamCfg,), {"height": 270, "width": 480})
+        cfg3 = run_hp2_config(dev, world, rank, label="BASELINE configs[2]: 270x480 depth+seg camera, 1024 boxes (12,288 triangles) per env",
+                              metric="depth rays/sec (270x480 depth+seg camera, 1024-obstacle scene)", E=args.cfg3_envs, K=1024, cfg=cam3,
+                              frames=2, extent=8.0, seed=11, cpu_sample_envs=1)
+        # BASELINE.json configs[3]: 64x512 LiDAR + segmentation on a fully-actuated octarotor, 16384 envs
+        cfg4 = run_hp2_config(dev, world, rank, label="BASELINE configs[3]: 64x512 LiDAR range+seg (OSDome-64), 44 boxes per env",
+                              metric="LiDAR rays/sec (64x512 range+seg, 44-box scene)", E=args.cfg4_envs, K=44, cfg=_LidarCfg,
+                              frames=5, extent=6.0, seed=13, cpu_sample_envs=2)
+        cfg4["dynamics"] = run_hp1_physics(dev, world, rank, robot="base_octarotor", controller=args.cfg4_controller,
+                                           N=args.cfg4_envs, substeps=10, steps=20)
+        # BASELINE.json configs[4]: env-count sweep of the dynamics + controller step
+        sweep = run_hp1_sweep(dev, world, rank, args, [1024, 4096, 16384, 65536, 262144, 1048576])
+        nav = run_nav_task(dev, world, rank, args)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -490,6 +507,7 @@ def run_ours(args):
             "value_hot_l2": value_hot,
             "value_obs_gather_sync": value_sync,
             "obs_gather_check": gather_check,
+            "obs_gather_throttled_steps": (gather.throttled if gather is not None else None),
             "wall_s_timed_region": t_wall,
             "host_enqueue_us_per_step": 1e6 * t_enqueue / K,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,true> (the whole fused step is this one launch)", "achieved": achieved, "peak": peak,
@@ -511,6 +529,10 @@ def run_ours(args):
             "gpu_launches": K,
             "clocks": clocks,
             "hp2_depth": hp2,
+            "config3_depth_270x480_1024box": cfg3,
+            "config4_lidar_64x512_octarotor": cfg4,
+            "config5_env_sweep": sweep,
+            "navigation_task_e2e": nav,
         }
         print(json.dumps(line))
     if world > 1:
@@ -518,45 +540,92 @@ def run_ours(args):
     return 0
 
 
-def run_hp2_depth(dev, world, rank, args):
-    """Second headline of BASELINE.json: depth rays/sec, 64x48 depth+segmentation camera, 8192 envs
-    per GPU, 44-box scenes (the shipped env_with_obstacles count).  Synthetic randomly posed boxes;
-    the 8192 scenes (~240 MB) exceed L2, so no flush is needed between frames."""
+class _CamCfg:
+    """BaseDepthCameraConfig (config/sensor_config/camera_config/base_depth_camera_config.py:16-52): depth + segmentation, normalised"""
+    sensor_type, num_sensors, height, width = "camera", 1, 48, 64
+    horizontal_fov_deg, max_range, min_range = 87.0, 10.0, 0.2
+    calculate_depth, return_pointcloud, pointcloud_in_world_frame = True, False, False
+    segmentation_camera, normalize_range = True, True
+    far_out_of_range_value, near_out_of_range_value = 10.0, -10.0
+    euler_frame_rot_deg = [-90.0, 0, -90.0]
+
+
+class _LidarCfg:
+    """OSDome_64_Config (config/sensor_config/lidar_config/osdome_64_config.py:4-32): 64 x 512, az +-180, el 0..90, range + segmentation"""
+    sensor_type, num_sensors, height, width = "lidar", 1, 64, 512
+    horizontal_fov_deg_min, horizontal_fov_deg_max, vertical_fov_deg_min, vertical_fov_deg_max = -180, 180, 0, 90
+    max_range, min_range = 20.0, 0.5
+    return_pointcloud, pointcloud_in_world_frame, segmentation_camera, normalize_range = False, False, True, True
+    far_out_of_range_value, near_out_of_range_value = 20.0, -20.0
+    euler_frame_rot_deg = [0.0, 0.0, 0.0]
+
+
+def _peak_hbm():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def cpu_ray_baseline(sensor, scene_np, robot_np, sample_envs):
+    """rays/s of the oracle's brute-force closest hit (oracle/hp2_oracle.c, one thread) on `sample_envs` envs of the same scene
+    and sensor -- a `port`: the reference's own ray query is Warp's BVH (warp-lang 1.0.0, not installable here)"""
+    import numpy as np
+
+    from oracle import hp2_oracle as RO
+
+    E = sample_envs
+    offs = np.arange(0, 12 * (len(scene_np["templates"]) + 1), 12, dtype=np.int32)
+    nt = 12 * len(scene_np["templates"])
+    tris, segs, cnt = RO.build_world_tris(scene_np["pose"][:E, :, :7], scene_np["tm"][:E], scene_np["ctr"][:E], offs,
+                                          np.concatenate(scene_np["templates"]), np.zeros(nt, np.int32), np.ones(nt, np.int32),
+                                          scene_np["tm"].shape[1] * 12)
+    so = RO.Hp2oSensor()
+    for f, _ in RO.Hp2oSensor._fields_:
+        if hasattr(sensor.c, f):
+            setattr(so, f, getattr(sensor.c, f))
+    mount = np.zeros((E, 1, 7), np.float32)
+    mount[..., 6] = 1
+    table = sensor.ray_table.cpu().numpy() if getattr(sensor, "ray_table", None) is not None else None
+    t0 = time.perf_counter()
+    RO.cast(so, robot_np[:E, :7], mount, table, tris, segs, cnt)
+    dt = time.perf_counter() - t0
+    rays = E * sensor.c.height * sensor.c.width
+    return {"value": rays / dt, "unit": "rays/s", "cores": 1, "kind": "port",
+            "sample": f"{E} env(s) x {sensor.c.height}x{sensor.c.width} rays against {int(cnt[0])} triangles, brute-force closest hit "
+                      f"(oracle/hp2_oracle.c, 1 thread, {dt:.2f} s); the reference's Warp BVH query is not installable"}
+
+
+def run_hp2_config(dev, world, rank, *, label, metric, E, K, cfg, frames, extent, seed, cpu_sample_envs=0):
+    """rays/sec of the ray-caster on one BASELINE.json sensor config: E envs per GPU, K randomly posed boxes per env (12 triangles
+    each), one sensor per env.  Synthetic scenes; the E scenes together exceed L2, so no flush is needed between frames."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from aerial_gym_simulator_b200.hp2 import RayScene, RaySensor, box_obb, box_triangles
 
-    E, K, H, W = args.hp2_envs, 44, 48, 64
-    g = torch.Generator().manual_seed(7 + rank)
+    H, W = cfg.height, cfg.width
+    g = torch.Generator().manual_seed(seed + rank)
     sizes = torch.rand(5, 3, generator=g) * 1.2 + 0.15
-    templates = [box_triangles(s.tolist()) for s in sizes]
+    templates = [box_triangles(s_.tolist()) for s_ in sizes]
     pose = torch.zeros(E, K, 13)
-    pose[..., 0:3] = (torch.rand(E, K, 3, generator=g) * 2 - 1) * 5.0
+    pose[..., 0:3] = (torch.rand(E, K, 3, generator=g) * 2 - 1) * extent
     q = torch.randn(E, K, 4, generator=g)
     pose[..., 3:7] = q / q.norm(dim=-1, keepdim=True)
     tm = torch.randint(0, 5, (E, K), generator=g).numpy()
-    ctr = (100 + torch.arange(E * K).reshape(E, K)).numpy()
+    ctr = (100 + torch.arange(E * K).reshape(E, K) % 100000).numpy()
     scene = RayScene(templates, [0] * 5, [1] * 5, tm, ctr, pose.to(dev), dev,
-                     tmpl_obb=np.stack([box_obb(s.tolist()) for s in sizes]))
-
-    class cam:
-        sensor_type, num_sensors, height, width = "camera", 1, H, W
-        horizontal_fov_deg, max_range, min_range = 87.0, 10.0, 0.2
-        calculate_depth, return_pointcloud, pointcloud_in_world_frame = True, False, False
-        segmentation_camera, normalize_range = True, True
-        far_out_of_range_value, near_out_of_range_value = 10.0, -10.0
-        euler_frame_rot_deg = [-90.0, 0, -90.0]
-
+                     tmpl_obb=np.stack([box_obb(s_.tolist()) for s_ in sizes]))
     robot = torch.zeros(E, 13)
-    robot[:, 0:3] = (torch.rand(E, 3, generator=g) * 2 - 1) * 4.0
+    robot[:, 0:3] = (torch.rand(E, 3, generator=g) * 2 - 1) * (extent * 0.8)
     rq = torch.randn(E, 4, generator=g)
     robot[:, 3:7] = rq / rq.norm(dim=-1, keepdim=True)
     robot_d = robot.to(dev)
     pix = torch.zeros(E, 1, H, W, device=dev)
     seg = torch.zeros(E, 1, H, W, dtype=torch.int32, device=dev)
-    sensor = RaySensor(cam, scene, robot_d, pix, seg)
+    sensor = RaySensor(cfg, scene, robot_d, pix, seg)
     stream = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -564,8 +633,7 @@ def run_hp2_depth(dev, world, rank, args):
     e1.record(stream)
     torch.cuda.synchronize(dev)
     build_ms = e0.elapsed_time(e1)
-    frames = max(5, min(args.steps, 50))
-    for _ in range(3):
+    for _ in range(3 if frames > 3 else 1):
         sensor.capture()
     if world > 1:
         dist.barrier()
@@ -585,14 +653,189 @@ def run_hp2_depth(dev, world, rank, args):
     hit_frac = float((seg >= 0).float().mean())
     out_bytes = rays * 8
     scene_bytes = E * (K * 12 * 48 + (2 * scene.P - 1) * 32 + max(scene.P, 4) * 4)
-    return {
-        "metric": "depth rays/sec (64x48 depth+seg camera, 44-box scene)", "value": world * rays * frames / sec,
-        "unit": "rays/s", "envs_per_gpu": E, "frames": frames, "ms_per_frame": sec * 1e3 / frames, "hit_fraction": hit_frac,
-        "scene_update_ms_all_envs": build_ms, "gpu_launches": frames,
-        "roofline": {"bound": "hbm (nominal; FP32 traversal binds)", "achieved": (out_bytes + scene_bytes) * frames / sec / 1e9,
-                     "unit": "GB/s", "algorithmic_bytes_per_frame": out_bytes + scene_bytes,
-                     "note": "8 B/ray written + every env's scene (slabs+BVH) staged once per frame"},
+    peak, peak_src = _peak_hbm()
+    achieved = (out_bytes + scene_bytes) * frames / sec / 1e9
+    cpu = None
+    if cpu_sample_envs and rank == 0 and world == 1:
+        cpu = cpu_ray_baseline(sensor, {"templates": templates, "pose": pose.numpy(), "tm": tm, "ctr": ctr}, robot.numpy(), cpu_sample_envs)
+    res = {
+        "metric": metric, "value": world * rays * frames / sec, "unit": "rays/s", "workload": label, "envs_per_gpu": E, "image": [H, W],
+        "objects_per_env": K, "triangles_per_env": K * 12, "frames": frames, "ms_per_frame": sec * 1e3 / frames, "hit_fraction": hit_frac,
+        "scene_update_ms_all_envs": build_ms, "gpu_launches": frames, "n_gpus": world, "scaling": "weak",
+        "traversal": "tile path (scene staged into shared memory by TMA bulk copies)" if scene.P <= 128 else "per-ray BVH traversal from L2 (scene larger than shared memory)",
+        "roofline": {"bound": "hbm (nominal: FP32 traversal / intersection issue binds, see DESIGN 6)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_frame": out_bytes + scene_bytes,
+                     "note": "8 B/ray written (depth or range + segmentation) + every env's scene (48-byte triangle slabs + BVH) read once per frame"},
+        "cpu_baseline": cpu,
     }
+    del sensor, scene, pix, seg
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_hp1_physics(dev, world, rank, *, robot, controller, N, substeps, steps):
+    """env-steps/sec of the HP1 physics launch alone (agx_hp1_physics_step, `substeps` fused physics steps per env step) for a robot /
+    controller pair from the registry -- the dynamics side of BASELINE config #4 (fully-actuated octarotor, 16,384 envs)"""
+    import torch
+    import torch.distributed as dist
+
+    import aerial_gym_simulator_b200.robots  # noqa: F401
+    from aerial_gym_simulator_b200.config.env_config import EmptyEnvCfg
+    from aerial_gym_simulator_b200.config.sim_config import BaseSimConfig
+    from aerial_gym_simulator_b200.hp1 import Hp1Engine
+    from aerial_gym_simulator_b200.registry._core import robot_registry
+
+    rb, _ = robot_registry.make_robot(robot, controller, EmptyEnvCfg, "cpu")
+    spec = rb.make_spec(BaseSimConfig, EmptyEnvCfg)
+    eng = Hp1Engine(spec, N, dev, seed=5, env_id_offset=rank * N, materialize_derived=True)
+    eng.reset(torch.ones(N, dtype=torch.bool, device=dev))
+    eng.refresh()
+    g = torch.Generator(device=dev).manual_seed(9 + rank)
+    acts = (torch.rand(N, spec.num_actions, generator=g, device=dev) * 2 - 1).contiguous()
+    if spec.num_actions == 7:  # pose command: position + unit quaternion
+        acts[:, 3:7] = torch.nn.functional.normalize(acts[:, 3:7], dim=1)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(5):
+        eng.physics_step(acts, physics_steps=substeps)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        eng.physics_step(acts, physics_steps=substeps)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) * 1e-3
+    assert torch.isfinite(eng.root_state).all()
+    return {"metric": f"env-steps/sec ({robot} + {controller}, {substeps} physics sub-steps per env step, physics launch only)",
+            "value": world * N * steps / sec, "unit": "env-steps/s", "envs_per_gpu": N, "ms_per_env_step": sec * 1e3 / steps,
+            "physics_substeps_per_s": world * N * steps * substeps / sec, "gpu_launches": steps, "num_motors": spec.num_motors}
+
+
+def run_hp1_sweep(dev, world, rank, args, sizes):
+    """BASELINE config #5: env-count sweep of the fused position-task step (dynamics + controller + task epilogue), N > 1 with the
+    observation all-gather.  Per size: one replica set sized to exceed L2 (or 2 replicas at the large sizes), K steps."""
+    import torch
+    import torch.distributed as dist
+
+    from aerial_gym_simulator_b200.distributed import ObsAllGather, PipelinedObsGather
+    from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
+
+    peak, _ = _peak_hbm()
+    out = []
+    for N in sizes:
+        R = max(2, min(16, (160 << 20) // (N * 190)))  # ~190 B of state / outputs per env: replicas until the set exceeds L2
+        K = max(20, min(args.steps, 200))
+        engines = []
+        for rep in range(R):
+            e = Hp1Engine(MultirotorSpec(), N, dev, seed=1 + rep, env_id_offset=rank * N, materialize_derived=False)
+            e.reset(torch.ones(N, dtype=torch.bool, device=dev))
+            e.refresh()
+            e.sim_steps.copy_((torch.arange(N, device=dev) % 500).int())
+            engines.append(e)
+        chained = bool(engines[0].lib.agx_hp1_task_step_is_chained(engines[0]._cfg_ref, engines[0]._buf_ref))
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        acts = [(torch.rand(N, 4, generator=g, device=dev) * 2 - 1).contiguous() for _ in range(4)]
+        gather, nccl = None, None
+        if world > 1:
+            if args.gather != "nccl" and (N * 52) % 16 == 0:
+                gather = PipelinedObsGather(N, 13, dev, num_buffers=4, max_ctas=args.gather_ctas)
+                for e in engines:
+                    e.attach_obs_gather(gather)
+            else:
+                nccl = ObsAllGather(N, 13, world * N, dev)
+        stream = torch.cuda.current_stream(dev)
+
+        def loop(n):
+            for i in range(n):
+                e = engines[i % R]
+                e.position_task_step(acts[i % 4])
+                if nccl is not None:
+                    nccl(e.obs)
+            if gather is not None:
+                gather.fence()
+                gather.wait()
+
+        loop(max(R, 5))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        loop(K)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item()) * 1e-3
+        if gather is not None:
+            gather.check()
+        engines[0].check()
+        val = world * N * K / sec
+        out.append({"envs_per_gpu": N, "global_envs": N * world, "value": val, "unit": "env-steps/s", "us_per_step": sec * 1e6 / K, "steps": K,
+                    "replicas": R, "path": "single launch, chained per tile" if chained else "two launches (grid larger than one resident wave)",
+                    "roofline_frac": ALG_BYTES_PER_ENV_STEP * N * K / sec / 1e9 / peak,
+                    "nvlink_floor_us": ((world - 1) * N * 52 / 900e9 * 1e6) if world > 1 else None})
+        for e in engines:
+            if gather is not None:
+                e.attach_obs_gather(None)
+        del engines, gather, nccl
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_nav_task(dev, world, rank, args):
+    """navigation_task end to end through the task API at its shipped configuration (config/task_config/navigation_task_config.py:
+    lmf2 + lmf2_velocity_control, env_with_obstacles = 44 boxes, 135x240 depth camera, VAE latents, 10 physics sub-steps per env
+    step) -- env-steps/s of task.step(actions) with device-resident actions."""
+    import torch
+    import torch.distributed as dist
+
+    import aerial_gym_simulator_b200.task  # noqa: F401
+    from aerial_gym_simulator_b200.registry.task_registry import task_registry
+
+    N = args.nav_envs
+    tcfg = task_registry.get_task_config("navigation_task")
+    old = (tcfg.args, tcfg.device) if hasattr(tcfg, "args") else (None, tcfg.device)
+    try:
+        tcfg.device = str(dev)
+        t0 = time.perf_counter()
+        task = task_registry.make_task("navigation_task", seed=3 + rank, num_envs=N, headless=True)
+        build_s = time.perf_counter() - t0
+    finally:
+        tcfg.device = old[1]
+    task.reset()
+    A = task.task_config.action_space_dim
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    acts = [(torch.rand(N, A, generator=g, device=dev) * 2 - 1) for _ in range(4)]
+    K = max(10, min(args.steps, 50))
+    for i in range(5):
+        task.step(acts[i % 4])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(K):
+        task.step(acts[i % 4])
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    env = task.sim_env
+    rays = N * env.sensor.c.height * env.sensor.c.width if getattr(env, "sensor", None) is not None else 0
+    res = {"metric": "env-steps/sec (navigation_task: lmf2, env_with_obstacles, 135x240 depth camera + VAE, 10 physics sub-steps)",
+           "value": world * N * K / sec, "unit": "env-steps/s", "envs_per_gpu": N, "ms_per_env_step": sec * 1e3 / K, "steps": K,
+           "rays_per_s_inside": world * rays * K / sec, "construction_s": build_s,
+           "step_mode": getattr(env, "step_mode", "launch per kernel"), "timing": "host wall clock around K x task.step, synchronised"}
+    task.close()
+    return res
 
 
 def main():
@@ -607,9 +850,14 @@ def main():
                     help="N>1 observation all-gather: hand-written NVLink push / wait kernels beside the chained steps, the push of "
                          "step t overlapping step t+1 (default; actions are pre-generated, as at N=1); the same kernels awaited "
                          "after every step; or NCCL's all_gather_into_tensor after every step")
-    ap.add_argument("--gather-ctas", type=int, default=64, help="CTAs of the push kernel (it shares the GPU with the step kernel)")
+    ap.add_argument("--gather-ctas", type=int, default=24, help="CTAs of the push kernel (it shares the GPU with the step kernel)")
     ap.add_argument("--no-hp2", action="store_true", help="skip the secondary depth rays/sec measurement")
     ap.add_argument("--hp2-envs", type=int, default=8192)
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] sub-lines and the navigation_task line")
+    ap.add_argument("--cfg3-envs", type=int, default=8192)
+    ap.add_argument("--cfg4-envs", type=int, default=16384)
+    ap.add_argument("--cfg4-controller", default="rov_fully_actuated_control", help="7-D pose command, FullyActuatedController")
+    ap.add_argument("--nav-envs", type=int, default=1024)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -134,12 +134,6 @@ typedef struct AgxHp1Buffers {
     uint32_t* tile_sync;      /* [2][ceil(N/32)] device scratch, zero-initialised once: per-tile claim / done counters that
                                  chain consecutive single-launch steps tile by tile (hp1.cu "chained steps").
                                  NULL = the step always takes the two-launch path. */
-    /* multi-GPU (NULL = off): back-pressure from the observation all-gather that runs BESIDE the chained steps
-     * (agx_obs_gather_push on a side stream reads `obs` asynchronously).  `obs` is then one slot of a ring of observation
-     * buffers chosen by the caller per step, and the step may write it only once *gather_consumed >= gather_need, i.e. once
-     * the push that last read this slot has finished reading.  The step kernel itself never touches NVLink. */
-    const unsigned long long* gather_consumed; /* device u64, bumped by agx_obs_gather_push */
-    uint64_t gather_need;
 } AgxHp1Buffers;
 
 /* explicit uniform draws u in [0,1) for agx_hp1_reset, in the reference's call order */
@@ -196,7 +190,9 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
  * 32-env tile (all CTAs of a step co-resident; device-RNG reset + strict stale observation + tile_sync given), 0 when it takes
  * the two-launch path, negative on error.  Step T (0-based count of such launches since tile_sync / any_reset were zeroed) is
  * complete -- observation included -- when the u64 at any_reset + 8 + 2 * (T & 3) has reached (T / 4 + 1) * ceil(N / 32):
- * that is the (ready_ctr, ready_target) pair agx_obs_gather_push waits on. */
+ * that is the (ready_ctr, ready_target) pair agx_obs_gather_push waits on.  (Multi-GPU: the step kernel itself never
+ * touches NVLink and never waits for the gather; `obs` is then one slot of a ring of observation buffers the caller rotates and
+ * throttles with stream events, see agx_obs_gather_push.) */
 int agx_hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* buf);
 /* Bound of every in-kernel wait (chained steps, observation gather), wall clock; default 20 s.  On expiry a kernel records an
  * error word and goes on (no trap, the context survives); the next agx_hp1_check / agx_obs_gather_check returns AGX_E_TIMEOUT. */
@@ -501,13 +497,15 @@ int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const
  * agx_obs_gather_push: optionally spin until *ready_ctr >= ready_target (the step that produces `local` has published it: see
  * agx_hp1_task_step_is_chained; NULL = `local` is already complete in stream order), copy the `bytes` (multiple of 16) of `local`
  * into slot `rank` of every rank's gathered buffer (peer_bufs[p] + rank * bytes; the own slot is skipped when `local` already is
- * that slot), bump *consumed (if given) once `local` has been read, then -- when all stores of this rank have been performed at
- * system scope -- publish `epoch` into peer_flags[p][rank] on every rank p.  The kernel never waits for a peer.
+ * that slot), then -- when all stores of this rank have been performed at system scope -- publish `epoch` into flag word
+ * peer_flags[p][flag_slot * AGX_MAX_PEERS + rank] on every rank p.  The kernel never waits for a peer.  Pushes into different ring
+ * slots may run concurrently (one stream and one scratch block per slot); re-use of a slot is ordered by the caller (an event
+ * recorded behind the push, awaited by the stream that next writes `local`).
  *   peer_bufs / peer_flags : DEVICE arrays of `world` device pointers (symmetric-memory rendezvous)
- *   scratch                : device uint32[4], zero-initialised once
+ *   scratch                : device uint32[4] of this ring slot, zero-initialised once
  *   error_word             : device uint32, zero-initialised once (agx_obs_gather_check)
  *   epoch                  : strictly increasing per push, starting at 1
- *   max_ctas               : upper bound of the grid (0 = default 64): the push shares the GPU with the chained step */
+ *   max_ctas               : upper bound of the grid (0 = default 24): the pushes share the GPU with the chained step */
 typedef struct AgxObsGatherPush {
     const void* local;
     void* const* peer_bufs;
@@ -518,14 +516,16 @@ typedef struct AgxObsGatherPush {
     int32_t max_ctas;
     const unsigned long long* ready_ctr;
     uint64_t ready_target;
-    unsigned long long* consumed;
     uint32_t* scratch;
     uint32_t* error_word;
+    int32_t flag_slot;
+    int32_t pad_;
 } AgxObsGatherPush;
 int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream);
-/* Receiver side: one tiny kernel that retires when my_flags[q] >= epoch for every rank q < world (wrap-safe compare), i.e.
- * when every rank's rows of `epoch` have landed in this rank's gathered buffer; work queued behind it on `stream` may read it. */
-int agx_obs_gather_wait(const uint32_t* my_flags, int world, uint32_t epoch, uint32_t* error_word, void* stream);
+/* Receiver side: one tiny kernel that retires when my_flags[flag_slot * AGX_MAX_PEERS + q] >= epoch for every rank q < world
+ * (wrap-safe compare), i.e. when every rank's rows of `epoch` have landed in this rank's gathered buffer of that ring slot; work
+ * queued behind it on `stream` may read it. */
+int agx_obs_gather_wait(const uint32_t* my_flags, int flag_slot, int world, uint32_t epoch, uint32_t* error_word, void* stream);
 /* Synchronises `stream`; AGX_E_TIMEOUT if a push / wait gave up (bounded by agx_set_spin_timeout_ms). */
 int agx_obs_gather_check(const uint32_t* error_word, void* stream);
 int agx_obs_gather_set_timeout_ns(uint64_t ns);

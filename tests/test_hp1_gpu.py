@@ -381,7 +381,7 @@ def test_pipelined_obs_gather_loopback(n, two_launch):
     """The observation all-gather beside the chained steps, on ONE GPU with an emulated world of 3 (every "peer" buffer is a local
     tensor): the step writes its rows into the ring slot, the push kernel (side stream, waiting on the step's completion counter in
     device memory -- or in stream order on the two-launch path) copies them into every peer's buffer and publishes the epoch;
-    ring back-pressure lets at most `num_buffers` steps run ahead.  Results equal those of an engine without a gather, bit for bit."""
+    a step waits (stream event) only for the push that last read its ring slot.  Results equal those of an engine without a gather, bit for bit."""
     from aerial_gym_simulator_b200.distributed import PipelinedObsGather
 
     spec = H.spec_for("quad_attitude")
@@ -410,8 +410,9 @@ def test_pipelined_obs_gather_loopback(n, two_launch):
         assert torch.equal(got[:n], ref.obs)
         for peer in (1, 2):  # rank 0's rows landed in slot 0 of every peer's buffer
             assert torch.equal(gth.peer_outs[(step + 1) % 4][peer][:n], ref.obs), f"step {step} peer {peer}"
-        assert gth.flags[0].item() == step + 1 and gth.peer_flags[1][0].item() == step + 1 and gth.peer_flags[2][0].item() == step + 1
-        assert gth.scratch[:2].tolist() == [0, 0] and gth.consumed.item() == step + 1
+        fw = ((step + 1) % 4) * 16  # flag words of this epoch's ring slot
+        assert gth.flags[fw].item() == step + 1 and gth.peer_flags[1][fw].item() == step + 1 and gth.peer_flags[2][fw].item() == step + 1
+        assert gth.scratch.sum().item() == 0
     # (2) free running: 40 steps enqueued back to back, pushes overlap the following steps, the ring throttles
     for step in range(40):
         ref.position_task_step(act, mid_event=mid)
@@ -422,7 +423,7 @@ def test_pipelined_obs_gather_loopback(n, two_launch):
     eng.check()
     assert torch.equal(got[:n], ref.obs) and torch.equal(eng.root_state, ref.root_state)
     assert torch.equal(gth.peer_outs[gth.epoch % 4][2][:n], ref.obs)
-    assert gth.consumed.item() == 46 and gth.flags[0].item() == 46
+    assert gth.flags[(46 % 4) * 16].item() == 46 and gth.flags[(45 % 4) * 16].item() == 45
     # (3) detach: the engine owns its observation buffer again
     eng.attach_obs_gather(None)
     ref.position_task_step(act)
@@ -432,7 +433,7 @@ def test_pipelined_obs_gather_loopback(n, two_launch):
 
 
 def test_chained_step_wait_times_out_instead_of_trapping():
-    """A wait that can never be satisfied (ring back-pressure on a counter nobody bumps) expires by wall clock, the step
+    """A wait that can never be satisfied (a tile whose done-counter is ahead of its claim counter) expires by wall clock, the step
     goes on, agx_hp1_check reports AGX_E_TIMEOUT and the CUDA context survives (no __trap on a late producer)."""
     from aerial_gym_simulator_b200 import _lib
 
@@ -441,10 +442,9 @@ def test_chained_step_wait_times_out_instead_of_trapping():
     n = 2048
     eng = Hp1Engine(spec, n, DEV, seed=1, materialize_derived=False)
     eng.reset(torch.ones(n, dtype=torch.bool, device=DEV))
-    never = torch.zeros(1, dtype=torch.int64, device=DEV)
     _lib.check(lib.agx_set_spin_timeout_ms(50), "agx_set_spin_timeout_ms")
     try:
-        eng._buf.gather_consumed, eng._buf.gather_need = never.data_ptr(), 1
+        eng.tile_sync[n // 32 + 5] = 7  # tile 5 "has published step 7": its step-0 warp waits for a done-counter of 0 that never comes
         eng.position_task_step(torch.zeros(n, 4, device=DEV))
         with pytest.raises(_lib.AgxError, match="timed out"):
             eng.check()
