@@ -42,11 +42,12 @@ class AgxHp1Config(C.Structure):
         ("tau_inc_range", f32 * 2), ("tau_dec_range", f32 * 2), ("k_thrust_range", f32 * 2),
         ("K_pos_min", f32 * 3), ("K_pos_max", f32 * 3), ("K_vel_min", f32 * 3), ("K_vel_max", f32 * 3),
         ("K_rot_min", f32 * 3), ("K_rot_max", f32 * 3), ("K_angvel_min", f32 * 3), ("K_angvel_max", f32 * 3),
+        ("dist_prob", f32), ("dist_max", f32 * 6), ("dist_pad_", C.c_uint32), ("dist_seed", C.c_uint64),
     ]
 
 
 _HP1_BUF_FIELDS = [
-    "root_state", "motor_thrust", "sim_steps", "actions", "disturbance", "target_position",
+    "root_state", "motor_thrust", "sim_steps", "actions", "disturbance", "dist_counter", "dist_offset_", "target_position",
     "tau_inc", "tau_dec", "k_thrust", "K_pos", "K_vel", "K_rot", "K_angvel", "bounds_min", "bounds_max",
     "euler", "vehicle_orientation", "vehicle_linvel", "body_linvel", "body_angvel", "body_wrench",
     "obs", "reward", "terminations", "truncations", "reset_mask", "any_reset", "episode_count", "fresh_vel", "tile_sync",
@@ -54,7 +55,16 @@ _HP1_BUF_FIELDS = [
 
 
 class AgxHp1Buffers(C.Structure):
-    _fields_ = [(n, fp) for n in _HP1_BUF_FIELDS]
+    # dist_offset_: the uint32 pair (dist_offset, pad) travels as one 8-byte slot; the `dist_offset` property reads / writes its low word
+    _fields_ = [(n, (C.c_uint64 if n == "dist_offset_" else fp)) for n in _HP1_BUF_FIELDS]
+
+    @property
+    def dist_offset(self):
+        return self.dist_offset_ & 0xFFFFFFFF
+
+    @dist_offset.setter
+    def dist_offset(self, v):
+        self.dist_offset_ = int(v) & 0xFFFFFFFF
 
 
 class AgxObsGatherPush(C.Structure):
@@ -167,6 +177,7 @@ def load():
         "agx_obs_gather_set_timeout_ns": [C.c_uint64],
         "agx_set_spin_timeout_ms": [C.c_uint64],
         "agx_hp1_check": [C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_counter_add": [C.c_void_p, C.c_uint32, C.c_void_p],
         "agx_hp1_task_step_is_chained": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers)],
         "agx_nav_reward": [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                            C.POINTER(AgxNavRewardParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -18,6 +18,7 @@
 #include "agx_common.cuh"
 #include "agx_math.cuh"
 #include "hp1_core.cuh"
+#include "disturbance_core.cuh"
 
 using namespace agx;
 
@@ -66,8 +67,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // run, not a poisoned CUDA context.  agx_set_spin_timeout_ms() changes the bound (default 20 s).
 __device__ unsigned long long g_hp1_spin_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
 constexpr int kErrWord = 2;  // index into any_reset[]
+// error word = code | step << 4: 1 = the tile's previous step never published, 2 = step T-2 never completed, 3 = the reset decision
+// never closed (not every warp of the step arrived: the grid was not fully resident)
 template <class Pred>
-__device__ __forceinline__ bool spin_until(Pred ok, int32_t* any_reset) {
+__device__ __forceinline__ bool spin_until(Pred ok, int32_t* any_reset, int code) {
     if (ok()) return true;
     volatile int32_t* err = any_reset + kErrWord;
     if (*err) return false;
@@ -77,7 +80,7 @@ __device__ __forceinline__ bool spin_until(Pred ok, int32_t* any_reset) {
         if ((++polls & 255u) == 0u) {
             if (*err) return false;
             if (globaltimer_ns() - t0 > limit) {
-                atomicExch(any_reset + kErrWord, 1);
+                atomicCAS(any_reset + kErrWord, 0, code);
                 return false;
             }
         }
@@ -253,7 +256,10 @@ AGX_HP1_RESET_FN void reset_one_env(const AgxHp1Config& cfg, const AgxHp1Buffers
 // warps with a resetting env) no longer gates the next step.  A warp also waits until step T-2 is complete
 // everywhere, so at most two consecutive steps are in flight and four parity slots suffice:
 //   any_reset[4 + (T & 3)]        u32 flag of step T: raised = holds T + 1 (monotonic, never cleared)
-//   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared)
+//   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared): "this warp's physics and reset
+//                                 decision are done" -- in the rare no-reset-yet case counted BEFORE the observation is written
+//   any_reset[16 + 2 * (T & 3)]   u64 published tiles of the steps = T mod 4 (cumulative): "this tile's state, observation, reward
+//                                 and flags are in memory" -- what a consumer outside the kernel (agx_obs_gather_push) waits on
 //   tile_sync[tile], tile_sync[n_tiles + tile]   claim / done counters of the tile
 // (3) Multi-GPU: the step kernel never touches NVLink and never waits for the gather.  With an observation all-gather attached
 // (agx_obs_gather_push, p2p_allgather.cu, on side streams) buf.obs is one slot of a ring the push kernels read asynchronously; the
@@ -288,6 +294,7 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     AGX_TL(0);
     uint32_t* reset_flag = reinterpret_cast<uint32_t*>(buf.any_reset);
     unsigned long long* arrive_ctr = nullptr;
+    unsigned long long* publish_ctr = nullptr;
     unsigned long long arrive_target = 0;  // arrivals once every warp of this step has counted itself in
     uint32_t step_T = 0;
     if constexpr (COOP) {
@@ -325,14 +332,15 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
                 if (ready) {
                     __threadfence();  // relaxed reads + fence = acquire
                 } else {
-                    spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset);
-                    if (step_T >= 2u) spin_until([&] { return ld_acquire_gpu_u64(arrivals + (P & 3u)) >= want2; }, buf.any_reset);
+                    spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset, 1 | (int)(step_T << 4));
+                    if (step_T >= 2u) spin_until([&] { return ld_acquire_gpu_u64(arrivals + (P & 3u)) >= want2; }, buf.any_reset, 2 | (int)(step_T << 4));
                 }
             }
             __syncwarp();
         }
         reset_flag = reinterpret_cast<uint32_t*>(buf.any_reset) + 4 + (step_T & 3u);
         arrive_ctr = reinterpret_cast<unsigned long long*>(buf.any_reset + 8) + (step_T & 3u);
+        publish_ctr = reinterpret_cast<unsigned long long*>(buf.any_reset + 16) + (step_T & 3u);
         arrive_target = (unsigned long long)(step_T / 4u + 1u) * (unsigned long long)n_tiles;
     }
     const uint32_t flag_tag = step_T + 1u;
@@ -429,6 +437,12 @@ AGX_HP1_MOTOR_UNROLL
                     const float* dp = buf.disturbance + (size_t)env * 6;
                     df = df + ld3cg(dp);
                     dtq = dtq + ld3cg(dp + 3);
+                } else if (buf.dist_counter) {  // the same draw, in the kernel: counter word from device memory (graph replays)
+                    float d6[6];
+                    disturbance_env((uint32_t)(cfg.env_id_offset + env), *buf.dist_counter + buf.dist_offset + (uint32_t)step, cfg.dist_prob, cfg.dist_max,
+                                    (uint32_t)(cfg.dist_seed & 0xffffffffu), (uint32_t)(cfg.dist_seed >> 32), d6);
+                    df = df + V3{d6[0], d6[1], d6[2]};
+                    dtq = dtq + V3{d6[3], d6[4], d6[5]};
                 }
                 V3 com = ld3c(cfg.com);
                 V3 F{w6[0] + df.x, w6[1] + df.y, w6[2] + df.z};
@@ -516,7 +530,7 @@ AGX_HP1_MOTOR_UNROLL
                     volatile uint32_t* fl = reset_flag;
                     const unsigned long long* cnt = arrive_ctr;
                     // until the flag rises, or every warp of this step has arrived (then the flag is final)
-                    spin_until([&] { return *fl == flag_tag || ld_acquire_gpu_u64(cnt) >= arrive_target; }, buf.any_reset);
+                    spin_until([&] { return *fl == flag_tag || ld_acquire_gpu_u64(cnt) >= arrive_target; }, buf.any_reset, 3 | (int)(step_T << 4));
                     any = (*fl == flag_tag);
                 }
                 // ---- derived states for the observation: one common pass for resetting envs (new state)
@@ -546,6 +560,7 @@ AGX_HP1_MOTOR_UNROLL
                 if (lane == 0) {
                     __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
                     if (!counted) atomicAdd(arrive_ctr, 1ull);
+                    atomicAdd(publish_ctr, 1ull);
                     st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
                 }
             }
@@ -746,6 +761,11 @@ inline int coop_capacity(StepKernel k) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // Kernels that run BESIDE the chained step (the gather's push / wait kernels) must not pin an SM to a smaller shared-memory
+    // carve-out than this kernel's eight 4.3 KB CTAs need: measured (round 2), one push CTA that reached an idle SM first left room
+    // for ~1 step CTA there, 24 of them cost > 160 slots and a step that needs its whole grid resident starved.  Every such
+    // kernel and this one ask for the same (maximum) carve-out.
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
     const int cap = sms * per_sm;
     if (n_seen < 32) { seen[n_seen] = k; caps[n_seen] = cap; ++n_seen; }
@@ -777,6 +797,13 @@ int agx_hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* b
     if (!cfg || !buf) return agx_set_error(AGX_E_NULL, "cfg/buf is NULL");
     if (cfg->num_motors != 4 && cfg->num_motors != 8) return agx_set_error(AGX_E_INVALID, "num_motors must be 4 or 8");
     return hp1_task_step_is_chained(cfg, buf) ? 1 : 0;
+}
+
+__global__ void counter_add_kernel(uint32_t* c, uint32_t n) { *c += n; }
+int agx_counter_add(uint32_t* counter, uint32_t n, void* stream) {
+    if (!counter) return agx_set_error(AGX_E_NULL, "agx_counter_add: NULL counter");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, n);
+    return agx_check_launch("counter_add_kernel");
 }
 
 int agx_set_spin_timeout_ms(uint64_t ms) {

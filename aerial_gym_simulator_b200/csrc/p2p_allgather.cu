@@ -78,8 +78,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
     return v;
 }
 // wall-clock bounded wait; on expiry: error word, no trap (see hp1.cu spin_until)
+// error word: (epoch << 8) | code, code 1 = a push never saw its producer step complete, 2 = a wait never saw a peer's flag
 template <class Pred>
-__device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word) {
+__device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word, uint32_t code) {
     if (ok()) return true;
     volatile uint32_t* err = err_word;
     if (*err) return false;
@@ -89,7 +90,7 @@ __device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word) {
         if ((++polls & 63u) == 0u) {
             if (*err) return false;
             if (globaltimer_ns() - t0 > limit) {
-                atomicExch(err_word, 1u);
+                atomicCAS(err_word, 0u, code);
                 return false;
             }
         }
@@ -120,7 +121,7 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
         if (a.ready_ctr) {
             const unsigned long long* c = a.ready_ctr;
             const unsigned long long want = a.ready_target;
-            spin_until([&] { return ld_acquire_gpu_u64(c) >= want; }, a.error_word);
+            spin_until([&] { return ld_acquire_gpu_u64(c) >= want; }, a.error_word, (a.epoch << 8) | 1u);
         }
     }
     __syncthreads();
@@ -155,7 +156,7 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
 __global__ void __launch_bounds__(32)
 obs_gather_wait_kernel(const uint32_t* __restrict__ my_flags, int world, uint32_t epoch, uint32_t* error_word) {
     const int q = threadIdx.x;
-    if (q < world) spin_until([&] { return (int32_t)(ld_acquire_sys(my_flags + q) - epoch) >= 0; }, error_word);
+    if (q < world) spin_until([&] { return (int32_t)(ld_acquire_sys(my_flags + q) - epoch) >= 0; }, error_word, (epoch << 8) | ((uint32_t)q << 4) | 2u);
     __syncwarp();
     __threadfence_system();
 }
@@ -182,6 +183,12 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
     const int cap = a->max_ctas > 0 ? a->max_ctas : 24;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
+    static bool carve_set = false;
+    if (!carve_set) {  // same shared-memory carve-out as the step kernel it runs beside (hp1.cu coop_capacity)
+        cudaFuncSetAttribute(obs_gather_push_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(obs_gather_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     obs_gather_push_kernel<<<(int)ctas, kPushThreads, 0, (cudaStream_t)stream>>>(*a, n_vec);
     return agx_check_launch("obs_gather_push_kernel");
 }
@@ -189,6 +196,11 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
 extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int flag_slot, int world, uint32_t epoch, uint32_t* error_word, void* stream) {
     if (!my_flags || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_wait: NULL argument");
     if (world < 1 || world > AGX_MAX_PEERS || flag_slot < 0 || flag_slot > 3) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world / flag_slot");
+    static bool carve_set = false;
+    if (!carve_set) {
+        cudaFuncSetAttribute(obs_gather_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     obs_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags + flag_slot * AGX_MAX_PEERS, world, epoch, error_word);
     return agx_check_launch("obs_gather_wait_kernel");
 }
@@ -200,7 +212,9 @@ extern "C" int agx_obs_gather_check(const uint32_t* error_word, void* stream) {
     if (rc) return rc;
     rc = agx_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "agx_obs_gather_check");
     if (rc) return rc;
-    return w ? agx_set_error(AGX_E_TIMEOUT, "observation gather: a wait timed out (a producer step or a peer never arrived)") : AGX_OK;
+    if (!w) return AGX_OK;
+    return (w & 15u) == 1u ? agx_set_error(AGX_E_TIMEOUT, "observation gather: the push of epoch %u never saw its producer step complete (wait timed out)", w >> 8)
+                           : agx_set_error(AGX_E_TIMEOUT, "observation gather: the wait for epoch %u never saw rank %u's flag (wait timed out)", w >> 8, (w >> 4) & 15u);
 }
 
 extern "C" int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const* peer_flags, int world, int rank,

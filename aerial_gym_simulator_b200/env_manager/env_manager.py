@@ -99,7 +99,14 @@ class EnvManager:
             raise ValueError("args['reset_rng'] must be 'device' or 'torch'")
         self.global_tensor_dict = {}
         self.step_counter = 0
+        self._graphs, self._dist_ctr_dev = {}, None
         self._populate()
+        # "graph" (default where it applies): the per-sub-step launches of an env step with obstacles / disturbances replay as one CUDA
+        # graph; "launch": one C-ABI call per kernel, as in round 1.  The torch-order RNG mode draws with torch inside the loop: launches.
+        want = self.env_args.get("step_mode", "graph")
+        if want not in ("graph", "launch"):
+            raise ValueError("args['step_mode'] must be 'graph' or 'launch'")
+        self.step_mode = want if (self.reset_rng == "device" and self.device.type == "cuda") else "launch"
         self.sim_steps = self.engine.sim_steps  # int32 [N] (env_manager.py:78-80)
         # the reference's object graph, as far as its examples / tasks / trainers walk it: env.robot_manager.robot.{cfg, controller,
         # controller_config}, env.IGE_env.num_assets_per_env (robot included, IGE_env_manager.py:269-276)
@@ -442,12 +449,58 @@ class EnvManager:
                                                         self._dist_max, self._dist_seed, self._dist_counter & 0xFFFFFFFF,
                                                         C.c_void_p(self._dist_buf.data_ptr()), stream), "agx_disturbance_draw")
             self._dist_counter += 1
+            if self._dist_ctr_dev is not None:  # the graph path's device-resident copy of the counter follows
+                _lib.check(_lib.load().agx_counter_add(C.c_void_p(self._dist_ctr_dev.data_ptr()), 1, stream), "agx_counter_add")
             return self._dist_buf
         occ = torch.bernoulli(sp.prob_apply_disturbance * torch.ones(N, device=dev))
         mx = torch.tensor(sp.max_disturbance, dtype=torch.float32, device=dev).expand(N, -1)
         f = _lerp(-mx[:, 0:3], mx[:, 0:3], torch.rand(N, 3, device=dev)) * occ.unsqueeze(1)
         t = _lerp(-mx[:, 3:6], mx[:, 3:6], torch.rand(N, 3, device=dev)) * occ.unsqueeze(1)
         return torch.cat([f, t], dim=1).contiguous()
+
+    def _graph_for(self, n):
+        """CUDA graph of the n physics sub-steps of one env step (captured once per n): per sub-step ONE physics launch that draws its
+        disturbance in the kernel (AgxHp1Buffers.dist_counter: the draw counter lives in device memory, so a replay draws afresh) and
+        ONE collision launch, then one single-thread kernel that advances the draw counter.  Same kernels, same arithmetic, same
+        draws as the launch-by-launch loop (tests: bit-identical trajectories); every C-ABI call is capture-safe (no allocation, no
+        synchronisation).  Navigation-type envs run 10 sub-steps per env step (config/env_config/env_with_obstacles.py:29-30):
+        ~30 launches become one."""
+        g = self._graphs.get(n)
+        if g is not None:
+            return g
+        eng, a = self.engine, self.global_tensor_dict["robot_actions"]
+        dist = self.spec.enable_disturbance
+        if dist and self._dist_ctr_dev is None:
+            self._draw_disturbance()  # creates the stream state (seed, counters); the draw itself is discarded ...
+            self._dist_counter -= 1   # ... and not counted
+            self._dist_ctr_dev = torch.tensor([self._dist_counter & 0xFFFFFFFF], dtype=torch.int32, device=self.device)
+        lib = _lib.load()
+
+        def body():
+            for i in range(n):
+                eng.physics_step(a, physics_steps=1, dist_counter=self._dist_ctr_dev if dist else None, dist_offset=i)
+                self.compute_observations()
+            if dist and n:
+                _lib.check(lib.agx_counter_add(C.c_void_p(self._dist_ctr_dev.data_ptr()), n,
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "agx_counter_add")
+
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up outside the capture (first launches may load modules), on throw-away copies of the state
+            keep = (eng.root_state.clone(), eng.motor_thrust.clone(), self.collision_tensor.clone(),
+                    None if not dist else self._dist_ctr_dev.clone())
+            body()
+            eng.root_state.copy_(keep[0]); eng.motor_thrust.copy_(keep[1]); self.collision_tensor.copy_(keep[2])
+            if dist:
+                self._dist_ctr_dev.copy_(keep[3])
+        cur.wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()
+        # capturing does not execute: the state is untouched, the caller replays
+        self._graphs[n] = g
+        return g
 
     def sample_physics_steps(self):
         e = self.cfg.env
@@ -470,11 +523,15 @@ class EnvManager:
         gtd["robot_actions"][:] = actions
         a = gtd["robot_actions"]
         if self.spec.enable_disturbance or self.scene is not None:
-            # per-physics-step launches: fresh disturbance draws and a collision check after every
-            # physics step, like the reference loop (env_manager.py:426-428)
-            for _ in range(n):
-                self.engine.physics_step(a, disturbance=self._draw_disturbance(), physics_steps=1)
-                self.compute_observations()
+            # the reference loop (env_manager.py:426-428): fresh disturbance draws and a collision check after EVERY physics step
+            if self.step_mode == "graph":
+                self._graph_for(n).replay()  # the n x (physics launch with in-kernel draw, collision launch) of this env step: one graph launch
+                if self.spec.enable_disturbance:
+                    self._dist_counter += n
+            else:
+                for i in range(n):
+                    self.engine.physics_step(a, disturbance=self._draw_disturbance(), physics_steps=1)
+                    self.compute_observations()
         elif n > 0:
             self.engine.physics_step(a, physics_steps=n)  # n sub-steps fused in one launch
         if env_actions is not None and self.num_obs_in_env > 1 and n > 0:  # ObstacleManager.pre_physics_step, obstacle_manager.py:40-44

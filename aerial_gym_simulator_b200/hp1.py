@@ -168,6 +168,9 @@ def build_config(spec: MultirotorSpec, num_envs: int, *, physics_steps=1, episod
     _set(c.K_angvel, mid((f32a(spec.K_angvel_range[0]), f32a(spec.K_angvel_range[1]))))
     c.tau_inc, c.tau_dec, c.k_thrust = spec.tau_inc_range[0], spec.tau_dec_range[0], spec.k_thrust_range[0]
     c.crash_distance = crash_distance
+    c.dist_prob = float(spec.prob_apply_disturbance)
+    _set(c.dist_max, spec.max_disturbance)
+    c.dist_seed = (int(seed) ^ 0xD157_0000_D157) & 0xFFFFFFFFFFFFFFFF  # the stream EnvManager._draw_disturbance uses for agx_disturbance_draw
     _set(c.min_init_state, spec.min_init_state); _set(c.max_init_state, spec.max_init_state)
     _set(c.bounds_lo_min, spec.bounds_lower_range[0]); _set(c.bounds_lo_max, spec.bounds_lower_range[1])
     _set(c.bounds_hi_min, spec.bounds_upper_range[0]); _set(c.bounds_hi_max, spec.bounds_upper_range[1])
@@ -227,7 +230,7 @@ class Hp1Engine:
             self.terminations = z(N, dt=torch.bool)
             self.truncations = z(N, dt=torch.bool)
         self.reset_mask = z(N, dt=torch.bool)
-        self.any_reset = z(16, dt=torch.int32)
+        self.any_reset = z(32, dt=torch.int32)
         self.tile_sync = z(2 * ((N + 31) // 32), dt=torch.int32)  # per-tile claim / done counters (chained steps)
         self.episode_count = z(N, dt=torch.int32)
         self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
@@ -290,7 +293,7 @@ class Hp1Engine:
     def _sync_buffers(self):
         b = self._buf
         for name in _lib._HP1_BUF_FIELDS:
-            if name in ("actions", "disturbance"):
+            if name in ("actions", "disturbance", "dist_counter", "dist_offset_"):
                 continue
             setattr(b, name, self._ptr(getattr(self, name, None)))
 
@@ -314,7 +317,7 @@ class Hp1Engine:
             self.obs, self._buf.obs = self._own_obs, self._own_obs.data_ptr()
         self._gather, self.gathered_obs = gather, None
         if gather is not None:
-            self._ready_base = self.any_reset.data_ptr() + 32  # four u64 arrival counters (hp1.cu)
+            self._ready_base = self.any_reset.data_ptr() + 64  # four u64 published-tile counters (hp1.cu)
             self._n_tiles = (self.N + 31) // 32
 
     def _arm_gather(self, chained):
@@ -367,9 +370,13 @@ class Hp1Engine:
         self._buf.actions = actions.data_ptr()
 
     # ---- C ABI calls ------------------------------------------------------------------------
-    def physics_step(self, actions, disturbance=None, physics_steps=None):
+    def physics_step(self, actions, disturbance=None, physics_steps=None, dist_counter=None, dist_offset=0):
+        """dist_counter: device uint32 tensor -- draw the disturbance inside the kernel (sub-step s uses draw counter
+        *dist_counter + dist_offset + s; AgxHp1Buffers.dist_counter), instead of reading `disturbance` [N,6]"""
         self._check_actions(actions)
         self._buf.disturbance = self._ptr(disturbance)
+        self._buf.dist_counter = None if (dist_counter is None or disturbance is not None) else dist_counter.data_ptr()
+        self._buf.dist_offset = dist_offset
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
         _lib.check(self.lib.agx_hp1_physics_step(self._cfg_ref, self._buf_ref, self._stream()), "agx_hp1_physics_step")
@@ -379,6 +386,7 @@ class Hp1Engine:
         handle exists); the library records it between the main kernel and the refresh pass."""
         self._check_actions(actions)
         self._buf.disturbance = None if disturbance is None else disturbance.data_ptr()
+        self._buf.dist_counter = None
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
         chained = self._chain_counts and mid_event is None  # which path the library takes for this launch

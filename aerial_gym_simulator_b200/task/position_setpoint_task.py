@@ -40,6 +40,11 @@ class PositionSetpointTask(BaseTask):
             raise ValueError("task action_space_dim does not match the controller's action count")
         eng.cfg.episode_len_steps = int(self.task_config.episode_len_steps)
         self.num_envs = env.num_envs
+        # a disturbance-enabled robot in an env with several (or a random number of) physics sub-steps per env step needs a fresh draw
+        # per sub-step: the fused one-launch step cannot do that, the reference-order sequence over EnvManager.step can (decided
+        # here, once, so that no step consumes random.gauss and then fails)
+        e = env.cfg.env
+        self._unfused = bool(env.spec.enable_disturbance and (e.num_physics_steps_per_env_step_mean != 1 or e.num_physics_steps_per_env_step_std != 0))
         self.actions = torch.zeros((self.num_envs, self.task_config.action_space_dim), device=self.device)
         self.prev_actions = torch.zeros_like(self.actions)
         self.counter = 0
@@ -85,16 +90,14 @@ class PositionSetpointTask(BaseTask):
         env, eng = self.sim_env, self.sim_env.engine
         if actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.float().contiguous()
-        if self._overridden("compute_rewards_and_crashes") or self.task_config.return_state_before_reset:
+        if self._overridden("compute_rewards_and_crashes") or self.task_config.return_state_before_reset or self._unfused:
             return self._step_with_reward_hook(actions)  # (the fused step resets inside the launch: nothing to return "before")
         if eng.host_io and actions.device.type == "cpu" and not actions.is_pinned():
             eng.host_actions.copy_(actions)  # pageable host memory: stage through the mapped buffer
             actions = eng.host_actions
         self.prev_actions, self.actions = self.actions, actions  # the reference copies; nobody reads prev afterwards
         n = env.sample_physics_steps()  # consumes random.gauss like env_manager.py:417-425
-        dist = env._draw_disturbance() if (env.spec.enable_disturbance and n == 1) else None
-        if env.spec.enable_disturbance and n != 1:
-            raise NotImplementedError("fused task step with per-substep disturbance draws: use EnvManager.step")
+        dist = env._draw_disturbance() if (env.spec.enable_disturbance and n == 1) else None  # (n != 1 with disturbances: _unfused)
         eng.position_task_step(actions, disturbance=dist, physics_steps=n)
         env.step_counter += 1
         if env.reset_rng == "torch":

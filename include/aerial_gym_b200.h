@@ -88,6 +88,12 @@ typedef struct AgxHp1Config {
     float tau_inc_range[2], tau_dec_range[2], k_thrust_range[2];
     float K_pos_min[3], K_pos_max[3], K_vel_min[3], K_vel_max[3];
     float K_rot_min[3], K_rot_max[3], K_angvel_min[3], K_angvel_max[3];
+    /* in-kernel disturbance (AgxHp1Buffers.dist_counter != NULL): BaseMultirotor.apply_disturbance (base_multirotor.py:213-234)
+     * drawn inside the physics sub-step with the same Philox stream as agx_disturbance_draw (disturbance_core.cuh) */
+    float dist_prob;
+    float dist_max[6];
+    uint32_t dist_pad_;
+    uint64_t dist_seed;
 } AgxHp1Config;
 
 /* All pointers are DEVICE pointers.  [N,...] arrays are dense row-major fp32 unless noted. */
@@ -99,6 +105,13 @@ typedef struct AgxHp1Buffers {
     /* inputs */
     const float* actions;     /* [N,num_actions] */
     const float* disturbance; /* [N,6] gated body-0 wrench or NULL (base_multirotor.py:213-234) */
+    const uint32_t* dist_counter; /* device u32 or NULL.  When `disturbance` is NULL and this is set, physics sub-step s of the launch
+                                     draws its disturbance in the kernel with draw counter *dist_counter + dist_offset + s -- bit for bit
+                                     what agx_disturbance_draw(counter = that value) would have put into `disturbance`.  The counter
+                                     lives in device memory so that a CUDA graph of an env step (n physics launches with
+                                     dist_offset = 0..n-1, then agx_counter_add(dist_counter, n)) replays with fresh draws. */
+    uint32_t dist_offset;
+    uint32_t dist_pad_;
     const float* target_position; /* [N,3] or NULL (= zeros) */
     /* per-env parameters; NULL = use the AgxHp1Config constant.  Written on reset. */
     float* tau_inc;           /* [N,M] */
@@ -123,10 +136,11 @@ typedef struct AgxHp1Buffers {
     uint8_t* terminations;    /* [N] bool ("crashes") */
     uint8_t* truncations;     /* [N] bool */
     uint8_t* reset_mask;      /* [N] bool, envs reset (or to be reset) this step; may be NULL */
-    int32_t* any_reset;       /* [16] device scratch, 16-byte aligned, zero-initialised by the caller once and then always
+    int32_t* any_reset;       /* [32] device scratch, 16-byte aligned, zero-initialised by the caller once and then always
                                  used with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path);
                                  [2] error word of the chained step's bounded waits (agx_hp1_check);
-                                 [4..7] per-step flags, [8..15] four 64-bit arrival counters (single-launch path, hp1.cu) */
+                                 [4..7] per-step flags, [8..15] four 64-bit arrival counters, [16..23] four 64-bit published-tile
+                                 counters (single-launch path, hp1.cu) */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
                                  when the stale-observation quirk is on and no derived array is materialised; the
@@ -189,7 +203,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
 /* 1 when agx_hp1_position_task_step(cfg, buf) takes the single-launch path whose consecutive launches are chained per
  * 32-env tile (all CTAs of a step co-resident; device-RNG reset + strict stale observation + tile_sync given), 0 when it takes
  * the two-launch path, negative on error.  Step T (0-based count of such launches since tile_sync / any_reset were zeroed) is
- * complete -- observation included -- when the u64 at any_reset + 8 + 2 * (T & 3) has reached (T / 4 + 1) * ceil(N / 32):
+ * complete -- observation included -- when the u64 at any_reset + 16 + 2 * (T & 3) has reached (T / 4 + 1) * ceil(N / 32):
  * that is the (ready_ctr, ready_target) pair agx_obs_gather_push waits on.  (Multi-GPU: the step kernel itself never
  * touches NVLink and never waits for the gather; `obs` is then one slot of a ring of observation buffers the caller rotates and
  * throttles with stream events, see agx_obs_gather_push.) */
@@ -197,6 +211,8 @@ int agx_hp1_task_step_is_chained(const AgxHp1Config* cfg, const AgxHp1Buffers* b
 /* Bound of every in-kernel wait (chained steps, observation gather), wall clock; default 20 s.  On expiry a kernel records an
  * error word and goes on (no trap, the context survives); the next agx_hp1_check / agx_obs_gather_check returns AGX_E_TIMEOUT. */
 int agx_set_spin_timeout_ms(uint64_t ms);
+/* *counter += n on `stream` (one thread): advances the device-resident draw counter of the in-kernel disturbance. */
+int agx_counter_add(uint32_t* counter, uint32_t n, void* stream);
 /* Synchronises `stream` and returns AGX_E_TIMEOUT if a wait of the chained step expired since any_reset was zeroed. */
 int agx_hp1_check(const AgxHp1Buffers* buf, void* stream);
 

@@ -25,7 +25,7 @@ class ShadowHp1Engine:
         self.motor_thrust, self.sim_steps, self.target_position = z(N, M), z(N, dt=torch.int32), z(N, 3)
         self.obs, self.reward = z(N, 13), z(N)
         self.terminations, self.truncations, self.reset_mask = z(N, dt=torch.bool), z(N, dt=torch.bool), z(N, dt=torch.bool)
-        self.any_reset, self.episode_count = z(16, dt=torch.int32), z(N, dt=torch.int32)
+        self.any_reset, self.episode_count = z(32, dt=torch.int32), z(N, dt=torch.int32)
         self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32).expand(N, -1).clone()
         self.bounds_max = torch.tensor(spec.bounds_upper_range[0], dtype=torch.float32).expand(N, -1).clone()
         allp = per_env_params == "all"
@@ -44,7 +44,7 @@ class ShadowHp1Engine:
         self.body_wrench = z(N, 6) if debug_wrench else None
         self._buf = _lib.AgxHp1Buffers()
         for name in _lib._HP1_BUF_FIELDS:
-            if name not in ("actions", "disturbance"):
+            if name not in ("actions", "disturbance", "dist_counter", "dist_offset_"):
                 t = getattr(self, name, None)
                 setattr(self._buf, name, None if t is None else t.data_ptr())
 

@@ -448,7 +448,7 @@ def test_chained_step_wait_times_out_instead_of_trapping():
         eng.position_task_step(torch.zeros(n, 4, device=DEV))
         with pytest.raises(_lib.AgxError, match="timed out"):
             eng.check()
-        assert int(eng.any_reset[2]) == 1
+        assert int(eng.any_reset[2]) & 15 == 1  # code 1: a tile's previous step never published
     finally:
         _lib.check(lib.agx_set_spin_timeout_ms(20000), "agx_set_spin_timeout_ms")
     # the context is alive and a fresh engine steps normally
