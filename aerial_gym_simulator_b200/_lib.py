@@ -70,7 +70,7 @@ class AgxHp1Buffers(C.Structure):
 class AgxObsGatherPush(C.Structure):
     _fields_ = [("local", fp), ("peer_bufs", fp), ("peer_flags", fp), ("world", C.c_int32), ("rank", C.c_int32),
                 ("bytes", C.c_uint64), ("epoch", C.c_uint32), ("max_ctas", C.c_int32), ("ready_ctr", fp), ("ready_target", C.c_uint64),
-                ("scratch", fp), ("error_word", fp), ("flag_slot", C.c_int32), ("pad_", C.c_int32)]
+                ("scratch", fp), ("error_word", fp), ("flag_slot", C.c_int32), ("pad_", C.c_int32), ("read_done", fp)]
 
 
 _HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",
@@ -174,6 +174,7 @@ def load():
         "agx_obs_gather_push": [C.POINTER(AgxObsGatherPush), C.c_void_p],
         "agx_obs_gather_wait": [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_obs_gather_check": [C.c_void_p, C.c_void_p],
+        "agx_obs_gather_gate": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
         "agx_obs_gather_set_timeout_ns": [C.c_uint64],
         "agx_set_spin_timeout_ms": [C.c_uint64],
         "agx_hp1_check": [C.POINTER(AgxHp1Buffers), C.c_void_p],

@@ -142,8 +142,12 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
         const float4 v = __ldcg(local + i);
         for (int p = 0; p < np; ++p) s_dst[p][i] = v;
     }
-    __syncthreads();  // the CTA's peer stores are ordered before thread 0's fences (cumulativity)
+    __syncthreads();  // the CTA's loads have returned (their values went into the stores) and its peer stores are ordered before thread 0's fences
     if (threadIdx.x == 0) {
+        if (a.read_done && atomicAdd(a.scratch + 1, 1u) == gridDim.x - 1) {  // every CTA has finished READING `local`:
+            a.scratch[1] = 0u;                                               // the producer may overwrite it (agx_obs_gather_gate)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.read_done), "r"(a.epoch) : "memory");
+        }
         __threadfence_system();  // waits until this CTA's NVLink stores have been performed
         if (atomicAdd(a.scratch, 1u) == gridDim.x - 1) {  // ... and so have everybody else's
             a.scratch[0] = 0u;
@@ -151,6 +155,22 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
             for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + a.flag_slot * AGX_MAX_PEERS + a.rank, a.epoch);
         }
     }
+}
+
+// gate in front of a chained step: launched with programmatic stream serialization BETWEEN two step launches, it lets the next
+// launch in (griddepcontrol.launch_dependents) only when the push that last read the ring slot has finished reading.  One warp, no
+// resources to speak of: while it waits, the step behind it is not resident, so the push it waits for always finds CTA slots.
+__global__ void __launch_bounds__(32)
+obs_gather_gate_kernel(const uint32_t* __restrict__ read_done, uint32_t need_epoch, uint32_t* error_word) {
+    if (threadIdx.x == 0) {
+        spin_until([&] {
+            uint32_t v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(read_done) : "memory");
+            return (int32_t)(v - need_epoch) >= 0;
+        }, error_word, (need_epoch << 8) | 3u);
+    }
+    __syncwarp();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(32)
@@ -193,6 +213,25 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
     return agx_check_launch("obs_gather_push_kernel");
 }
 
+extern "C" int agx_obs_gather_gate(const uint32_t* read_done, uint32_t need_epoch, uint32_t* error_word, void* stream) {
+    if (!read_done || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_gate: NULL argument");
+    static bool carve_set = false;
+    if (!carve_set) {
+        cudaFuncSetAttribute(obs_gather_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(1);
+    lc.blockDim = dim3(32);
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    return agx_check_cuda(cudaLaunchKernelEx(&lc, obs_gather_gate_kernel, read_done, need_epoch, error_word), "obs_gather_gate_kernel");
+}
+
 extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int flag_slot, int world, uint32_t epoch, uint32_t* error_word, void* stream) {
     if (!my_flags || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_wait: NULL argument");
     if (world < 1 || world > AGX_MAX_PEERS || flag_slot < 0 || flag_slot > 3) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world / flag_slot");
@@ -213,6 +252,7 @@ extern "C" int agx_obs_gather_check(const uint32_t* error_word, void* stream) {
     rc = agx_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "agx_obs_gather_check");
     if (rc) return rc;
     if (!w) return AGX_OK;
+    if ((w & 15u) == 3u) return agx_set_error(AGX_E_TIMEOUT, "observation gather: the gate in front of a step never saw the push of epoch %u finish reading (wait timed out)", w >> 8);
     return (w & 15u) == 1u ? agx_set_error(AGX_E_TIMEOUT, "observation gather: the push of epoch %u never saw its producer step complete (wait timed out)", w >> 8)
                            : agx_set_error(AGX_E_TIMEOUT, "observation gather: the wait for epoch %u never saw rank %u's flag (wait timed out)", w >> 8, (w >> 4) & 15u);
 }

@@ -139,9 +139,10 @@ class PipelinedObsGather:
       few microseconds;
     * receiver: `wait(epoch)` = a one-warp kernel on the consumer's stream that retires when all `world` flags show `epoch`.
 
-    The push never waits for a peer and the step kernel never waits for anything of this class.  Re-use of a ring slot is ordered by
-    the HOST: `next_epoch()` makes the current stream wait for the event recorded behind the push that last read the slot -- only
-    when that push has not finished yet, so the chained step launches stay back to back while the gather keeps up.  Equal shards only.
+    The push never waits for a peer and the step kernel never waits for anything of this class.  Re-use of a ring slot is ordered by a
+    one-warp GATE kernel that `next_epoch()` puts in front of the step (agx_obs_gather_gate, programmatic stream serialization): it
+    lets the step launch in only when the push that last read the slot has finished reading -- the chained step launches stay
+    chained (no event, no stream-level wait), and a step that has to wait is not resident while it waits.  Equal shards only.
     `loopback_world` (tests, one GPU): emulate a world of that size inside one process -- every "peer" buffer is a local
     buffer, rank 0 is this process; the protocol (ring, flags, counters) runs exactly as on several GPUs."""
 
@@ -200,30 +201,32 @@ class PipelinedObsGather:
         self._raw = [st.cuda_stream for st in self.streams]
         self.events = [torch.cuda.Event() for _ in range(B)]
         self._pending = [False] * B
+        self.read_done = torch.zeros(B, dtype=torch.int32, device=self.device)  # per ring slot: epoch of the last push that finished reading
         self._pushes = []
         for b in range(B):
             a = _lib.AgxObsGatherPush()
             a.peer_bufs, a.peer_flags, a.world, a.rank = self.buf_ptrs[b].data_ptr(), self.flag_ptrs.data_ptr(), self.world, self.rank
             a.bytes, a.max_ctas, a.flag_slot = self.bytes, self.max_ctas, b
             a.scratch, a.error_word = self.scratch[b].data_ptr(), self.error_word.data_ptr()
+            a.read_done = self.read_done[b].data_ptr()
             self._pushes.append((a, C.byref(a)))
         self.epoch = 0
-        self.throttled = 0  # how many times a step had to wait for the push that last read its ring slot
+        self._read_done_ptr = [self.read_done[b].data_ptr() for b in range(B)]
+        self._err_ptr = self.error_word.data_ptr()
         torch.cuda.synchronize(self.device)
         if not loopback_world:
             dist.barrier(group)  # every rank's flags are zeroed before anybody publishes epoch 1
 
     def next_epoch(self):
-        """(epoch, ring slot) of the next step.  The step will overwrite this rank's rows in ring buffer `slot`: the current stream
-        first waits for the push that last read them, if it is still running."""
+        """(epoch, ring slot) of the next step.  The step will overwrite this rank's rows in ring buffer `slot`: a gate kernel in
+        front of it (current stream) holds it back until the push that last read them has finished reading."""
         self.epoch += 1
         slot = self.epoch % self.num_buffers
-        if self._pending[slot]:
-            ev = self.events[slot]
-            if not ev.query():
-                torch.cuda.current_stream(self.device).wait_event(ev)
-                self.throttled += 1
-            self._pending[slot] = False
+        if self.epoch > self.num_buffers:
+            rc = self._lib.agx_obs_gather_gate(self._read_done_ptr[slot], self.epoch - self.num_buffers, self._err_ptr,
+                                               torch.cuda.current_stream(self.device).cuda_stream)
+            if rc:
+                self._check(rc, "agx_obs_gather_gate")
         return self.epoch, slot
 
     def push(self, local_ptr: int, epoch: int, slot: int, ready_ctr: int = 0, ready_target: int = 0, stream=None):
@@ -236,7 +239,6 @@ class PipelinedObsGather:
         if rc:
             self._check(rc, "agx_obs_gather_push")
         if stream is None:
-            self.events[slot].record(self.streams[slot])
             self._pending[slot] = True
 
     def wait(self, epoch: Optional[int] = None, stream=None):
@@ -254,6 +256,7 @@ class PipelinedObsGather:
         cur = torch.cuda.current_stream(self.device)
         for b in range(self.num_buffers):
             if self._pending[b]:
+                self.events[b].record(self.streams[b])
                 cur.wait_event(self.events[b])
                 self._pending[b] = False
 

@@ -507,7 +507,6 @@ def run_ours(args):
             "value_hot_l2": value_hot,
             "value_obs_gather_sync": value_sync,
             "obs_gather_check": gather_check,
-            "obs_gather_throttled_steps": (gather.throttled if gather is not None else None),
             "wall_s_timed_region": t_wall,
             "host_enqueue_us_per_step": 1e6 * t_enqueue / K,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,true> (the whole fused step is this one launch)", "achieved": achieved, "peak": peak,

@@ -515,8 +515,8 @@ int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const
  * into slot `rank` of every rank's gathered buffer (peer_bufs[p] + rank * bytes; the own slot is skipped when `local` already is
  * that slot), then -- when all stores of this rank have been performed at system scope -- publish `epoch` into flag word
  * peer_flags[p][flag_slot * AGX_MAX_PEERS + rank] on every rank p.  The kernel never waits for a peer.  Pushes into different ring
- * slots may run concurrently (one stream and one scratch block per slot); re-use of a slot is ordered by the caller (an event
- * recorded behind the push, awaited by the stream that next writes `local`).
+ * slots may run concurrently (one stream and one scratch block per slot); re-use of a slot is ordered by the caller
+ * (agx_obs_gather_gate on `read_done`, or plain stream order).
  *   peer_bufs / peer_flags : DEVICE arrays of `world` device pointers (symmetric-memory rendezvous)
  *   scratch                : device uint32[4] of this ring slot, zero-initialised once
  *   error_word             : device uint32, zero-initialised once (agx_obs_gather_check)
@@ -536,8 +536,15 @@ typedef struct AgxObsGatherPush {
     uint32_t* error_word;
     int32_t flag_slot;
     int32_t pad_;
+    uint32_t* read_done;   /* device uint32 of this ring slot or NULL: receives `epoch` (release, gpu scope) as soon as every CTA has
+                              finished READING `local` -- before the NVLink drain; agx_obs_gather_gate waits on it */
 } AgxObsGatherPush;
 int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream);
+/* Ring-slot gate for a producer that runs ahead of its pushes: a one-warp kernel, launched with programmatic stream serialization
+ * on the producer's stream, that lets the launch behind it start only once *read_done >= need_epoch (wrap-safe), i.e. once the push
+ * that last read the ring slot the next step is about to overwrite has finished reading it.  Between two chained
+ * agx_hp1_position_task_step launches it keeps their per-tile chaining (no event, no stream-level wait). */
+int agx_obs_gather_gate(const uint32_t* read_done, uint32_t need_epoch, uint32_t* error_word, void* stream);
 /* Receiver side: one tiny kernel that retires when my_flags[flag_slot * AGX_MAX_PEERS + q] >= epoch for every rank q < world
  * (wrap-safe compare), i.e. when every rank's rows of `epoch` have landed in this rank's gathered buffer of that ring slot; work
  * queued behind it on `stream` may read it. */

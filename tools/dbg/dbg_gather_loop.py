@@ -1,34 +1,33 @@
+"""1-GPU loopback timing of the chained steps with / without the observation gather attached (emulated world: pushes go to local buffers)."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from aerial_gym_simulator_b200.distributed import PipelinedObsGather
 from aerial_gym_simulator_b200.hp1 import Hp1Engine, MultirotorSpec
 from aerial_gym_simulator_b200 import _lib
-from tests import _hp1_common as H
 DEV='cuda:0'; n=65536
-_lib.check(_lib.load().agx_set_spin_timeout_ms(2000), "t")
-def run(with_ref, with_gather=True, lb=3, steps=46, ctas=24, nb=4, prio=-1):
-    spec = H.spec_for("quad_attitude")
-    root, actions, params = H.random_inputs(spec, n, seed=4)
-    eng = Hp1Engine(spec, n, DEV, seed=9, materialize_derived=False)
-    ref = Hp1Engine(spec, n, DEV, seed=9, materialize_derived=False)
-    for e in (eng, ref):
-        H.load_engine_state(e, root, params)
-        e.sim_steps.copy_((torch.arange(n, device=DEV) % 500 + 480).int() % 501)
-    gth = PipelinedObsGather(n, 13, DEV, num_buffers=nb, loopback_world=lb, max_ctas=ctas)
-    if prio != -1:
-        gth.streams = [torch.cuda.Stream(device=DEV) for _ in range(nb)]; gth._raw = [st.cuda_stream for st in gth.streams]
-    if with_gather: eng.attach_obs_gather(gth)
-    act = actions.to(DEV)
-    for step in range(steps):
-        if with_ref: ref.position_task_step(act)
-        eng.position_task_step(act)
-    if with_gather:
-        gth.loopback_complete(gth.epoch); gth.wait()
+_lib.check(_lib.load().agx_set_spin_timeout_ms(3000), "t")
+def run(R, lb, ctas=24, nb=4, steps=200):
+    engines = []
+    for r in range(R):
+        e = Hp1Engine(MultirotorSpec(), n, DEV, seed=9 + r, materialize_derived=False)
+        e.reset(torch.ones(n, dtype=torch.bool, device=DEV)); e.refresh()
+        e.sim_steps.copy_((torch.arange(n, device=DEV) % 500).int())
+        engines.append(e)
+    gth = None
+    if lb:
+        gth = PipelinedObsGather(n, 13, DEV, num_buffers=nb, loopback_world=lb, max_ctas=ctas)
+        for e in engines: e.attach_obs_gather(gth)
+    act = torch.zeros(n, 4, device=DEV)
+    def loop(k):
+        for i in range(k): engines[i % R].position_task_step(act)
+        if gth is not None:
+            gth.loopback_complete(gth.epoch); gth.fence(); gth.wait()
+    loop(32); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time; t0 = time.perf_counter()
+    e0.record(); loop(steps); e1.record(); th = time.perf_counter() - t0
     torch.cuda.synchronize()
-    ar = eng.any_reset.cpu().tolist()
-    ts = eng.tile_sync.cpu()
-    nt = n // 32
-    print("ctas", ctas, "nb", nb, "prio", prio, "with_ref", with_ref, "gather", with_gather, "err", hex(gth.error_word.item()), "throttled", gth.throttled, "T", eng._chain_T,
-          "flags", gth.flags.view(4,16)[:, 0].tolist(), "arrivals", [ar[8+2*k] + (ar[9+2*k] << 32) for k in range(4)], "stepflags", ar[4:8], "engerr", hex(ar[2]),
-          "claim min/max", ts[:nt].min().item(), ts[:nt].max().item(), "done min/max", ts[nt:].min().item(), ts[nt:].max().item(), flush=True)
-run(False); run(True); run(False, ctas=37); run(False, ctas=16)
+    err = hex(gth.error_word.item()) if gth is not None else None
+    engerr = [hex(e.any_reset[2].item()) for e in engines if e.any_reset[2].item()]
+    print(f"replicas={R} loopback_world={lb} ctas={ctas} ring={nb}: {e0.elapsed_time(e1) * 1e3 / steps:.2f} us/step, host enqueue {th * 1e6 / steps:.2f} us/step, gather err {err}, engine errs {engerr}", flush=True)
+run(1, 0); run(16, 0); run(1, 2); run(16, 2); run(16, 4); run(16, 8); run(16, 2, ctas=8); run(16, 2, ctas=48, nb=2)
