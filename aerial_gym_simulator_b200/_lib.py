@@ -178,6 +178,8 @@ def load():
         "agx_obs_gather_set_timeout_ns": [C.c_uint64],
         "agx_set_spin_timeout_ms": [C.c_uint64],
         "agx_hp1_check": [C.POINTER(AgxHp1Buffers), C.c_void_p],
+        "agx_hp1_position_task_step_gathered": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                C.POINTER(AgxObsGatherPush), C.c_void_p],
         "agx_counter_add": [C.c_void_p, C.c_uint32, C.c_void_p],
         "agx_hp1_task_step_is_chained": [C.POINTER(AgxHp1Config), C.POINTER(AgxHp1Buffers)],
         "agx_nav_reward": [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,

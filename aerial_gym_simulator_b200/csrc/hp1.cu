@@ -844,6 +844,15 @@ int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf
     return agx_hp1_position_task_step_profiled(cfg, buf, stream, nullptr);
 }
 
+int agx_hp1_position_task_step_gathered(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream, const uint32_t* gate_read_done,
+                                        uint32_t gate_need_epoch, uint32_t* gate_error_word, const AgxObsGatherPush* push, void* push_stream) {
+    int rc = AGX_OK;
+    if (gate_read_done) rc = agx_obs_gather_gate(gate_read_done, gate_need_epoch, gate_error_word, stream);
+    if (rc == AGX_OK) rc = agx_hp1_position_task_step_profiled(cfg, buf, stream, nullptr);
+    if (rc == AGX_OK && push) rc = agx_obs_gather_push(push, push_stream);
+    return rc;
+}
+
 int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream,
                                         void* ev_after_main) {
     int rc = validate(cfg, buf, true);

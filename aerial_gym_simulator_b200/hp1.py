@@ -266,6 +266,7 @@ class Hp1Engine:
         self._chain_counts = bool(self.lib.agx_hp1_task_step_is_chained(self._cfg_ref, self._buf_ref))
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._task_step = self.lib.agx_hp1_position_task_step
+        self._task_step_gathered = self.lib.agx_hp1_position_task_step_gathered
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _host_tensor(self, shape, dtype):
@@ -390,7 +391,26 @@ class Hp1Engine:
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
         chained = self._chain_counts and mid_event is None  # which path the library takes for this launch
-        armed = self._arm_gather(chained) if self._gather is not None else None
+        g = self._gather
+        if g is not None and chained:
+            # gate (ring slot free?) + step + push of its rows: one C call, three launches
+            g.epoch += 1
+            e, B = g.epoch, g.num_buffers
+            slot = e % B
+            own = g.own_slot_ptr[slot]
+            self.obs, self._buf.obs = g.own_slot[slot], own
+            a, ref = g._pushes[slot]
+            T = self._chain_T
+            a.local, a.epoch, a.ready_ctr, a.ready_target = own, e, self._ready_base + 8 * (T & 3), (T // 4 + 1) * self._n_tiles
+            rc = self._task_step_gathered(self._cfg_ref, self._buf_ref, self._stream(), g._read_done_ptr[slot] if e > B else None, e - B,
+                                          g._err_ptr, ref, g._raw[slot])
+            if rc:
+                _lib.check(rc, "agx_hp1_position_task_step_gathered")
+            g._pending[slot] = True
+            self.gathered_obs = g.outs[slot]
+            self._chain_T = T + 1
+            return
+        armed = self._arm_gather(chained) if g is not None else None
         if mid_event is None:
             rc = self._task_step(self._cfg_ref, self._buf_ref, self._stream())
         else:

@@ -44,10 +44,13 @@ class TaskRegistry(_Table):
     def get_task_configs(self):
         return list(self._configs.values())
 
-    def make_task(self, task_name, seed=None, num_envs=None, headless=None, use_warp=None):
-        return self.get_task_class(task_name)(
-            self.get_task_config(task_name), seed=seed, num_envs=num_envs, headless=headless, use_warp=use_warp
-        )
+    def make_task(self, task_name, seed=None, num_envs=None, headless=None, use_warp=None, args=None):
+        """registry/task_registry.py:25-30, plus `args` (not in the reference): merged into task_config.args for this task, e.g.
+        {"world_size": W, "rank": r} for an env-sharded task whose observation is all-gathered (task/base_task.py)"""
+        cfg = self.get_task_config(task_name)
+        if args:
+            cfg.args = {**dict(getattr(cfg, "args", None) or {}), **dict(args)}
+        return self.get_task_class(task_name)(cfg, seed=seed, num_envs=num_envs, headless=headless, use_warp=use_warp)
 
 
 class RobotRegistry(_Table):

@@ -44,9 +44,13 @@ class NavigationTask(BaseTask):
         self._params = _lib.AgxNavRewardParams()
         for i, name in enumerate(_PARAM_ORDER):
             self._params.v[i] = float(self.task_config.reward_parameters[name])
+        args = dict(self.task_config.args or {})
+        world, rank, _ = self.shard_spec()
+        if world > 1:  # env-sharded: global env ids rank * num_envs ... (keys the device RNG)
+            args.setdefault("env_id_offset", rank * int(self.task_config.num_envs))
         self.sim_env = SimBuilder().build_env(
             sim_name=self.task_config.sim_name, env_name=self.task_config.env_name, robot_name=self.task_config.robot_name,
-            controller_name=self.task_config.controller_name, args=self.task_config.args, device=self.device,
+            controller_name=self.task_config.controller_name, args=args, device=self.device,
             num_envs=self.task_config.num_envs, use_warp=self.task_config.use_warp, headless=self.task_config.headless)
         N, dev = self.sim_env.num_envs, self.device
         self.num_envs = N
@@ -77,6 +81,8 @@ class NavigationTask(BaseTask):
         self.task_obs = {"observations": torch.zeros((N, self.task_config.observation_space_dim), device=dev)}
         self.infos = {}
         self.num_task_steps = 0
+        if self.init_sharding(N, self.task_config.observation_space_dim, dev) is not None:  # BaseTask: multi-GPU, observation all-gather
+            self.task_obs["observations_local"] = self.task_obs["observations"]
 
     def close(self):
         self.sim_env.delete_env()
@@ -166,6 +172,8 @@ class NavigationTask(BaseTask):
 
     def get_return_tuple(self):
         self.process_obs_for_task()
+        if self.obs_gather is not None:  # sharded: the policy gets the global [W * N, D] observation tensor
+            self.task_obs["observations"], _ = self.gather_observations(self.task_obs["observations_local"])
         return (self.task_obs, self.rewards, self.terminations, self.truncations, self.infos)
 
     def process_obs_for_task(self, u_vec=None, u_euler=None):
@@ -175,7 +183,7 @@ class NavigationTask(BaseTask):
             u_vec = torch.rand((N, 3), device=dev)
         if u_euler is None:
             u_euler = torch.rand((N, 3), device=dev)
-        st, obs = od["robot_state_tensor"], self.task_obs["observations"]
+        st, obs = od["robot_state_tensor"], (self.task_obs["observations_local"] if self.obs_gather is not None else self.task_obs["observations"])
         p = lambda t: C.c_void_p(t.data_ptr())
         _lib.check(self.lib.agx_nav_obs(
             N, p(st), st.stride(0), p(od["robot_vehicle_orientation"]), p(od["robot_euler_angles"]), p(od["robot_body_linvel"]),

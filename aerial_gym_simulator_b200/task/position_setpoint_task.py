@@ -31,6 +31,9 @@ class PositionSetpointTask(BaseTask):
             self.task_config.reward_parameters[key] = torch.as_tensor(self.task_config.reward_parameters[key], device=self.device)
         args = dict(self.task_config.args or {})
         args.setdefault("seed", self._seed)
+        world, rank, _ = self.shard_spec()
+        if world > 1:  # env-sharded: this rank's envs are the global ids rank * num_envs ... (keys the device RNG)
+            args.setdefault("env_id_offset", rank * int(self.task_config.num_envs))
         self.sim_env = SimBuilder().build_env(
             sim_name=self.task_config.sim_name, env_name=self.task_config.env_name, robot_name=self.task_config.robot_name,
             controller_name=self.task_config.controller_name, args=args, device=self.device,
@@ -48,6 +51,7 @@ class PositionSetpointTask(BaseTask):
         self.actions = torch.zeros((self.num_envs, self.task_config.action_space_dim), device=self.device)
         self.prev_actions = torch.zeros_like(self.actions)
         self.counter = 0
+        self._published_epoch = -1
         self.target_position = eng.target_position  # [N,3], read by the kernel
         self.obs_dict = env.get_obs()
         self.obs_dict["num_obstacles_in_env"] = 1
@@ -65,8 +69,14 @@ class PositionSetpointTask(BaseTask):
             "truncations": self.truncations,
         }
         self.infos = {}
+        if self.init_sharding(self.num_envs, 13, self.device) is not None:
+            if eng.host_io:
+                raise ValueError("args['host_io'] and a sharded task are mutually exclusive")
+            eng.attach_obs_gather(self.obs_gather)  # the fused step writes its observation into the gather's ring; the push runs beside it
 
     def close(self):
+        if getattr(self, "obs_gather", None) is not None and self.sim_env.engine is not None:
+            self.sim_env.engine.attach_obs_gather(None)
         self.sim_env.delete_env()
 
     def reset(self):
@@ -114,7 +124,21 @@ class PositionSetpointTask(BaseTask):
         return self.get_return_tuple()
 
     def get_return_tuple(self):
+        if self.obs_gather is not None:
+            self._publish_global_observations()
         return (self.task_obs, self.rewards, self.terminations, self.truncations, self.infos)
+
+    def _publish_global_observations(self):
+        """sharded task: task_obs['observations'] <- the gathered [W*N, 13] tensor of this step (waits for every rank's rows)"""
+        g, eng = self.obs_gather, self.sim_env.engine
+        if eng.gathered_obs is None or self._published_epoch == g.epoch:  # reset() / a hook path: the engine's observation was written outside the fused step
+            glob, loc = self.gather_observations(eng.obs)
+        else:
+            if getattr(g, "peer_outs", None) is not None:
+                g.loopback_complete(g.epoch)
+            glob, loc = g.wait(), eng.obs
+        self._published_epoch = g.epoch
+        self.task_obs["observations"], self.task_obs["observations_local"] = glob, loc
 
     # ------------------------------------------------------------------------------------------
     # The reference's two hooks (position_setpoint_task.py:194-229).  For THIS class they are fused into the step kernel and never

@@ -393,7 +393,10 @@ def run_ours(args):
 
     def make_task(host_io):
         old_args, old_dev = tcfg.args, tcfg.device
-        tcfg.args, tcfg.device = {"env_id_offset": rank * N, "host_io": host_io}, str(dev)
+        # N > 1: the env-sharded task of the product API -- step() runs the fused step, the observation all-gather beside it and
+        # waits for every rank's rows: the observation it returns is the global [world * N, 13] tensor
+        tcfg.args = {"shard": "torchrun"} if world > 1 else {"env_id_offset": rank * N, "host_io": host_io}
+        tcfg.device = str(dev)
         try:
             t = task_registry.make_task("position_setpoint_task", seed=7, num_envs=N, headless=True)
         finally:
@@ -419,16 +422,19 @@ def run_ours(args):
 
     # (1) host I/O mode: the one kernel of task.step loads the actions from pinned host memory and
     # stores obs / rewards / terminations / truncations into pinned host memory over PCIe; step()
-    # returns when the stream has drained.  Each rank's host consumer gets its own shard.
-    task = make_task(True)
-    sink = torch.zeros(4, dtype=torch.float64)
+    # returns when the stream has drained.  Each rank's host consumer gets its own shard.  (N = 1 only: at N > 1 the
+    # observation lives in the gather's ring in device memory.)
+    e2e_hostio = None
+    if world == 1:
+        task = make_task(True)
+        sink = torch.zeros(4, dtype=torch.float64)
 
-    def e2e_step_hostio(i):
-        obs_d, rew_d, term_d, trunc_d, _ = task.step(h_act[i % 8])
-        sink[0] += float(rew_d[-1])  # the results are plain CPU tensors: the host reads them in place
+        def e2e_step_hostio(i):
+            obs_d, rew_d, term_d, trunc_d, _ = task.step(h_act[i % 8])
+            sink[0] += float(rew_d[-1])  # the results are plain CPU tensors: the host reads them in place
 
-    e2e_value = time_e2e(e2e_step_hostio)
-    task.close()
+        e2e_hostio = time_e2e(e2e_step_hostio)
+        task.close()
 
     # (2) for comparison: device-resident task + explicit pinned-memory copies around step()
     task = make_task(False)
@@ -441,14 +447,22 @@ def run_ours(args):
     def e2e_step_memcpy(i):
         d_act.copy_(h_act[i % 8], non_blocking=True)
         obs_d, rew_d, term_d, trunc_d, _ = task.step(d_act)
-        h_obs.copy_(obs_d["observations"], non_blocking=True)
+        h_obs.copy_(obs_d["observations_local"] if world > 1 else obs_d["observations"], non_blocking=True)
         h_rew.copy_(rew_d, non_blocking=True)
         h_term.copy_(term_d, non_blocking=True)
         h_trunc.copy_(trunc_d, non_blocking=True)
         stream.synchronize()  # the user reads the result of every step
 
     e2e_memcpy = time_e2e(e2e_step_memcpy)
+    e2e_gather_ok = None
+    if world > 1:  # the global observation the sharded task hands out == the library collective's gather of the ranks' rows
+        obs_d = task.step(d_act)[0]
+        want = nccl_gather(obs_d["observations_local"].contiguous()).clone()
+        okt = torch.tensor([int(torch.equal(obs_d["observations"], want))], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        e2e_gather_ok = bool(okt.item())
     task.close()
+    e2e_value = e2e_hostio if world == 1 else e2e_memcpy
     h2d = N * 4 * 4
     d2h = N * 13 * 4 + N * 4 + 2 * N
 
@@ -520,11 +534,15 @@ def run_ours(args):
                                  "launch alone spans ~11.5 us (tools/dbg/timeline.py) and 17-19 us when serialised by its own event pair / ncu"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "value_memcpy_variant": e2e_memcpy,
-                    "api": "task_registry.make_task('position_setpoint_task', args={'host_io': True}).step(actions): the "
-                           "step kernel reads the pinned host actions and writes obs/reward/flags to pinned host memory "
-                           "over PCIe (no staging copies), step() returns after the stream drained and the host reads "
-                           "its shard in place; value_memcpy_variant = device-resident task + cudaMemcpyAsync both ways."},
+                    "value_memcpy_variant": e2e_memcpy, "sharded_task_obs_equals_nccl": e2e_gather_ok,
+                    "api": ("task_registry.make_task('position_setpoint_task', args={'host_io': True}).step(actions): the "
+                            "step kernel reads the pinned host actions and writes obs/reward/flags to pinned host memory "
+                            "over PCIe (no staging copies), step() returns after the stream drained and the host reads "
+                            "its shard in place; value_memcpy_variant = device-resident task + cudaMemcpyAsync both ways.") if world == 1 else
+                           ("task_registry.make_task('position_setpoint_task', args={'shard': 'torchrun'}).step(actions) on every rank: pinned "
+                            "host actions -> cudaMemcpyAsync -> fused step + observation all-gather (push / wait kernels, awaited every "
+                            "step: the global [world*N,13] observation is what step() returns) -> cudaMemcpyAsync of this rank's rows, "
+                            "rewards and flags to pinned host memory -> stream synchronise")},
             "gpu_launches": K,
             "clocks": clocks,
             "hp2_depth": hp2,
@@ -858,9 +876,35 @@ def main():
     ap.add_argument("--cfg4-controller", default="rov_fully_actuated_control", help="7-D pose command, FullyActuatedController")
     ap.add_argument("--nav-envs", type=int, default=1024)
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_ours(args)
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner, the reference's logger)
+    # goes to stderr -- file descriptor 1 is pointed at stderr for the run and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    orig_print = print
+
+    def capture_print(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            orig_print(*a, **k)
+
+    import builtins
+    builtins.print = capture_print
+    try:
+        rc = run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        if ln.startswith("{"):
+            print(ln, flush=True)
+        else:
+            sys.stderr.write(ln + "\n")
+    return rc
 
 
 if __name__ == "__main__":

@@ -165,6 +165,7 @@ typedef struct AgxHp1ResetDraws {
     const float* k_thrust;    /* [N,M] motor_model.py:151-154 (NULL unless use_rps) */
 } AgxHp1ResetDraws;
 
+struct AgxObsGatherPush;
 int agx_abi_version(void);
 const char* agx_last_error(void);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check):
@@ -195,6 +196,12 @@ int agx_hp1_physics_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void
  * envs to reset are only flagged (reset_mask, any_reset[0]) and the caller follows with
  * agx_hp1_reset + agx_hp1_refresh. */
 int agx_hp1_position_task_step(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream);
+/* The chained step with its observation gather in ONE call (three launches, one host round trip -- at ~10 us per step the host's
+ * launch path is the next bottleneck): agx_obs_gather_gate(gate_read_done, gate_need_epoch) on `stream` unless gate_read_done is
+ * NULL, agx_hp1_position_task_step(cfg, buf, stream), agx_obs_gather_push(push, push_stream).  See those three. */
+int agx_hp1_position_task_step_gathered(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream, const uint32_t* gate_read_done,
+                                        uint32_t gate_need_epoch, uint32_t* gate_error_word, const struct AgxObsGatherPush* push,
+                                        void* push_stream);
 /* Same call; additionally records the cudaEvent_t `ev_after_main` between the main kernel and the
  * conditional refresh pass, so a caller can time the dominant kernel alone (bench.py roofline). */
 int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buffers* buf, void* stream,
