@@ -445,6 +445,7 @@ __device__ __forceinline__ v3 shfl3(v3 a, int src) {
 }
 
 constexpr int kTileMaxLeaves = 128;
+constexpr int kBigSceneRecords = 384;  // record slots of the <false, true> tile path (43 KB of shared memory per CTA)
 // per-image object record (shared memory, built once per work item by build_records):
 //   [0..8] box axes A0 A1 A2 | [9..11] (o - c).A_k for the sensor origin o | [12..14] true half extents |
 //   [15] pad | [16] kind (0 generic mesh in its AABB, 1 box-shaped bound only, 2 canonical box) | [17] object index |
@@ -457,7 +458,7 @@ constexpr int kRecFloats = 28;
 // rays span all of them); objects entirely outside one plane get no record.
 __device__ __forceinline__ void build_records(const float* __restrict__ nodes, const int32_t* __restrict__ leaf,
                                               const float* __restrict__ obb, int P, v3 o, const v3* frustum, float t_far,
-                                              float* __restrict__ rec, int* n_rec) {
+                                              float* __restrict__ rec, int* n_rec, int cap) {
     for (int slot = threadIdx.x; slot < P; slot += blockDim.x) {
         const int obj = leaf[slot];
         if (obj < 0) continue;
@@ -495,7 +496,9 @@ __device__ __forceinline__ void build_records(const float* __restrict__ nodes, c
             }
             if (outside) continue;
         }
-        float* q = rec + (size_t)atomicAdd(n_rec, 1) * kRecFloats;
+        const int idx = atomicAdd(n_rec, 1);
+        if (idx >= cap) continue;  // more survivors than record slots: the caller sees *n_rec > cap and walks the BVH per ray instead
+        float* q = rec + (size_t)idx * kRecFloats;
         q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = a1.x; q[4] = a1.y; q[5] = a1.z; q[6] = a2.x; q[7] = a2.y; q[8] = a2.z;
         q[9] = dot3(r, a0); q[10] = dot3(r, a1); q[11] = dot3(r, a2);
         q[12] = h.x; q[13] = h.y; q[14] = h.z;
@@ -734,7 +737,7 @@ constexpr int kCastThreads = 256;
 template <bool SMEM, bool TILE = false>
 __global__ void __launch_bounds__(kCastThreads, AGX_CAST_MIN_BLOCKS)
 hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ AgxHp2Sensor sn, int rows_per_item,
-                int items_per_image, long long n_items) {
+                int items_per_image, long long n_items, int rec_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_nrec;
@@ -749,7 +752,8 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
     float* s_tris = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_leaf) + ((leaf_bytes + 15u) & ~15u));
     const uint32_t obb_bytes = sc.obb ? (uint32_t)((size_t)K * kObbFloats * 4) : 0u;
     float* s_obb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_tris) + tri_bytes);
-    float* s_rec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_obb) + ((obb_bytes + 15u) & ~15u));  // TILE only
+    // TILE only: object records behind the staged scene, or (scene too large to stage: <false, true>) at the start of the buffer
+    float* s_rec = SMEM ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_obb) + ((obb_bytes + 15u) & ~15u)) : reinterpret_cast<float*>(smem_raw);
     if (SMEM && threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -819,8 +823,14 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         // warp <-> 8x4 pixel tile: neighbouring rays stay in one warp (coherent traversal, SIMT efficiency)
         const int tiles_x = (W + 7) >> 3, tiles_y = (y1 - y0 + 3) >> 2;
         const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
-        constexpr bool tile_path = SMEM && TILE;
-        if constexpr (tile_path) {  // per-image object records (depend on the sensor origin)
+        // Tile path.  <true, true>: scene staged in shared memory (<= 128 leaf slots, every shipped environment).  <false, true>: scene
+        // too large to stage (BASELINE configs[2]: 1024 boxes = 590 KB): the records of the objects that survive the work item's
+        // frustum (a 4096-ray row block: a few percent of a cluttered scene) still fit shared memory, the per-tile culling and the
+        // uniform candidate loop are the same, only the candidates' triangle slabs come from L2 -- no per-ray BVH walk with its
+        // divergent stack.  If more objects survive than there are record slots (LiDAR row blocks span the full azimuth), this
+        // work item walks the BVH per ray as before.
+        constexpr bool tile_path = TILE;
+        if constexpr (tile_path) {  // per-item object records (depend on the sensor origin)
             __syncthreads();        // previous item's records are no longer read
             if (threadIdx.x == 0) s_nrec = 0;
             __syncthreads();
@@ -854,10 +864,11 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
                 else if (sn.kind != AGX_SENSOR_NORMAL_FACEID_CAMERA && !sn.return_pointcloud && sn.calculate_depth)
                     item_far = FLT_MAX;
             }
-            build_records(nodes, leaf, obb, P, sp, have_frustum ? fr : nullptr, item_far, s_rec, &s_nrec);
+            build_records(nodes, leaf, obb, P, sp, have_frustum ? fr : nullptr, item_far, s_rec, &s_nrec, rec_cap);
             __syncthreads();
         }
         const int n_rec = tile_path ? s_nrec : 0;
+        const bool rec_overflow = tile_path && n_rec > rec_cap;
         for (int tix = threadIdx.x >> 5; tix < tiles_x * tiles_y; tix += kCastThreads / 32) {
             int x = (tix % tiles_x) * 8 + lx, y = y0 + (tix / tiles_x) * 4 + ly;
             const bool in_image = x < W && y < y1;
@@ -881,7 +892,8 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
             }
             Hit h;
             if constexpr (tile_path) {
-                h = tile_closest_hit(s_rec, n_rec, tris, L, sp, rd, max_t, lane);
+                if (!rec_overflow) h = tile_closest_hit(s_rec, n_rec, tris, L, sp, rd, max_t, lane);
+                else h = traverse<SMEM>(nodes, leaf, tris, obb, P, L, sp, rd, max_t);
                 if (!in_image) continue;
             } else {
                 h = traverse<SMEM>(nodes, leaf, tris, obb, P, L, sp, rd, max_t);
@@ -1061,7 +1073,7 @@ int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)sms * per_sm;
         if (grid > n_items) grid = n_items;
-        hp2_cast_kernel<true, true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+        hp2_cast_kernel<true, true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items, sc->num_objects);
     } else if (use_smem) {
         rc = agx_check_cuda(cudaFuncSetAttribute(hp2_cast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(cast)");
@@ -1071,14 +1083,27 @@ int agx_hp2_cast(const AgxHp2Scene* sc, const AgxHp2Sensor* sn, void* stream) {
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)sms * per_sm;
         if (grid > n_items) grid = n_items;
-        hp2_cast_kernel<true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+        hp2_cast_kernel<true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items, 0);
+    } else if (sn->kind == AGX_SENSOR_CAMERA || sn->kind == AGX_SENSOR_STEREO_CAMERA || sn->kind == AGX_SENSOR_NORMAL_FACEID_CAMERA) {
+        // scene too large for shared memory, pinhole sensor: tile path with records only (see the kernel)
+        const int cap = sc->num_objects < kBigSceneRecords ? sc->num_objects : kBigSceneRecords;
+        smem = record_smem_bytes(cap);
+        rc = agx_check_cuda(cudaFuncSetAttribute(hp2_cast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(cast)");
+        if (rc) return rc;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp2_cast_kernel<false, true>, kCastThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sms * per_sm;
+        if (grid > n_items) grid = n_items;
+        hp2_cast_kernel<false, true><<<(int)grid, kCastThreads, smem, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items, cap);
     } else {
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp2_cast_kernel<false>, kCastThreads, 0);
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)sms * per_sm;
         if (grid > n_items) grid = n_items;
-        hp2_cast_kernel<false><<<(int)grid, kCastThreads, 0, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items);
+        hp2_cast_kernel<false><<<(int)grid, kCastThreads, 0, st>>>(*sc, *sn, rows_per_item, items_per_image, n_items, 0);
     }
     return agx_check_launch("hp2_cast_kernel");
 }

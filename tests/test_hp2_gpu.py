@@ -104,14 +104,26 @@ def test_object_counts_shared_memory_path(K):
     check(sensor, *oracle_cast(sc, cfg, sensor, robot, mount))
 
 
-def test_large_scene_global_memory_path():
-    """1024 boxes / env = 12,288 triangles (BASELINE config #3 stress scene): ~590 KB per env,
-    does not fit shared memory -> L2 traversal path."""
-    cfg = H.cfg_variant(H.CamCfg, height=12, width=16)
-    sc = H.make_scene(2, 1024, seed=50, extent=8.0)
+@pytest.mark.parametrize("h,w,extent", [(12, 16, 8.0), (40, 200, 8.0), (12, 16, 1.5)])
+def test_large_scene_global_memory_path(h, w, extent):
+    """1024 boxes / env = 12,288 triangles (BASELINE config #3 stress scene): ~590 KB per env, does not fit shared memory ->
+    cameras take the records-only tile path (object records in shared memory, candidate slabs from L2).  40 x 200: two row-block
+    work items per image; extent 1.5 m: every object is in the frustum and within range, more survivors than record slots ->
+    that work item falls back to the per-ray BVH walk.  All bit-identical to the brute-force oracle."""
+    cfg = H.cfg_variant(H.CamCfg, height=h, width=w)
+    sc = H.make_scene(2, 1024, seed=50, extent=extent)
     scene, sensor, robot, mount, _ = build(sc, cfg, seed=8)
     sensor.capture()
     check(sensor, *oracle_cast(sc, cfg, sensor, robot, mount))
+
+
+def test_large_scene_lidar_and_pointcloud():
+    """large scene, LiDAR (per-ray BVH walk from L2) and a camera point cloud (records-only tile path)"""
+    sc = H.make_scene(2, 600, seed=51, extent=6.0)
+    for cfg in (H.cfg_variant(H.LidarCfg, height=8, width=64), H.cfg_variant(H.CamCfg, height=10, width=14, return_pointcloud=True)):
+        scene, sensor, robot, mount, _ = build(sc, cfg, seed=9)
+        sensor.capture()
+        check(sensor, *oracle_cast(sc, cfg, sensor, robot, mount))
 
 
 def test_masked_scene_update_after_reset():
