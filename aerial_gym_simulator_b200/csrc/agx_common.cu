@@ -2,6 +2,8 @@
 #include <stdio.h>
 
 #include "../../include/aerial_gym_b200.h"
+#include <stdlib.h>
+
 #include "agx_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -20,6 +22,16 @@ int agx_check_cuda(cudaError_t e, const char* what) {
 }
 
 int agx_check_launch(const char* what) { return agx_check_cuda(cudaPeekAtLastError(), what); }
+
+// The chained HP1 step and the gather kernels that run beside it must agree on the SM's shared-memory carve-out (see agx_common.cuh).
+int agx_coresident_carveout_pct() {
+    static int pct = -2;
+    if (pct == -2) {
+        const char* e = getenv("AGX_CARVEOUT_PCT");  // A/B knob: percent of the unified L1 / shared memory, -1 = leave the driver's choice
+        pct = e ? atoi(e) : 25;
+    }
+    return pct;
+}
 
 extern "C" {
 int agx_abi_version(void) { return AGX_ABI_VERSION; }

@@ -761,11 +761,7 @@ inline int coop_capacity(StepKernel k) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // Kernels that run BESIDE the chained step (the gather's push / wait kernels) must not pin an SM to a smaller shared-memory
-    // carve-out than this kernel's eight 4.3 KB CTAs need: measured (round 2), one push CTA that reached an idle SM first left room
-    // for ~1 step CTA there, 24 of them cost > 160 slots and a step that needs its whole grid resident starved.  Every such
-    // kernel and this one ask for the same (maximum) carve-out.
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    agx_set_coresident_carveout(k);  // same shared-memory carve-out as the gather kernels that run beside this one (agx_common.cuh)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
     const int cap = sms * per_sm;
     if (n_seen < 32) { seen[n_seen] = k; caps[n_seen] = cap; ++n_seen; }

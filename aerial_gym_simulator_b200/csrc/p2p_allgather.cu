@@ -205,8 +205,8 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
     if (ctas < 1) ctas = 1;
     static bool carve_set = false;
     if (!carve_set) {  // same shared-memory carve-out as the step kernel it runs beside (hp1.cu coop_capacity)
-        cudaFuncSetAttribute(obs_gather_push_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(obs_gather_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        agx_set_coresident_carveout(obs_gather_push_kernel);
+        agx_set_coresident_carveout(obs_gather_wait_kernel);
         carve_set = true;
     }
     obs_gather_push_kernel<<<(int)ctas, kPushThreads, 0, (cudaStream_t)stream>>>(*a, n_vec);
@@ -217,7 +217,7 @@ extern "C" int agx_obs_gather_gate(const uint32_t* read_done, uint32_t need_epoc
     if (!read_done || !error_word) return agx_set_error(AGX_E_NULL, "obs_gather_gate: NULL argument");
     static bool carve_set = false;
     if (!carve_set) {
-        cudaFuncSetAttribute(obs_gather_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        agx_set_coresident_carveout(obs_gather_gate_kernel);
         carve_set = true;
     }
     cudaLaunchConfig_t lc = {};
@@ -237,7 +237,7 @@ extern "C" int agx_obs_gather_wait(const uint32_t* my_flags, int flag_slot, int 
     if (world < 1 || world > AGX_MAX_PEERS || flag_slot < 0 || flag_slot > 3) return agx_set_error(AGX_E_INVALID, "obs_gather_wait: bad world / flag_slot");
     static bool carve_set = false;
     if (!carve_set) {
-        cudaFuncSetAttribute(obs_gather_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        agx_set_coresident_carveout(obs_gather_wait_kernel);
         carve_set = true;
     }
     obs_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags + flag_slot * AGX_MAX_PEERS, world, epoch, error_word);

@@ -339,6 +339,19 @@ class Hp1Engine:
             g.push(self._buf.obs, epoch, slot, stream=self._stream())  # two-launch path: plain stream order
         self.gathered_obs = g.outs[slot]
 
+    CHAIN_REBASE_STEPS = 1 << 30  # the kernel's step index, flags and per-tile counters are 32-bit: rebased long before they wrap (~3 h at 10 us / step)
+
+    def _rebase_chain(self):
+        """zero the chained step's counters at a quiet point (stream drained, pushes finished) and restart the step index at 0"""
+        if self._gather is not None:
+            self._gather.fence()
+        torch.cuda.current_stream(self.device).synchronize()
+        err = int(self.any_reset[2].item())
+        self.tile_sync.zero_()
+        self.any_reset[4:].zero_()
+        self.any_reset[2] = err
+        self._chain_T = 0
+
     def check(self):
         """Synchronise the current stream and raise if a bounded in-kernel wait of the chained step expired (AGX_E_TIMEOUT)."""
         _lib.check(self.lib.agx_hp1_check(self._buf_ref, self._stream()), "agx_hp1_check")
@@ -391,6 +404,8 @@ class Hp1Engine:
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
         chained = self._chain_counts and mid_event is None  # which path the library takes for this launch
+        if chained and self._chain_T >= self.CHAIN_REBASE_STEPS:
+            self._rebase_chain()
         g = self._gather
         if g is not None and chained:
             # gate (ring slot free?) + step + push of its rows: one C call, three launches

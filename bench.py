@@ -679,7 +679,9 @@ def run_hp2_config(dev, world, rank, *, label, metric, E, K, cfg, frames, extent
         "metric": metric, "value": world * rays * frames / sec, "unit": "rays/s", "workload": label, "envs_per_gpu": E, "image": [H, W],
         "objects_per_env": K, "triangles_per_env": K * 12, "frames": frames, "ms_per_frame": sec * 1e3 / frames, "hit_fraction": hit_frac,
         "scene_update_ms_all_envs": build_ms, "gpu_launches": frames, "n_gpus": world, "scaling": "weak",
-        "traversal": "tile path (scene staged into shared memory by TMA bulk copies)" if scene.P <= 128 else "per-ray BVH traversal from L2 (scene larger than shared memory)",
+        "traversal": ("tile path, scene staged into shared memory by TMA bulk copies" if scene.P <= 128 else
+                      ("tile path, object records in shared memory + candidate slabs from L2 (scene larger than shared memory)" if cfg.sensor_type != "lidar"
+                       else "per-ray BVH traversal" + (" from shared memory" if scene.P * 12 * 48 < 200000 else " from L2"))),
         "roofline": {"bound": "hbm (nominal: FP32 traversal / intersection issue binds, see DESIGN 6)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_frame": out_bytes + scene_bytes,
                      "note": "8 B/ray written (depth or range + segmentation) + every env's scene (48-byte triangle slabs + BVH) read once per frame"},
@@ -847,10 +849,25 @@ def run_nav_task(dev, world, rank, args):
     sec = float(t.item())
     env = task.sim_env
     rays = N * env.sensor.c.height * env.sensor.c.width if getattr(env, "sensor", None) is not None else 0
+    # where the env step goes: the three device-side stages alone (CUDA events), the rest is the task's torch / host code
+    def stage_ms(fn, reps=10):
+        fn()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        return a0.elapsed_time(a1) / reps
+    act_t = task.action_transformation_function(acts[0])
+    breakdown = {"physics_x10_plus_collision_ms": stage_ms(lambda: env.step(actions=act_t)), "render_depth_ms": stage_ms(lambda: env.render()),
+                 "vae_encode_ms": stage_ms(task.process_image_observation)}
     res = {"metric": "env-steps/sec (navigation_task: lmf2, env_with_obstacles, 135x240 depth camera + VAE, 10 physics sub-steps)",
            "value": world * N * K / sec, "unit": "env-steps/s", "envs_per_gpu": N, "ms_per_env_step": sec * 1e3 / K, "steps": K,
            "rays_per_s_inside": world * rays * K / sec, "construction_s": build_s,
-           "step_mode": getattr(env, "step_mode", "launch per kernel"), "timing": "host wall clock around K x task.step, synchronised"}
+           "step_mode": getattr(env, "step_mode", "launch per kernel"), "breakdown": breakdown,
+           "timing": "host wall clock around K x task.step, synchronised"}
     task.close()
     return res
 
