@@ -89,3 +89,39 @@ def test_sharded_oracle_equals_single_process(n_global):
     for _ in range(3):
         obs, *_ = O.position_task_step(model, st, acts, torch.zeros(n_global, 3))
     assert np.array_equal(gathered, obs.numpy())  # sharding changes nothing, bit for bit
+
+
+def test_task_shard_spec_and_registry_args(monkeypatch):
+    """host side of the env-sharded task API (task/base_task.py): where world / rank come from, and make_task(..., args=) merging into
+    task_config.args without touching the registered defaults' other keys"""
+    import types
+
+    from aerial_gym_simulator_b200.task.base_task import BaseTask
+
+    class T(BaseTask):
+        reset = reset_idx = step = render = close = lambda self, *a, **k: None
+
+    mk = lambda args: T(types.SimpleNamespace(seed=1, args=args))
+    assert mk(None).shard_spec() == (1, 0, False)
+    assert mk({"world_size": 4, "rank": 3}).shard_spec() == (4, 3, False)
+    assert mk({"world_size": 2, "loopback": True}).shard_spec() == (2, 0, True)
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    monkeypatch.setenv("RANK", "5")
+    assert mk({"shard": "torchrun"}).shard_spec() == (8, 5, False)
+    t = mk({"world_size": 1})
+    assert t.init_sharding(16, 13, "cpu") is None and t.obs_gather is None  # unsharded: nothing is built
+    with pytest.raises(ValueError, match="CUDA"):
+        mk({"world_size": 2, "rank": 0}).init_sharding(16, 13, "cpu")
+
+    from aerial_gym_simulator_b200.registry._core import TaskRegistry
+
+    seen = {}
+
+    class Fake:
+        def __init__(self, cfg, **kw):
+            seen["args"] = dict(cfg.args)
+
+    reg = TaskRegistry()
+    reg.register_task("fake", Fake, types.SimpleNamespace(args={"reset_rng": "device"}))
+    reg.make_task("fake", args={"world_size": 2, "rank": 1})
+    assert seen["args"] == {"reset_rng": "device", "world_size": 2, "rank": 1}
