@@ -384,6 +384,29 @@ def run_ours(args):
         dist.all_reduce(hot_ms, op=dist.ReduceOp.MAX)
     value_hot = world * N * K / (float(hot_ms.item()) * 1e-3)
 
+    # ---- the same rotating loop on engines configured like the task API's (EnvManager passes materialize_derived=True: the five
+    # derived-state arrays of BaseMultirotor.update_states, 64 B/env, are written every step) -- N = 1 only, no gather ----------------
+    value_api = None
+    if world == 1:
+        api_engines = []
+        for rep in range(R):
+            e = Hp1Engine(spec, N, dev, seed=1 + rep, env_id_offset=rank * N, device_rng_reset=True, strict_stale_obs=True, materialize_derived=True)
+            e.reset(torch.ones(N, dtype=torch.bool, device=dev))
+            e.refresh()
+            e.sim_steps.copy_((torch.arange(N, device=dev) % 500).int())
+            api_engines.append(e)
+        for i in range(R):
+            api_engines[i].position_task_step(acts[i % 8])
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for i in range(K):
+            api_engines[i % R].position_task_step(acts[i % 8])
+        b1.record(stream)
+        barrier()
+        value_api = N * K / (b0.elapsed_time(b1) * 1e-3)
+        del api_engines
+
     # ---- e2e: the call a user makes -- task_registry.make_task(...).step(actions) -- with HOST
     # buffers: pinned actions in, obs / reward / terminations / truncations out, every step ---------
     import aerial_gym_simulator_b200.task  # noqa: F401  (registers tasks)
@@ -519,6 +542,7 @@ def run_ours(args):
             "config": workload_config(world, {"envs_per_gpu": N, "global_envs": N * world,
                                               "obs_all_gather": (args.gather if world > 1 else None)}),
             "value_hot_l2": value_hot,
+            "value_api_config": value_api,
             "value_obs_gather_sync": value_sync,
             "obs_gather_check": gather_check,
             "wall_s_timed_region": t_wall,
