@@ -15,7 +15,8 @@ UNITS = [
     ("agx_common.cu", []),
     # hp1: 2-ulp division / sqrt (no slow-path branches): the step is instruction-fetch bound at
     # 65,536 envs (profiles/hp1_step_r1.md: stall_no_instruction dominates), every instruction counts
-    ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
+    # AGX_HP1_NOINLINE_TRIG: one shared out-of-line sincosf instead of seven inlined copies (same function, same bits): -2..5 % step time
+    ("hp1.cu", ["-prec-div=false", "-prec-sqrt=false", "-DAGX_HP1_NOINLINE_TRIG"]),  # AGX_FAST_TRIG measured: -7% time, 3x parity error -> off
     ("hp1_aux.cu", []),
     ("lidar_nav.cu", []),
     # device-RNG units: no FMA contraction, so "lo + (hi - lo) u" and the noise model round like their numpy oracles

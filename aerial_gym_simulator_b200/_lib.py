@@ -50,7 +50,7 @@ _HP1_BUF_FIELDS = [
     "root_state", "motor_thrust", "sim_steps", "actions", "disturbance", "dist_counter", "dist_offset_", "target_position",
     "tau_inc", "tau_dec", "k_thrust", "K_pos", "K_vel", "K_rot", "K_angvel", "bounds_min", "bounds_max",
     "euler", "vehicle_orientation", "vehicle_linvel", "body_linvel", "body_angvel", "body_wrench",
-    "obs", "reward", "terminations", "truncations", "reset_mask", "any_reset", "episode_count", "fresh_vel", "tile_sync",
+    "obs", "reward", "terminations", "truncations", "reset_mask", "any_reset", "episode_count", "fresh_vel", "publish_ctr", "tile_sync",
 ]
 
 

@@ -258,8 +258,10 @@ AGX_HP1_RESET_FN void reset_one_env(const AgxHp1Config& cfg, const AgxHp1Buffers
 //   any_reset[4 + (T & 3)]        u32 flag of step T: raised = holds T + 1 (monotonic, never cleared)
 //   any_reset[8 + 2 * (T & 3)]    u64 arrivals of the steps = T mod 4 (cumulative, never cleared): "this warp's physics and reset
 //                                 decision are done" -- in the rare no-reset-yet case counted BEFORE the observation is written
-//   any_reset[16 + 2 * (T & 3)]   u64 published tiles of the steps = T mod 4 (cumulative): "this tile's state, observation, reward
-//                                 and flags are in memory" -- what a consumer outside the kernel (agx_obs_gather_push) waits on
+//   publish_ctr[T & 3]            u64 published tiles of the steps = T mod 4 (cumulative; optional, on a cache line of its own --
+//                                 the arrival line is hammered by 2048 atomics and their pollers per step, a second atomic per warp
+//                                 on it cost the dependent-chain loop 2.5 us): "this tile's state, observation, reward and flags
+//                                 are in memory" -- what a consumer outside the kernel (agx_obs_gather_push) waits on
 //   tile_sync[tile], tile_sync[n_tiles + tile]   claim / done counters of the tile
 // (3) Multi-GPU: the step kernel never touches NVLink and never waits for the gather.  With an observation all-gather attached
 // (agx_obs_gather_push, p2p_allgather.cu, on side streams) buf.obs is one slot of a ring the push kernels read asynchronously; the
@@ -300,47 +302,31 @@ hp1_step_kernel(const __grid_constant__ AgxHp1Config cfg, const __grid_constant_
     if constexpr (COOP) {
         const int my_tile = blockIdx.x * kWarpsPerBlock + warp;
         const bool has_tile = my_tile < n_tiles;
-        // The claim, the tile's done-counter and the four arrival counters are fetched TOGETHER (one memory round trip instead of
-        // three in a row: the prologue is pure latency on the warp's critical path).  The two speculative reads are relaxed; once the
-        // claim says which step this is they are checked, and if they already show what the step needs (the steady state) a
-        // gpu-scope fence turns them into acquires.  Otherwise the warp falls back to the acquire spins.
-        uint32_t done_spec = 0;
-        unsigned long long arr_spec[4] = {0ull, 0ull, 0ull, 0ull};
-        const uint32_t* done = buf.tile_sync + n_tiles + (has_tile ? my_tile : 0);
-        const unsigned long long* arrivals = reinterpret_cast<const unsigned long long*>(buf.any_reset + 8);
-        if (has_tile && lane == 0) {
-            step_T = atomicAdd(buf.tile_sync + my_tile, 1u);  // claim: which step of this tile am I?
-            done_spec = ld_relaxed_gpu_u32(done);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) arr_spec[k] = ld_relaxed_gpu_u64(arrivals + k);
-        }
+        // (Round 2 tried fetching the tile's done-counter and the four arrival counters together with the claim -- one round trip
+        // instead of three.  Measured (profiles/hp1_bisect_r2i.jsonl): 2048 extra loads per step on the line the arrival atomics
+        // hammer made the dependent-chain loop 4 us SLOWER; the acquire spins below touch that line only when they must.)
+        if (has_tile && lane == 0) step_T = atomicAdd(buf.tile_sync + my_tile, 1u);  // claim: which step of this tile am I?
         step_T = __shfl_sync(0xffffffffu, step_T, 0);
         __syncthreads();  // every warp of the CTA holds its claim before the CTA lets the next launch in
         // programmatic dependent launch: once every CTA of this grid is here, the NEXT step's CTAs may be scheduled
         asm volatile("griddepcontrol.launch_dependents;" ::"r"(step_T) : "memory");
         if (has_tile) {
             if (lane == 0) {
-                bool ready = done_spec == step_T;  // this tile's previous step has published its state
-                unsigned long long want2 = 0ull;
-                const uint32_t P = step_T - 2u;
+                const uint32_t* done = buf.tile_sync + n_tiles + my_tile;
+                // this tile's previous step has published its state
+                spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset, 1 | (int)(step_T << 4));
                 if (step_T >= 2u) {  // step T-2 complete everywhere: bounds the skew to two steps in flight
-                    want2 = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
-                    const unsigned sel = P & 3u;  // (selects, not a dynamically indexed local array)
-                    const unsigned long long a = sel == 0u ? arr_spec[0] : sel == 1u ? arr_spec[1] : sel == 2u ? arr_spec[2] : arr_spec[3];
-                    ready = ready && a >= want2;
-                }
-                if (ready) {
-                    __threadfence();  // relaxed reads + fence = acquire
-                } else {
-                    spin_until([&] { return ld_acquire_gpu_u32(done) == step_T; }, buf.any_reset, 1 | (int)(step_T << 4));
-                    if (step_T >= 2u) spin_until([&] { return ld_acquire_gpu_u64(arrivals + (P & 3u)) >= want2; }, buf.any_reset, 2 | (int)(step_T << 4));
+                    const uint32_t P = step_T - 2u;
+                    const unsigned long long* a2 = reinterpret_cast<const unsigned long long*>(buf.any_reset + 8) + (P & 3u);
+                    const unsigned long long want2 = (unsigned long long)(P / 4u + 1u) * (unsigned long long)n_tiles;
+                    spin_until([&] { return ld_acquire_gpu_u64(a2) >= want2; }, buf.any_reset, 2 | (int)(step_T << 4));
                 }
             }
             __syncwarp();
         }
         reset_flag = reinterpret_cast<uint32_t*>(buf.any_reset) + 4 + (step_T & 3u);
         arrive_ctr = reinterpret_cast<unsigned long long*>(buf.any_reset + 8) + (step_T & 3u);
-        publish_ctr = reinterpret_cast<unsigned long long*>(buf.any_reset + 16) + (step_T & 3u);
+        publish_ctr = buf.publish_ctr ? buf.publish_ctr + (step_T & 3u) : nullptr;
         arrive_target = (unsigned long long)(step_T / 4u + 1u) * (unsigned long long)n_tiles;
     }
     const uint32_t flag_tag = step_T + 1u;
@@ -437,7 +423,8 @@ AGX_HP1_MOTOR_UNROLL
                     const float* dp = buf.disturbance + (size_t)env * 6;
                     df = df + ld3cg(dp);
                     dtq = dtq + ld3cg(dp + 3);
-                } else if (buf.dist_counter) {  // the same draw, in the kernel: counter word from device memory (graph replays)
+                }
+                else if (!TASK && buf.dist_counter) {  // the same draw, in the kernel (physics-only launches: EnvManager's graph step); counter word from device memory
                     float d6[6];
                     disturbance_env((uint32_t)(cfg.env_id_offset + env), *buf.dist_counter + buf.dist_offset + (uint32_t)step, cfg.dist_prob, cfg.dist_max,
                                     (uint32_t)(cfg.dist_seed & 0xffffffffu), (uint32_t)(cfg.dist_seed >> 32), d6);
@@ -560,7 +547,7 @@ AGX_HP1_MOTOR_UNROLL
                 if (lane == 0) {
                     __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
                     if (!counted) atomicAdd(arrive_ctr, 1ull);
-                    atomicAdd(publish_ctr, 1ull);
+                    if (publish_ctr) atomicAdd(publish_ctr, 1ull);  // only with a consumer outside the kernel (observation gather)
                     st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
                 }
             }

@@ -232,6 +232,7 @@ class Hp1Engine:
         self.reset_mask = z(N, dt=torch.bool)
         self.any_reset = z(32, dt=torch.int32)
         self.tile_sync = z(2 * ((N + 31) // 32), dt=torch.int32)  # per-tile claim / done counters (chained steps)
+        self.publish_ctr = z(16, dt=torch.int64)  # [0..3] published-tile counters (a 128-byte line of their own), used while a gather is attached
         self.episode_count = z(N, dt=torch.int32)
         self.bounds_min = torch.tensor(spec.bounds_lower_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
         self.bounds_max = torch.tensor(spec.bounds_upper_range[0], dtype=torch.float32, device=dev).expand(N, -1).clone()
@@ -294,7 +295,7 @@ class Hp1Engine:
     def _sync_buffers(self):
         b = self._buf
         for name in _lib._HP1_BUF_FIELDS:
-            if name in ("actions", "disturbance", "dist_counter", "dist_offset_"):
+            if name in ("actions", "disturbance", "dist_counter", "dist_offset_", "publish_ctr"):
                 continue
             setattr(b, name, self._ptr(getattr(self, name, None)))
 
@@ -316,9 +317,14 @@ class Hp1Engine:
         if self._gather is not None and gather is None:
             self._gather.fence()
             self.obs, self._buf.obs = self._own_obs, self._own_obs.data_ptr()
+            self._buf.publish_ctr = None
         self._gather, self.gathered_obs = gather, None
         if gather is not None:
-            self._ready_base = self.any_reset.data_ptr() + 64  # four u64 published-tile counters (hp1.cu)
+            # four u64 published-tile counters on a line of their own, switched on only while a gather is attached; they must agree with
+            # the step index, so attaching is a quiet point: drain, zero them and restart the chain's step numbering
+            self._rebase_chain()
+            self._buf.publish_ctr = self.publish_ctr.data_ptr()
+            self._ready_base = self.publish_ctr.data_ptr()
             self._n_tiles = (self.N + 31) // 32
 
     def _arm_gather(self, chained):
@@ -349,6 +355,7 @@ class Hp1Engine:
         err = int(self.any_reset[2].item())
         self.tile_sync.zero_()
         self.any_reset[4:].zero_()
+        self.publish_ctr.zero_()
         self.any_reset[2] = err
         self._chain_T = 0
 

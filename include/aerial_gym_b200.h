@@ -105,7 +105,7 @@ typedef struct AgxHp1Buffers {
     /* inputs */
     const float* actions;     /* [N,num_actions] */
     const float* disturbance; /* [N,6] gated body-0 wrench or NULL (base_multirotor.py:213-234) */
-    const uint32_t* dist_counter; /* device u32 or NULL.  When `disturbance` is NULL and this is set, physics sub-step s of the launch
+    const uint32_t* dist_counter; /* device u32 or NULL (agx_hp1_physics_step only).  When `disturbance` is NULL and this is set, physics sub-step s of the launch
                                      draws its disturbance in the kernel with draw counter *dist_counter + dist_offset + s -- bit for bit
                                      what agx_disturbance_draw(counter = that value) would have put into `disturbance`.  The counter
                                      lives in device memory so that a CUDA graph of an env step (n physics launches with
@@ -139,12 +139,14 @@ typedef struct AgxHp1Buffers {
     int32_t* any_reset;       /* [32] device scratch, 16-byte aligned, zero-initialised by the caller once and then always
                                  used with the same num_envs: [0] flag + [1] block-arrival counter (two-launch path);
                                  [2] error word of the chained step's bounded waits (agx_hp1_check);
-                                 [4..7] per-step flags, [8..15] four 64-bit arrival counters, [16..23] four 64-bit published-tile
-                                 counters (single-launch path, hp1.cu) */
+                                 [4..7] per-step flags, [8..15] four 64-bit arrival counters (single-launch path, hp1.cu) */
     uint32_t* episode_count;  /* [N] device-RNG counter word, incremented per reset */
     float* fresh_vel;         /* [6][N] scratch (SoA): post-physics body lin/ang velocity, written by the fused step
                                  when the stale-observation quirk is on and no derived array is materialised; the
                                  conditional pass then only patches obs[:,7:13] instead of recomputing.  May be NULL. */
+    unsigned long long* publish_ctr; /* device u64[4] on a cache line of its own (zero-initialised once) or NULL: the single-launch step
+                                        bumps publish_ctr[T & 3] once per tile when the tile's outputs are in memory -- what
+                                        agx_obs_gather_push waits on (agx_hp1_task_step_is_chained) */
     uint32_t* tile_sync;      /* [2][ceil(N/32)] device scratch, zero-initialised once: per-tile claim / done counters that
                                  chain consecutive single-launch steps tile by tile (hp1.cu "chained steps").
                                  NULL = the step always takes the two-launch path. */
@@ -210,7 +212,7 @@ int agx_hp1_position_task_step_profiled(const AgxHp1Config* cfg, const AgxHp1Buf
 /* 1 when agx_hp1_position_task_step(cfg, buf) takes the single-launch path whose consecutive launches are chained per
  * 32-env tile (all CTAs of a step co-resident; device-RNG reset + strict stale observation + tile_sync given), 0 when it takes
  * the two-launch path, negative on error.  Step T (0-based count of such launches since tile_sync / any_reset were zeroed) is
- * complete -- observation included -- when the u64 at any_reset + 16 + 2 * (T & 3) has reached (T / 4 + 1) * ceil(N / 32):
+ * complete -- observation included -- when buf->publish_ctr[T & 3] has reached (T / 4 + 1) * ceil(N / 32):
  * that is the (ready_ctr, ready_target) pair agx_obs_gather_push waits on.  (Multi-GPU: the step kernel itself never
  * touches NVLink and never waits for the gather; `obs` is then one slot of a ring of observation buffers the caller rotates and
  * throttles with stream events, see agx_obs_gather_push.) */

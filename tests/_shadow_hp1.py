@@ -44,7 +44,7 @@ class ShadowHp1Engine:
         self.body_wrench = z(N, 6) if debug_wrench else None
         self._buf = _lib.AgxHp1Buffers()
         for name in _lib._HP1_BUF_FIELDS:
-            if name not in ("actions", "disturbance", "dist_counter", "dist_offset_"):
+            if name not in ("actions", "disturbance", "dist_counter", "dist_offset_", "publish_ctr"):
                 t = getattr(self, name, None)
                 setattr(self._buf, name, None if t is None else t.data_ptr())
 
