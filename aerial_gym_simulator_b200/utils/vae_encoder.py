@@ -55,12 +55,20 @@ class VAEImageEncoder(nn.Module):
             self.encoder.load_state_dict(clean)
             self.weights_loaded = True
         self.encoder.eval()
+        # CUDA: NHWC weights / activations and cuDNN's autotuner (cudnn.benchmark) -- the same convolutions, the fastest algorithm cuDNN
+        # has for each shape (the encoder is 83 % of a navigation_task env step at 1024 envs: bench.py navigation_task_e2e.breakdown)
+        self._cuda = torch.device(device).type == "cuda"
+        if self._cuda:
+            self.encoder.to(memory_format=torch.channels_last)
+            torch.backends.cudnn.benchmark = True
 
     @torch.no_grad()
     def encode(self, image_tensors):
         x = image_tensors.squeeze(0).unsqueeze(1)
         if tuple(self.config.image_res) != tuple(x.shape[-2:]):
             x = F.interpolate(x, tuple(self.config.image_res), mode=self.config.interpolation_mode)
+        if self._cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
         z = self.encoder(x)
         means, logvars = z[:, : self.latent_dim], z[:, self.latent_dim:]
         if not self.config.return_sampled_latent:
