@@ -70,7 +70,7 @@ class AgxHp1Buffers(C.Structure):
 class AgxObsGatherPush(C.Structure):
     _fields_ = [("local", fp), ("peer_bufs", fp), ("peer_flags", fp), ("world", C.c_int32), ("rank", C.c_int32),
                 ("bytes", C.c_uint64), ("epoch", C.c_uint32), ("max_ctas", C.c_int32), ("ready_ctr", fp), ("ready_target", C.c_uint64),
-                ("scratch", fp), ("error_word", fp), ("flag_slot", C.c_int32), ("pad_", C.c_int32), ("read_done", fp)]
+                ("scratch", fp), ("error_word", fp), ("flag_slot", C.c_int32), ("pad_", C.c_int32), ("read_done", fp), ("mc_buf", fp)]
 
 
 _HP1_DRAW_FIELDS = ["bounds_lo", "bounds_hi", "state", "K_pos", "K_vel", "K_rot", "K_angvel",

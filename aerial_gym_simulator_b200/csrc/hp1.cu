@@ -74,12 +74,13 @@ __device__ __forceinline__ bool spin_until(Pred ok, int32_t* any_reset, int code
     if (ok()) return true;
     volatile int32_t* err = any_reset + kErrWord;
     if (*err) return false;
-    const unsigned long long t0 = globaltimer_ns(), limit = g_hp1_spin_timeout_ns;
+    const long long t0 = clock64();
+    const long long limit = (long long)g_hp1_spin_timeout_ns * 2;  // ns -> SM cycles at <= 2 GHz; clock64 is monotonic per SM (%globaltimer may be re-synchronised and jump)
     unsigned polls = 0;
     while (!ok()) {
         if ((++polls & 255u) == 0u) {
             if (*err) return false;
-            if (globaltimer_ns() - t0 > limit) {
+            if (clock64() - t0 > limit) {
                 atomicCAS(any_reset + kErrWord, 0, code);
                 return false;
             }

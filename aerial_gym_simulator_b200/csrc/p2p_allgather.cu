@@ -84,12 +84,13 @@ __device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word, uint32_t
     if (ok()) return true;
     volatile uint32_t* err = err_word;
     if (*err) return false;
-    const unsigned long long t0 = globaltimer_ns(), limit = g_gather_spin_timeout_ns;
+    const long long t0 = clock64();
+    const long long limit = (long long)g_gather_spin_timeout_ns * 2;  // ns -> SM cycles at <= 2 GHz; clock64 is monotonic per SM (%globaltimer may be re-synchronised and jump)
     unsigned polls = 0;
     while (!ok()) {
         if ((++polls & 63u) == 0u) {
             if (*err) return false;
-            if (globaltimer_ns() - t0 > limit) {
+            if (clock64() - t0 > limit) {
                 atomicCAS(err_word, 0u, code);
                 return false;
             }
@@ -97,6 +98,11 @@ __device__ __forceinline__ bool spin_until(Pred ok, uint32_t* err_word, uint32_t
         __nanosleep(64);
     }
     return true;
+}
+
+// one 16-byte store to the NVSwitch multicast address: the switch writes it into every rank's copy of the buffer
+__device__ __forceinline__ void multimem_st_f4(float4* mc, float4 v) {
+    asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 constexpr int kPushThreads = 256;
@@ -128,6 +134,18 @@ obs_gather_push_kernel(const __grid_constant__ AgxObsGatherPush a, size_t n_vec)
     const int np = s_npeer;
     const size_t stride = (size_t)gridDim.x * kPushThreads;
     size_t i = (size_t)blockIdx.x * kPushThreads + threadIdx.x;
+    if (a.mc_buf) {  // NVSwitch multicast: one store per 16 bytes, whatever the world size (this rank's own copy is rewritten with the same bytes)
+        float4* mc = reinterpret_cast<float4*>(a.mc_buf) + (size_t)a.rank * n_vec;
+        for (; i + (kPushUnroll - 1) * stride < n_vec; i += kPushUnroll * stride) {
+            float4 v[kPushUnroll];
+#pragma unroll
+            for (int u = 0; u < kPushUnroll; ++u) v[u] = __ldcg(local + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < kPushUnroll; ++u) multimem_st_f4(mc + i + u * stride, v[u]);
+        }
+        for (; i < n_vec; i += stride) multimem_st_f4(mc + i, __ldcg(local + i));
+        i = n_vec;  // nothing left for the unicast loops
+    }
     for (; i + (kPushUnroll - 1) * stride < n_vec; i += kPushUnroll * stride) {
         float4 v[kPushUnroll];
 #pragma unroll

@@ -147,7 +147,10 @@ class PipelinedObsGather:
     buffer, rank 0 is this process; the protocol (ring, flags, counters) runs exactly as on several GPUs."""
 
     def __init__(self, local_count: int, feat: int, device, group=None, num_buffers: int = 4, max_ctas: int = 24,
-                 loopback_world: int = 0):
+                 loopback_world: int = 0, multicast: Optional[bool] = None):
+        """multicast: push through the NVSwitch multicast address of the ring buffers (`multimem.st`: every 16 bytes leave the GPU once,
+        the switch replicates) when the symmetric-memory rendezvous offers one; None = the AGX_GATHER_MULTICAST environment variable
+        (default on)"""
         import ctypes as C
 
         from . import _lib
@@ -162,7 +165,9 @@ class PipelinedObsGather:
             raise ValueError("shard bytes must be a multiple of 16")
         self.local_count, self.feat = local_count, feat
         i64 = lambda ptrs: torch.tensor(list(ptrs), dtype=torch.int64, device=self.device)
-        self._handles = []
+        self._handles, self.mc_ptrs = [], []
+        if multicast is None:
+            multicast = os.environ.get("AGX_GATHER_MULTICAST", "1") != "0"
         B = self.num_buffers
         if loopback_world:
             self.world, self.rank = int(loopback_world), 0
@@ -186,6 +191,7 @@ class PipelinedObsGather:
                 self.outs.append(o)
                 self.buf_ptrs.append(i64(h.buffer_ptrs))
                 self._handles.append(h)
+                self.mc_ptrs.append(int(getattr(h, "multicast_ptr", 0) or 0))
             self.flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
             self.flags.zero_()
             h = symm_mem.rendezvous(self.flags, group)
@@ -209,6 +215,8 @@ class PipelinedObsGather:
             a.bytes, a.max_ctas, a.flag_slot = self.bytes, self.max_ctas, b
             a.scratch, a.error_word = self.scratch[b].data_ptr(), self.error_word.data_ptr()
             a.read_done = self.read_done[b].data_ptr()
+            a.mc_buf = (self.mc_ptrs[b] or None) if (multicast and len(self.mc_ptrs) == B and all(self.mc_ptrs)) else None
+        self.multicast = bool(self._pushes[0][0].mc_buf)
             self._pushes.append((a, C.byref(a)))
         self.epoch = 0
         self._read_done_ptr = [self.read_done[b].data_ptr() for b in range(B)]

@@ -302,6 +302,11 @@ def run_ours(args):
         step(i)
     drain()
     barrier()
+    if gather is not None:  # a bounded wait that expired during warm-up is reported where it happened (the words are sticky)
+        w = int(gather.error_word.item())
+        ew = [hex(int(e_.any_reset[2].item())) for e_ in engines if int(e_.any_reset[2].item())]
+        if w or ew:
+            sys.stderr.write(f"[bench rank {rank}] after warm-up: gather error word {hex(w)}, engine error words {ew[:4]}\n")
 
     # ---- timed region: exactly K steps over rotating replicas ------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -330,13 +335,12 @@ def run_ours(args):
             got = gather.wait().clone()
             want = nccl_gather(e.obs).clone()
             okc = torch.tensor([int(torch.equal(got, want))], device=dev)
-            try:
-                gather.check()
-                for e_ in engines:
-                    e_.check()
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write(f"[bench rank {rank}] {exc}\n")
-                okc.zero_()
+            for chk in [gather.check] + [e_.check for e_ in engines]:
+                try:
+                    chk()
+                except Exception as exc:  # noqa: BLE001
+                    sys.stderr.write(f"[bench rank {rank}] {exc}\n")
+                    okc.zero_()
             dist.all_reduce(okc, op=dist.ReduceOp.MIN)
             gather_check = bool(okc.item())
             for i in range(R):
@@ -545,6 +549,7 @@ def run_ours(args):
             "value_api_config": value_api,
             "value_obs_gather_sync": value_sync,
             "obs_gather_check": gather_check,
+            "obs_gather_multicast": (bool(getattr(gather, "multicast", False)) if gather is not None else None),
             "wall_s_timed_region": t_wall,
             "host_enqueue_us_per_step": 1e6 * t_enqueue / K,
             "roofline": {"bound": "hbm", "kernel": "hp1_step_kernel<4,true,true> (the whole fused step is this one launch)", "achieved": achieved, "peak": peak,

@@ -547,6 +547,10 @@ typedef struct AgxObsGatherPush {
     int32_t pad_;
     uint32_t* read_done;   /* device uint32 of this ring slot or NULL: receives `epoch` (release, gpu scope) as soon as every CTA has
                               finished READING `local` -- before the NVLink drain; agx_obs_gather_gate waits on it */
+    void* mc_buf;          /* NVSwitch multicast address of the SAME gathered buffer (symmetric-memory multicast_ptr) or NULL.  When set,
+                              every 16 bytes leave this GPU ONCE (`multimem.st`) and the switch replicates them into all ranks' buffers:
+                              the push's store count and NVLink egress no longer grow with the world size (7x at 8 GPUs).  The flag
+                              words are still written peer by peer. */
 } AgxObsGatherPush;
 int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream);
 /* Ring-slot gate for a producer that runs ahead of its pushes: a one-warp kernel, launched with programmatic stream serialization

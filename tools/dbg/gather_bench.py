@@ -30,13 +30,24 @@ def run(gather, label):
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) * 1e3 / K], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         best = min(best, float(t))
-    if gather is not None: gather.check()
-    engines[0].check()
+    errs = []
+    for e in engines:
+        w = int(e.any_reset[2].item())
+        if w: errs.append(hex(w))
+    gerr = hex(int(gather.error_word.item())) if gather is not None else None
+    if errs or (gerr not in (None, "0x0")):
+        print(f"[rank {rank}] {label}: engine error words {errs[:4]} gather error word {gerr}", flush=True)
+        for e in engines: e.any_reset[2] = 0
+        if gather is not None: gather.error_word.zero_()
     if rank == 0:
         print(f"GATHER_BENCH world={world} {label}: {best:.2f} us/step  ({world * N / best * 1e6:.3e} env-steps/s, host {th * 1e6 / K:.1f} us/step, nvlink floor {(world - 1) * N * 52 / 900e9 * 1e6:.1f} us)", flush=True)
     for e in engines: e.attach_obs_gather(None)
-run(None, "no gather")
+FRESH = os.environ.get("FRESH", "0") == "1"  # attach the gather to engines that never stepped (their first steps are "no reset yet" steps)
+if not FRESH:
+    run(None, "no gather")
 for spec in sys.argv[1:]:
     ctas, nb = (int(x) for x in (spec.split("x") + ["4"])[:2])
-    run(PipelinedObsGather(N, 13, dev, num_buffers=nb, max_ctas=ctas), f"push ctas={ctas} ring={nb}")
+    for mc in ((True, False) if os.environ.get("MC_AB", "0") == "1" else (None,)):
+        gth = PipelinedObsGather(N, 13, dev, num_buffers=nb, max_ctas=ctas, multicast=mc)
+        run(gth, f"push ctas={ctas} ring={nb} multicast={gth.multicast}")
 dist.destroy_process_group()
