@@ -216,8 +216,8 @@ class PipelinedObsGather:
             a.scratch, a.error_word = self.scratch[b].data_ptr(), self.error_word.data_ptr()
             a.read_done = self.read_done[b].data_ptr()
             a.mc_buf = (self.mc_ptrs[b] or None) if (multicast and len(self.mc_ptrs) == B and all(self.mc_ptrs)) else None
-        self.multicast = bool(self._pushes[0][0].mc_buf)
             self._pushes.append((a, C.byref(a)))
+        self.multicast = bool(self._pushes[0][0].mc_buf)
         self.epoch = 0
         self._read_done_ptr = [self.read_done[b].data_ptr() for b in range(B)]
         self._err_ptr = self.error_word.data_ptr()
