@@ -191,6 +191,17 @@ obs_gather_gate_kernel(const uint32_t* __restrict__ read_done, uint32_t need_epo
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// "ready" gate on the push's own stream: ONE warp waits for the producer step's published-tile counter, then lets the push kernel
+// behind it in (programmatic stream serialization).  The push's CTAs are therefore never resident while they would only wait: beside
+// a step that needs its whole grid co-resident there are at most a few one-warp gates, not 96 spinning 256-thread CTAs.
+__global__ void __launch_bounds__(32)
+obs_gather_ready_kernel(const unsigned long long* __restrict__ ready_ctr, unsigned long long ready_target, uint32_t* error_word, uint32_t epoch) {
+    if (threadIdx.x == 0) spin_until([&] { return ld_acquire_gpu_u64(ready_ctr) >= ready_target; }, error_word, (epoch << 8) | 1u);
+    __syncwarp();
+    __threadfence();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(32)
 obs_gather_wait_kernel(const uint32_t* __restrict__ my_flags, int world, uint32_t epoch, uint32_t* error_word) {
     const int q = threadIdx.x;
@@ -226,6 +237,29 @@ extern "C" int agx_obs_gather_push(const AgxObsGatherPush* a, void* stream) {
         agx_set_coresident_carveout(obs_gather_push_kernel);
         agx_set_coresident_carveout(obs_gather_wait_kernel);
         carve_set = true;
+    }
+    if (a->ready_ctr) {
+        // one-warp gate first, the push itself as its programmatic dependent with nothing left to wait for
+        static bool gate_carve = false;
+        if (!gate_carve) {
+            agx_set_coresident_carveout(obs_gather_ready_kernel);
+            gate_carve = true;
+        }
+        obs_gather_ready_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->ready_ctr, a->ready_target, a->error_word, a->epoch);
+        int rc = agx_check_launch("obs_gather_ready_kernel");
+        if (rc) return rc;
+        AgxObsGatherPush b = *a;
+        b.ready_ctr = nullptr;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)ctas);
+        lc.blockDim = dim3(kPushThreads);
+        lc.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        return agx_check_cuda(cudaLaunchKernelEx(&lc, obs_gather_push_kernel, b, n_vec), "obs_gather_push_kernel");
     }
     obs_gather_push_kernel<<<(int)ctas, kPushThreads, 0, (cudaStream_t)stream>>>(*a, n_vec);
     return agx_check_launch("obs_gather_push_kernel");

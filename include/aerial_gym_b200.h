@@ -519,8 +519,9 @@ int agx_p2p_allgather(const void* local, void* const* peer_bufs, uint32_t* const
  * CTAs while the next steps compute, the WAIT (receiver side) runs on the consumer's stream just before the gathered buffer is
  * read.  Neither is on the step kernel's critical path.
  *
- * agx_obs_gather_push: optionally spin until *ready_ctr >= ready_target (the step that produces `local` has published it: see
- * agx_hp1_task_step_is_chained; NULL = `local` is already complete in stream order), copy the `bytes` (multiple of 16) of `local`
+ * agx_obs_gather_push: optionally wait until *ready_ctr >= ready_target (the step that produces `local` has published it: see
+ * agx_hp1_task_step_is_chained; NULL = `local` is already complete in stream order) -- a ONE-WARP gate kernel does the waiting and the
+ * push kernel is its programmatic dependent, so no push CTA is resident while it would only wait --, copy the `bytes` (multiple of 16) of `local`
  * into slot `rank` of every rank's gathered buffer (peer_bufs[p] + rank * bytes; the own slot is skipped when `local` already is
  * that slot), then -- when all stores of this rank have been performed at system scope -- publish `epoch` into flag word
  * peer_flags[p][flag_slot * AGX_MAX_PEERS + rank] on every rank p.  The kernel never waits for a peer.  Pushes into different ring
