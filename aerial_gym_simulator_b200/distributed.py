@@ -149,8 +149,8 @@ class PipelinedObsGather:
     def __init__(self, local_count: int, feat: int, device, group=None, num_buffers: int = 4, max_ctas: int = 24,
                  loopback_world: int = 0, multicast: Optional[bool] = None):
         """multicast: push through the NVSwitch multicast address of the ring buffers (`multimem.st`: every 16 bytes leave the GPU once,
-        the switch replicates) when the symmetric-memory rendezvous offers one; None = the AGX_GATHER_MULTICAST environment variable
-        (default on)"""
+        the switch replicates) when the symmetric-memory rendezvous offers one; None = the AGX_GATHER_MULTICAST environment variable if
+        set, else on for a world of 3 or more ranks"""
         import ctypes as C
 
         from . import _lib
@@ -166,8 +166,9 @@ class PipelinedObsGather:
         self.local_count, self.feat = local_count, feat
         i64 = lambda ptrs: torch.tensor(list(ptrs), dtype=torch.int64, device=self.device)
         self._handles, self.mc_ptrs = [], []
-        if multicast is None:
-            multicast = os.environ.get("AGX_GATHER_MULTICAST", "1") != "0"
+        if multicast is None:  # measured (profiles/gather_bench_*gpu_r2*.log): 2 GPUs 14.9 vs 13.8 us/step (slower), 4 GPUs 22.3 vs 25.5, 8 GPUs 39.9 vs 49.1
+            env = os.environ.get("AGX_GATHER_MULTICAST")
+            multicast = (env != "0") if env is not None else None
         B = self.num_buffers
         if loopback_world:
             self.world, self.rank = int(loopback_world), 0
@@ -215,7 +216,8 @@ class PipelinedObsGather:
             a.bytes, a.max_ctas, a.flag_slot = self.bytes, self.max_ctas, b
             a.scratch, a.error_word = self.scratch[b].data_ptr(), self.error_word.data_ptr()
             a.read_done = self.read_done[b].data_ptr()
-            a.mc_buf = (self.mc_ptrs[b] or None) if (multicast and len(self.mc_ptrs) == B and all(self.mc_ptrs)) else None
+            use_mc = (self.world >= 3) if multicast is None else bool(multicast)
+            a.mc_buf = (self.mc_ptrs[b] or None) if (use_mc and len(self.mc_ptrs) == B and all(self.mc_ptrs)) else None
             self._pushes.append((a, C.byref(a)))
         self.multicast = bool(self._pushes[0][0].mc_buf)
         self.epoch = 0
