@@ -30,4 +30,9 @@ def run(R, lb, ctas=24, nb=4, steps=200):
     err = hex(gth.error_word.item()) if gth is not None else None
     engerr = [hex(e.any_reset[2].item()) for e in engines if e.any_reset[2].item()]
     print(f"replicas={R} loopback_world={lb} ctas={ctas} ring={nb}: {e0.elapsed_time(e1) * 1e3 / steps:.2f} us/step, host enqueue {th * 1e6 / steps:.2f} us/step, gather err {err}, engine errs {engerr}", flush=True)
-run(1, 0); run(16, 0); run(1, 2); run(16, 2); run(16, 4); run(16, 8); run(16, 2, ctas=8); run(16, 2, ctas=48, nb=2)
+import os
+if os.environ.get("ONLY") == "ncu":
+    _lib.check(_lib.load().agx_set_spin_timeout_ms(120000), "t")
+    run(16, 2, steps=60)
+else:
+    run(1, 0); run(16, 0); run(1, 2); run(16, 2); run(16, 4); run(16, 8); run(16, 2, ctas=8); run(16, 2, ctas=48, nb=2)

@@ -19,6 +19,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:hp2_
 E=256 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hp2_cast_kernel -s 1 -c 1 \
     -f -o gpurun_out/hp2_cast_cfg3_$TAG python tools/dbg/cfg3_once.py > gpurun_out/ncu_hp2_cfg3_$TAG.log 2>&1
 # 4. the observation gather's push kernel beside the chained steps (one GPU, emulated world of 2: the stores go to local buffers)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:obs_gather_push_kernel -s 40 -c 1 \
+ONLY=ncu timeout 600 ncu --set full --clock-control none --import-source on -k regex:obs_gather_push_kernel -s 40 -c 1 \
     -f -o gpurun_out/obs_push_$TAG python tools/dbg/dbg_gather_loop.py > gpurun_out/ncu_push_$TAG.log 2>&1
 ls -la gpurun_out | tail -8
