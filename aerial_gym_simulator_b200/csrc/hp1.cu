@@ -37,6 +37,10 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -546,10 +550,14 @@ AGX_HP1_MOTOR_UNROLL
                 store_rows13(buf.obs, env0, n_valid, tile, lane, o, vec_ok);
                 __syncwarp();
                 if (lane == 0) {
-                    __threadfence();  // the tile's stores (and a raised flag) are visible before the arrival / the publish
+                    // ONE release fence (MEMBAR.ALL.GPU), then relaxed operations: the tile's stores (and a raised flag) are visible before
+                    // the arrival, the publish count and the done-counter (fence-based release; the consumers acquire).  Round 1 had
+                    // __threadfence() (MEMBAR.SC + L1 invalidate) followed by st.release (a second MEMBAR): ncu r2 showed `membar` as the
+                    // second largest stall of the kernel.
+                    fence_acq_rel_gpu();
                     if (!counted) atomicAdd(arrive_ctr, 1ull);
                     if (publish_ctr) atomicAdd(publish_ctr, 1ull);  // only with a consumer outside the kernel (observation gather)
-                    st_release_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
+                    st_relaxed_gpu_u32(buf.tile_sync + n_tiles + t, flag_tag);  // this tile may start step T + 1
                 }
             }
         }

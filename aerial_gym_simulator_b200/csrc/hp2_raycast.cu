@@ -776,10 +776,14 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         const int32_t* leaf = g_leaf;
         const float* tris = g_tris;
         const float* obb = g_obb;
+        bool fresh_scene = false;  // uniform: this item staged a new scene (its leading barrier also retired the previous item's records)
         if (SMEM) {
             if (e != staged_env) {
-                __syncthreads();  // everyone is done with the previous scene
+                __syncthreads();  // everyone is done with the previous scene (and with the previous item's records)
                 if (threadIdx.x == 0) {
+                    // record count of the new item: written before the mbarrier arrive (release) below, read by the others after their
+                    // mbar_wait (acquire) -- no CTA barrier of its own (ncu r1/r2: `barrier` was the top stall of this kernel)
+                    if (TILE) s_nrec = 0;
                     // order prior generic-proxy smem reads before the async-proxy writes
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_expect_tx(&s_bar, node_bytes + leaf_bytes + tri_bytes + obb_bytes);
@@ -791,6 +795,7 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
                 mbar_wait(&s_bar, parity);
                 parity ^= 1u;
                 staged_env = e;
+                fresh_scene = true;
             }
             nodes = s_nodes;
             leaf = s_leaf;
@@ -831,9 +836,11 @@ hp2_cast_kernel(const __grid_constant__ AgxHp2Scene sc, const __grid_constant__ 
         // work item walks the BVH per ray as before.
         constexpr bool tile_path = TILE;
         if constexpr (tile_path) {  // per-item object records (depend on the sensor origin)
-            __syncthreads();        // previous item's records are no longer read
-            if (threadIdx.x == 0) s_nrec = 0;
-            __syncthreads();
+            if (!fresh_scene) {     // same scene as the previous item (row blocks of a large image), or no staging at all
+                __syncthreads();    // previous item's records are no longer read
+                if (threadIdx.x == 0) s_nrec = 0;
+                __syncthreads();
+            }
             v3 fr[4];
             bool have_frustum = false;
             float item_far = sn.far_plane;
