@@ -25,6 +25,13 @@ def _extract_kernel_blocks():
             raise RuntimeError(f"marker AGX_SHADOW_BEGIN({name}) not found in hp1.cu")
         with open(os.path.join(os.path.dirname(LIB), f"hp1_{name}.inc"), "w") as f:
             f.write(m.group(1) + "\n")
+    # the instantiation table (which controller x motor-model combinations have a compile-time specialised kernel): the shadow
+    # dispatches over the same list, so the CPU suite can run the SPECIALISED text of hp1_core.cuh as well as the dynamic one
+    m = re.search(r"(#define AGX_SPEC_FLAGS_ALL[^\n]*\n#ifndef AGX_HP1_NO_SPEC\n.*?\n#endif)", txt, re.S)
+    if not m:
+        raise RuntimeError("instantiation table (AGX_HP1_SPEC_LIST) not found in hp1.cu")
+    with open(os.path.join(os.path.dirname(LIB), "hp1_spec_list.inc"), "w") as f:
+        f.write(m.group(1) + "\n")
 
 
 def build(force=False):
@@ -81,6 +88,10 @@ def load():
         lib.shadow_s2r_obs.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
         lib.shadow_disturbance_draw.restype = C.c_int
         lib.shadow_disturbance_draw.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        lib.shadow_hp1_set_specialised.restype = None
+        lib.shadow_hp1_set_specialised.argtypes = [C.c_int]
+        lib.shadow_hp1_spec_id.restype = C.c_int
+        lib.shadow_hp1_spec_id.argtypes = [C.POINTER(A.AgxHp1Config)]
         lib.shadow_hp1_position_reward.restype = C.c_int
         lib.shadow_hp1_position_reward.argtypes = [C.POINTER(A.AgxHp1Config), C.c_int] + [C.c_void_p] * 8
         _lib = lib

@@ -26,6 +26,17 @@ from tests._shadow_hp1 import ShadowHp1Engine
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+@pytest.fixture(params=["dynamic", "specialised"])
+def spec_text(request):
+    """which text of hp1_core.cuh's templates runs: HpSpec<-1> (every switch read from the launch constants) or the compile-time
+    specialised instantiation hp1.cu's pick_kernel would launch for the configuration (same table, tests/_shadow.py lifts it)"""
+    from tests import _shadow
+    lib = _shadow.load()
+    lib.shadow_hp1_set_specialised(int(request.param == "specialised"))
+    yield request.param
+    lib.shadow_hp1_set_specialised(0)
+
+
 def _derived_close(eng, d, tag):
     H.assert_close(eng.euler, d["euler"], f"{tag} euler", scale=np.pi)
     H.assert_close(eng.vehicle_orientation, d["vehicle_orientation"], f"{tag} vehicle q", scale=1.0)
@@ -76,11 +87,37 @@ def test_multi_substep_matches_oracle_and_single_steps():
     assert torch.equal(eng1.root_state, eng.root_state)
 
 
+@pytest.mark.parametrize("case", H.ALL_CASES)
+def test_specialised_and_dynamic_text_agree_bit_for_bit(case):
+    """HpSpec only removes branches: the specialised instantiation of a configuration and the generic text give the same bits
+    (10 fused sub-steps, per-env parameters); and the shipped robots' configurations do have an instantiation."""
+    import ctypes as C
+    spec = H.spec_for(case)
+    N = 512
+    root, actions, params = H.random_inputs(spec, N, seed=11 + sum(map(ord, case)) % 997)
+    out = []
+    for on in (0, 1):
+        eng = ShadowHp1Engine(spec, N, physics_steps=10, debug_wrench=True)
+        eng.lib.shadow_hp1_set_specialised(on)
+        try:
+            H.load_engine_state(eng, root, params)
+            sid = eng.lib.shadow_hp1_spec_id(C.byref(eng.cfg))
+            eng.physics_step(actions)
+        finally:
+            eng.lib.shadow_hp1_set_specialised(0)
+        out.append((sid, eng.root_state.clone(), eng.motor_thrust.clone(), eng.body_wrench.clone(), eng.body_angvel.clone()))
+    assert out[0][0] == -1
+    if case in ("quad_attitude", "quad_velocity", "quad_position", "quad_acceleration"):
+        assert out[1][0] >= 0, "the base_quadrotor controllers have specialised kernels"
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert torch.equal(a, b)
+
+
 STEP_FILES = sorted(glob.glob(os.path.join(GOLD, "hp1_step_*.npz")))
 
 
 @pytest.mark.parametrize("path", STEP_FILES, ids=[os.path.basename(p)[9:-4] for p in STEP_FILES])
-def test_device_code_matches_reference_golden(path):
+def test_device_code_matches_reference_golden(path, spec_text):
     """the kernels' arithmetic against outputs of the REFERENCE'S OWN code: derived states and motor thrusts directly, link
     forces / torques through the W f reduction (Appendix B)"""
     z = np.load(path)
@@ -94,7 +131,7 @@ REG_FILES = sorted(glob.glob(os.path.join(GOLD, "hp1_regstep_*.npz")))
 
 
 @pytest.mark.parametrize("path", REG_FILES, ids=[os.path.basename(p)[12:-4] for p in REG_FILES])
-def test_registry_built_spec_matches_reference_golden(path):
+def test_registry_built_spec_matches_reference_golden(path, spec_text):
     """as above, for 13 more robot x controller pairs (magpie, x500, lmf1, lmf2, tinyprop, base_random, morphy_stiff, octarotor;
     steering-angle controller), with the spec built by the PRODUCT's registries / config mirror / URDF pipeline"""
     z = np.load(path)
@@ -140,7 +177,7 @@ def _philox_draws(seed, gids, episodes, M):
 
 @pytest.mark.parametrize("case", ["quad_attitude", "octa_velocity"])
 @pytest.mark.parametrize("strict,coop", [(True, False), (True, True), (False, True)], ids=["strict-scalar_rng", "strict-coop_rng", "fresh-coop_rng"])
-def test_fused_position_task_step(case, strict, coop):
+def test_fused_position_task_step(case, strict, coop, spec_text):
     spec = H.spec_for(case)
     model = H.oracle_model_from_spec(spec)
     N, M, seed, off = 333, spec.num_motors, 99, 1000
