@@ -48,16 +48,19 @@ class ShadowHp1Engine:
                 t = getattr(self, name, None)
                 setattr(self._buf, name, None if t is None else t.data_ptr())
 
-    def _set_inputs(self, actions, disturbance, physics_steps):
+    def _set_inputs(self, actions, disturbance, physics_steps, dist_counter=None, dist_offset=0):
         assert actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.N, self.cfg.num_actions)
-        self._keep = (actions, disturbance)
+        self._keep = (actions, disturbance, dist_counter)
         self._buf.actions = actions.data_ptr()
         self._buf.disturbance = None if disturbance is None else disturbance.contiguous().data_ptr()
+        # as Hp1Engine.physics_step: the in-kernel draw only when no explicit [N,6] tensor is given
+        self._buf.dist_counter = None if (dist_counter is None or disturbance is not None) else dist_counter.data_ptr()
+        self._buf.dist_offset = int(dist_offset)
         if physics_steps is not None:
             self.cfg.physics_steps = int(physics_steps)
 
-    def physics_step(self, actions, disturbance=None, physics_steps=None):
-        self._set_inputs(actions, disturbance, physics_steps)
+    def physics_step(self, actions, disturbance=None, physics_steps=None, dist_counter=None, dist_offset=0):
+        self._set_inputs(actions, disturbance, physics_steps, dist_counter, dist_offset)
         assert self.lib.shadow_hp1_physics_step(C.byref(self.cfg), C.byref(self._buf)) == 0
 
     def position_task_step(self, actions, disturbance=None, physics_steps=None):

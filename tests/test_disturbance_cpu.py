@@ -63,3 +63,45 @@ def test_env_manager_uses_the_device_draw():
         s1 = torch.get_rng_state().clone()
         env2.step(actions=torch.zeros(200, 4))
         assert proxy.calls["agx_disturbance_draw"] == n0 and not torch.equal(torch.get_rng_state(), s1)  # torch mode: the reference's draws
+
+
+def test_in_kernel_draw_equals_explicit_disturbance_tensor():
+    """CPU twin of test_graph_step_gpu.py::test_in_kernel_disturbance_equals_separate_draw: the physics sub-step text of
+    hp1_step_kernel with AgxHp1Buffers.dist_counter set (draw inside the step: counter word + offset + sub-step) against the same
+    text fed the ORACLE's draw as an explicit [N,6] tensor -- single steps and three fused sub-steps in one call."""
+    from aerial_gym_simulator_b200.hp1 import build_config
+    from tests import _hp1_common as H
+    from tests._shadow_hp1 import ShadowHp1Engine
+
+    spec = H.spec_for("octa_velocity")
+    spec.enable_disturbance, spec.prob_apply_disturbance, spec.max_disturbance = True, 0.1, [4.75, 4.75, 4.75, 0.03, 0.03, 0.03]
+    n, off = 513, 1000
+    root, actions, params = H.random_inputs(spec, n, seed=21)
+    e1, e2 = (ShadowHp1Engine(spec, n, seed=9, env_id_offset=off) for _ in range(2))
+    for e in (e1, e2):
+        H.load_engine_state(e, root, params)
+    cfg = e1.cfg
+    assert cfg.dist_prob == np.float32(0.1) and cfg.dist_seed == build_config(spec, n, seed=9).dist_seed
+    ctr = torch.tensor([0], dtype=torch.int32)
+    hits = 0
+    for step in range(6):
+        d = D.draw(n, off, float(cfg.dist_prob), list(cfg.dist_max), int(cfg.dist_seed), step)
+        hits += int((d != 0).any(axis=1).sum())
+        e1.physics_step(actions, disturbance=torch.from_numpy(d), physics_steps=1)
+        e2.physics_step(actions, physics_steps=1, dist_counter=ctr, dist_offset=step)
+        assert torch.equal(e1.root_state, e2.root_state), f"step {step}"
+    assert hits > 100
+    for step in (6, 7, 8):
+        e1.physics_step(actions, disturbance=torch.from_numpy(D.draw(n, off, float(cfg.dist_prob), list(cfg.dist_max), int(cfg.dist_seed), step)),
+                        physics_steps=1)
+    ctr.fill_(6)
+    e2.physics_step(actions, physics_steps=3, dist_counter=ctr, dist_offset=0)
+    assert torch.equal(e1.root_state, e2.root_state)
+    # no counter, no tensor: no disturbance
+    e3 = ShadowHp1Engine(spec, n, seed=9, env_id_offset=off)
+    H.load_engine_state(e3, root, params)
+    e4 = ShadowHp1Engine(spec, n, seed=9, env_id_offset=off)
+    H.load_engine_state(e4, root, params)
+    e3.physics_step(actions)
+    e4.physics_step(actions, disturbance=torch.zeros(n, 6))
+    assert torch.equal(e3.root_state, e4.root_state)
