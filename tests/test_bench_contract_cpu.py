@@ -62,8 +62,9 @@ def test_final_lines_cover_one_to_eight_gpus():
 
 def test_reference_arm_line_here():
     """`bench.py --impl reference` on this host: same metric / config keys, impl + cpu_baseline + zero-byte e2e, one JSON line on stdout."""
-    if not (os.path.isdir("/root/reference") or os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "aerial_gym"))):
-        pytest.skip("no staged reference")
+    from oracle import reference_arm
+    if not reference_arm.staged():
+        pytest.skip("baseline/_ref is not staged (__graft_entry__.build() stages it where /root/reference exists)")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1",
                         "--envs", "4096"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
