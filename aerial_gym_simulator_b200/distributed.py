@@ -143,6 +143,10 @@ class PipelinedObsGather:
     one-warp GATE kernel that `next_epoch()` puts in front of the step (agx_obs_gather_gate, programmatic stream serialization): it
     lets the step launch in only when the push that last read the slot has finished reading -- the chained step launches stay
     chained (no event, no stream-level wait), and a step that has to wait is not resident while it waits.  Equal shards only.
+    Consumer side: nothing holds a PEER back, so the gathered buffer of epoch e may be overwritten by a peer's push of epoch
+    e + num_buffers.  A consumer that waits every step (the task API: the policy needs the observation) keeps the ranks within one
+    step of each other -- a rank's step e + 1 needs its own wait(e), i.e. every peer's push e -- so num_buffers >= 2 suffices; a
+    free-running producer (bench.py's timed loop) may only read the epoch it finally waits for.
     `loopback_world` (tests, one GPU): emulate a world of that size inside one process -- every "peer" buffer is a local
     buffer, rank 0 is this process; the protocol (ring, flags, counters) runs exactly as on several GPUs."""
 
