@@ -24,6 +24,10 @@ that tile's previous step -- the dependent-chain figure, what a policy-free roll
 Step launches are chained per 32-env tile, not per grid (hp1.cu "chained steps"), so in the rotating
 loop the tail of one replica's step overlaps the next replica's step.
 
+Sub-lines of the same JSON line at N = 1: `hp2_depth` (north_star's 64x48 depth target), `config3_*` / `config4_*` / `config5_env_sweep`
+(BASELINE configs[2..4] at full size) and `navigation_task_e2e`.  They are single-GPU workloads: at N > 1 they are skipped unless
+--multi-gpu-sublines is given (the N > 1 line is the headline workload with its all-gather, and the sharded-task e2e).
+
 Reference arm (`--impl reference`): the reference's Isaac Gym sim_device=cpu pipeline cannot run
 here or on the GPU box (isaacgym is a closed binary, not installed).  What CAN run is the reference's
 own torch control stack: `__graft_entry__.build()` installs the unmodified reference into the
@@ -921,7 +925,12 @@ def main():
     ap.add_argument("--cfg4-envs", type=int, default=16384)
     ap.add_argument("--cfg4-controller", default="rov_fully_actuated_control", help="7-D pose command, FullyActuatedController")
     ap.add_argument("--nav-envs", type=int, default=1024)
+    ap.add_argument("--multi-gpu-sublines", action="store_true",
+                    help="N > 1: also run the single-GPU sub-lines (hp2_depth, configs[2..4], navigation_task) on every rank; by default they are "
+                         "measured at N = 1 only -- the N > 1 line is the headline workload with its all-gather and the sharded-task e2e")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.multi_gpu_sublines:
+        args.no_hp2 = args.no_configs = True
     # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner, the reference's logger)
     # goes to stderr -- file descriptor 1 is pointed at stderr for the run and the line is written to the real stdout at the end
     sys.stdout.flush()
